@@ -1,0 +1,204 @@
+/*
+ * x2k.h — C ABI of the B200-native X²-VLM hot path (libx2k.so).
+ *
+ * The reference (zengyan-97/X2-VLM) has no FFI layer: its hot path is the Python
+ * nn.Module surface of models/beit2.py and models/xbert.py executing ATen ops.
+ * Each entry point below replaces one ATen op *sequence* of the reference; the
+ * file:line it replaces is cited on every function.  Conventions:
+ *   - every function returns int: 0 = ok, <0 = error (text via x2k_last_error());
+ *   - no C++ exceptions cross the boundary, no torch types in signatures;
+ *   - all device buffers are owned by the caller (raw pointers + explicit sizes);
+ *   - every launch takes an explicit cudaStream_t (passed as void*);
+ *   - functions are re-entrant and hold no mutable global state (the only cached
+ *     values are immutable device properties and driver entry points).
+ * bf16 tensors are passed as `const void*` / `void*` (2 bytes per element).
+ */
+#ifndef X2K_H_
+#define X2K_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X2K_VERSION 100 /* 0.1.0 */
+
+#define X2K_OK 0
+#define X2K_ERR_ARG (-1)
+#define X2K_ERR_CUDA (-2)
+#define X2K_ERR_UNSUPPORTED (-3)
+
+/* Library version (X2K_VERSION of the build). */
+int x2k_version(void);
+/* Thread-local text of the last error on this thread ("" if none). */
+const char* x2k_last_error(void);
+/* Number of kernels launched by this library in this process (monotonic counter, for
+ * bench.py's `gpu_launches`). */
+int64_t x2k_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused GEMM on tcgen05 tensor cores:  C[M,N] = epilogue( A[M,K] · B[N,K]^T )
+ *
+ * A and B are bf16.  "K-major" (x_mn_major = 0) means the matrix is stored row-major with the
+ * contraction dimension contiguous: A as [M,K] (ld = lda), B as [N,K] (ld = ldb) — the
+ * F.linear(x, W) layout.  "MN-major" (x_mn_major = 1) means the matrix is stored transposed:
+ * A as [K,M] row-major (M contiguous, ld = lda), B as [K,N] row-major (N contiguous).  This
+ * covers forward (x·Wᵀ), dgrad (dy·W) and wgrad (dyᵀ·x) of every Linear on the hot path
+ * without materialising a transpose.
+ *
+ * Epilogue, applied per element (m,n) in this order (each step optional):
+ *   v  = acc
+ *   v += bias[n]
+ *   if preact_out:  preact_out[m,n] = bf16(v)            (saved for GELU backward)
+ *   if act == X2K_ACT_GELU:       v = gelu_erf(v)
+ *   if act == X2K_ACT_GELU_BWD:   v = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation)
+ *   if dropout_p > 0:  v = keep(m,n) ? v/(1-p) : 0        (Philox4x32-10 keyed by seed,
+ *                                                          counter = offset + (m*N+n)/4)
+ *   if gamma:     v *= gamma[n]                           (BEiT LayerScale)
+ *   if row_scale: v *= row_scale[m / rows_per_scale]      (per-sample DropPath keep/(1-p))
+ *   if residual:  v += residual[m,n]                      (fp32)
+ *   if accumulate (fp32 output only): v += out_f32[m,n]
+ *   store to out_bf16 and/or out_f32.
+ *
+ * Replaces: F.linear / nn.Linear + bias + GELU + LayerScale + DropPath + residual of
+ *   models/beit2.py:61-68,127-133,160-161,206-207 and the dense(+dropout+residual) /
+ *   dense+GELU of models/xbert.py:339-362,427-431,496-499,511-515 (and their autograd
+ *   backward: dgrad, wgrad).
+ * ------------------------------------------------------------------------------------------ */
+#define X2K_ACT_NONE 0
+#define X2K_ACT_GELU 1
+#define X2K_ACT_GELU_BWD 2
+
+typedef struct X2kGemmArgs {
+  const void* A; /* bf16 */
+  const void* B; /* bf16 */
+  int32_t M, N, K;
+  int64_t lda, ldb; /* leading dimensions in elements (multiples of 8) */
+  int32_t a_mn_major, b_mn_major;
+  /* epilogue */
+  const float* bias;       /* [N] or NULL */
+  int32_t act;             /* X2K_ACT_* */
+  const void* aux;         /* bf16 [M, ld_aux], for X2K_ACT_GELU_BWD */
+  int64_t ld_aux;
+  void* preact_out;        /* bf16 [M, ld_preact] or NULL */
+  int64_t ld_preact;
+  float dropout_p;         /* 0 = off */
+  uint64_t dropout_seed, dropout_offset;
+  const float* gamma;      /* [N] or NULL */
+  const float* row_scale;  /* [ceil(M / rows_per_scale)] or NULL */
+  int32_t rows_per_scale;
+  const float* residual;   /* fp32 [M, ld_res] or NULL */
+  int64_t ld_res;
+  int32_t accumulate;      /* out_f32 += result */
+  void* out_bf16;          /* bf16 [M, ld_out_bf16] or NULL */
+  int64_t ld_out_bf16;
+  float* out_f32;          /* fp32 [M, ld_out_f32] or NULL */
+  int64_t ld_out_f32;
+  int32_t tile_n;          /* 0 = auto, else 128 or 256 */
+  int32_t max_ctas;        /* 0 = all SMs */
+} X2kGemmArgs;
+
+int x2k_gemm(const X2kGemmArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound): LayerNorm forward / backward.
+ *
+ * x2k_layernorm_fwd: y = (x - mean) * rstd * w + b over the last dim D of x[M,D] (fp32 in),
+ *   writes any of y_bf16 / y_f32, and mean/rstd [M] for backward.
+ *   Replaces nn.LayerNorm at models/beit2.py:193,201,207,411 (eps 1e-6) and
+ *   models/xbert.py:212,430,514 (eps 1e-12).
+ * x2k_layernorm_bwd: dx = LN'(dy) (+ dx_residual if given); dw/db are ACCUMULATED (+=) into
+ *   fp32 [D] buffers.  dy may be bf16 (dy_bf16) or fp32 (dy_f32) — exactly one non-NULL.
+ * ------------------------------------------------------------------------------------------ */
+int x2k_layernorm_fwd(const float* x, const float* w, const float* b, int32_t M, int32_t D, float eps,
+                      void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* w,
+                      const float* mean, const float* rstd, const float* dx_residual, int32_t M,
+                      int32_t D, float* dx, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * x2k_scale_cast_colsum: backward of the "dropout / LayerScale / DropPath + residual" epilogue.
+ *   g[m,n]   = bf16( dx[m,n] * keepscale(m,n) * gamma[n] * row_scale[m / rows_per_scale] )
+ *   dbias[n]  += sum_m g[m,n]                       (if dbias)
+ *   dgamma[n] += sum_m dx[m,n] * row_scale[..] * y[m,n]   (if dgamma; y = saved bf16 branch output)
+ * keepscale regenerates the Philox mask of x2k_gemm's dropout (same seed/offset, N = ld of the
+ * forward GEMM's logical N).
+ * Replaces autograd of models/beit2.py:206-207 and models/xbert.py:428-431,512-515.
+ * ------------------------------------------------------------------------------------------ */
+int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, int32_t N, const float* gamma,
+                          const float* row_scale, int32_t rows_per_scale, float dropout_p,
+                          uint64_t dropout_seed, uint64_t dropout_offset, const void* y_bf16,
+                          int64_t ld_y, void* g_bf16, int64_t ld_g, float* dbias, float* dgamma,
+                          void* stream);
+
+/* dcol[n] += sum_m x[m,n] for a bf16 matrix (bias gradients of Linear layers). */
+int x2k_colsum_bf16(const void* x_bf16, int64_t ld, int32_t M, int32_t N, float* dcol, void* stream);
+
+/* dst_bf16[i] = bf16(src_f32[i]), i < n (weight shadow copies, activation casts). */
+int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention on tcgen05:  O = softmax(scale·Q·Kᵀ + bias[h] + mask[b]) · V   per (batch b, head h).
+ *
+ * Q rows of sequence b live at q + (b*Lq + i)*ld_q + h*64 (bf16, head_dim 64 only); K/V rows of
+ * sequence b at k + (kv_index ? kv_index[b] : b)*Lk*ld_k + j*ld_k + h*64 — i.e. the kernels read
+ * the packed QKV projection output in place ([B·L, 3D] for BEiT/BERT self-attention, separate
+ * Q and KV buffers for cross-attention) and several query sequences may share one K/V sequence
+ * (the image K/V cache across the ITM/MLM passes, models/xvlm.py:859-899).
+ * bias: fp32 [H, Lq, Lk] or NULL (BEiT relative position bias, already gathered).
+ * mask: fp32 additive, [B, Lk] (mask_q_stride = 0) or [B, Lq, Lk] (mask_q_stride = Lk), or NULL.
+ * dropout on probabilities (BERT attention_probs_dropout) via Philox, as in x2k_gemm.
+ * Outputs: O bf16 at o + (b*Lq+i)*ld_o + h*64, lse fp32 [B,H,Lq].  Lk <= 256.
+ * Replaces models/beit2.py:135-159 and models/xbert.py:364-410.
+ *
+ * x2k_attn_bwd: given dO, recomputes P from lse and produces dQ, dK, dV (bf16, same addressing
+ * as q/k/v with their own pointers/ld; dK/dV are per *query batch* b — the caller reduces over
+ * shared K/V) and, if dbias != NULL, accumulates dbias[h,i,j] += sum_b dS (fp32 atomics).
+ * delta: fp32 workspace [B,H,Lq].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct X2kAttnArgs {
+  const void *q, *k, *v; /* bf16 */
+  int64_t ld_q, ld_k, ld_v;
+  int32_t B, H, Lq, Lk;
+  const int32_t* kv_index; /* [B] or NULL */
+  float scale;
+  const float* bias;       /* [H,Lq,Lk] or NULL */
+  const float* mask;       /* see above, or NULL */
+  int64_t mask_b_stride, mask_q_stride;
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
+  void* o;                 /* bf16 */
+  int64_t ld_o;
+  float* lse;              /* [B,H,Lq] */
+  /* backward only */
+  const void* d_o;         /* bf16, ld_o addressing */
+  void *dq, *dk, *dv;      /* bf16 */
+  int64_t ld_dq, ld_dk, ld_dv;
+  float* dbias;            /* [H,Lq,Lk] fp32 accumulate, or NULL */
+  float* delta;            /* [B,H,Lq] workspace */
+} X2kAttnArgs;
+
+int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);
+int x2k_attn_bwd(const X2kAttnArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Flat-buffer optimizer step (replaces optim.py:26-104 AdamW +
+ * accelerators/apex_ddp_accelerator.py:99-102 clip_grad_norm_):
+ * x2k_sumsq: out[0] += sum g[i]^2 (fp32, for the global grad norm).
+ * x2k_adamw_flat: decoupled-weight-decay Adam over a flat fp32 parameter buffer; per-element
+ *   hyper-parameters come from a segment table (seg_end[s] exclusive end offsets, lr[s], wd[s]);
+ *   grads are pre-scaled by *grad_scale_dev (clip coefficient computed on device);
+ *   also writes the bf16 shadow copy used by the GEMMs.  The step count (bias correction) is
+ *   `step`, or *step_dev when step_dev != NULL (so a captured CUDA graph can advance it).
+ * ------------------------------------------------------------------------------------------ */
+int x2k_sumsq(const float* g, int64_t n, float* out, void* stream);
+int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                   const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int32_t n_seg,
+                   float beta1, float beta2, float eps, int32_t step, const int32_t* step_dev,
+                   const float* grad_scale_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X2K_H_ */

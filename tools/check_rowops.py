@@ -1,0 +1,92 @@
+"""GPU check of the row kernels against torch (run under gpurun)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from x2vlm_b200 import _capi as C
+L = C.lib(); dev = torch.device("cuda:0"); torch.manual_seed(0)
+S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+ok_all = True
+def rep(name, err, tol):
+    global ok_all
+    ok = err <= tol; ok_all &= ok
+    print("ROW %-34s err %.4g tol %.3g %s" % (name, err, tol, "OK" if ok else "FAIL"))
+
+for (M, D, eps) in [(12608, 768, 1e-6), (2560, 768, 1e-12), (333, 1024, 1e-6), (77, 256, 1e-5)]:
+    x = torch.randn(M, D, device=dev) * 2 + 0.5; w = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
+    yb = torch.empty(M, D, device=dev, dtype=torch.bfloat16); yf = torch.empty(M, D, device=dev)
+    mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
+    C.check(L.x2k_layernorm_fwd(P(x), P(w), P(b), M, D, eps, P(yb), P(yf), P(mean), P(rstd), S()), "ln_fwd")
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, eps)
+    rep("ln_fwd f32 M=%d D=%d" % (M, D), (yf - ref).abs().max().item(), 1e-4)
+    rep("ln_fwd bf16", (yb.float() - ref).abs().max().item(), 0.05)
+    dy = torch.randn(M, D, device=dev); res = torch.randn(M, D, device=dev)
+    ref.backward(dy)
+    dx = torch.empty(M, D, device=dev); dw = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
+    C.check(L.x2k_layernorm_bwd(None, P(dy), P(x), P(w), P(mean), P(rstd), P(res), M, D, P(dx), P(dw), P(db), S()), "ln_bwd")
+    rep("ln_bwd dx", (dx - (xr.grad + res)).abs().max().item(), 1e-3)
+    rep("ln_bwd dw", ((dw - wr.grad).abs().max() / wr.grad.abs().max()).item(), 1e-4)
+    rep("ln_bwd db", ((db - br.grad).abs().max() / br.grad.abs().max()).item(), 1e-4)
+    dyb = dy.bfloat16()
+    dx2 = torch.empty(M, D, device=dev); dw.zero_(); db.zero_()
+    C.check(L.x2k_layernorm_bwd(P(dyb), None, P(x), P(w), P(mean), P(rstd), None, M, D, P(dx2), P(dw), P(db), S()), "ln_bwd")
+    xr.grad = None; torch.nn.functional.layer_norm(xr, (D,), w, b, eps).backward(dyb.float())
+    rep("ln_bwd(bf16 dy) dx", (dx2 - xr.grad).abs().max().item(), 1e-3)
+
+# scale_cast_colsum
+M, N = 12608, 768
+dx = torch.randn(M, N, device=dev); gamma = torch.randn(N, device=dev); rs = torch.rand(64, device=dev) + 0.5
+y = torch.randn(M, N, device=dev).bfloat16(); g = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+dbias = torch.zeros(N, device=dev); dgamma = torch.zeros(N, device=dev)
+C.check(L.x2k_scale_cast_colsum(P(dx), N, M, N, P(gamma), P(rs), 197, 0.0, 0, 0, P(y), N, P(g), N, P(dbias), P(dgamma), S()), "scc")
+rsx = rs.repeat_interleave(197)[:, None]
+gref = dx * rsx * gamma
+rep("scc g", (g.float() - gref).abs().max().item(), 0.05)
+rep("scc dbias", ((dbias - gref.sum(0)).abs().max() / gref.sum(0).abs().max()).item(), 1e-3)
+dgref = (dx * rsx * y.float()).sum(0)
+rep("scc dgamma", ((dgamma - dgref).abs().max() / dgref.abs().max()).item(), 1e-3)
+# dropout consistency between gemm epilogue and scc: run gemm with identity-ish to get mask
+A = torch.eye(256, device=dev).bfloat16(); Bm = torch.ones(256, 256, device=dev).bfloat16()
+o = torch.empty(256, 256, device=dev)
+a = C.X2kGemmArgs(); a.A = A.data_ptr(); a.B = Bm.data_ptr(); a.M = a.N = a.K = 256; a.lda = a.ldb = 256
+a.dropout_p = 0.1; a.dropout_seed = 99; a.dropout_offset = 12345; a.out_f32 = o.data_ptr(); a.ld_out_f32 = 256
+C.check(L.x2k_gemm(ctypes.byref(a), S()), "gemm")
+ones = torch.ones(256, 256, device=dev); g2 = torch.empty(256, 256, device=dev, dtype=torch.bfloat16)
+C.check(L.x2k_scale_cast_colsum(P(ones), 256, 256, 256, None, None, 0, 0.1, 99, 12345, None, 0, P(g2), 256, None, None, S()), "scc")
+rep("dropout mask gemm==scc", (o - g2.float()).abs().max().item(), 0.01)
+print("   keep frac", (o != 0).float().mean().item())
+# colsum
+xb = torch.randn(5120, 2304, device=dev).bfloat16(); dc = torch.zeros(2304, device=dev)
+C.check(L.x2k_colsum_bf16(P(xb), 2304, 5120, 2304, P(dc), S()), "colsum")
+r = xb.float().sum(0); rep("colsum_bf16", ((dc - r).abs().max() / r.abs().max()).item(), 1e-4)
+# cast
+src = torch.randn(1000003 + 5, device=dev)[:1000003]
+src = torch.randn(1000008, device=dev); dst = torch.empty(1000008, device=dev, dtype=torch.bfloat16)
+C.check(L.x2k_cast_f32_bf16(P(src), P(dst), 1000003, S()), "cast")
+rep("cast", (dst[:1000003].float() - src[:1000003].bfloat16().float()).abs().max().item(), 0)
+# sumsq
+out = torch.zeros(1, device=dev); C.check(L.x2k_sumsq(P(src), 1000003, P(out), S()), "sumsq")
+rep("sumsq", abs(out.item() - (src[:1000003].double() ** 2).sum().item()) / out.item(), 1e-5)
+# adamw
+n = 100000
+p = torch.randn(n, device=dev); gr = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+pb = torch.empty(n, device=dev, dtype=torch.bfloat16)
+pref = p.clone().requires_grad_(True)
+seg_end = torch.tensor([30000, 70000, n], device=dev, dtype=torch.int64)
+lrs = [1e-3, 2e-3, 5e-4]; wds = [0.01, 0.0, 0.05]
+opt = torch.optim.AdamW([{"params": [pp], "lr": lr, "weight_decay": wd} for pp, lr, wd in zip([], [], [])] or [{"params": [pref]}], lr=1e-3)
+# reference by segments
+prefs = [p[:30000].clone().requires_grad_(True), p[30000:70000].clone().requires_grad_(True), p[70000:].clone().requires_grad_(True)]
+opt = torch.optim.AdamW([{"params": [pp], "lr": lr, "weight_decay": wd} for pp, lr, wd in zip(prefs, lrs, wds)], betas=(0.9, 0.98), eps=1e-8)
+seg_lr = torch.tensor(lrs, device=dev); seg_wd = torch.tensor(wds, device=dev); gs = torch.tensor([0.5], device=dev)
+for step in (1, 2, 3):
+    gr = torch.randn(n, device=dev)
+    for pp, sl in zip(prefs, (slice(0, 30000), slice(30000, 70000), slice(70000, n))):
+        pp.grad = gr[sl].clone() * 0.5
+    opt.step()
+    C.check(L.x2k_adamw_flat(P(p), P(gr), P(m), P(v), P(pb), n, P(seg_end), P(seg_lr), P(seg_wd), 3, 0.9, 0.98, 1e-8, step, None, P(gs), S()), "adamw")
+rep("adamw 3 steps", (p - torch.cat([pp.detach() for pp in prefs])).abs().max().item(), 1e-5)
+rep("adamw bf16 shadow", (pb.float() - p.bfloat16().float()).abs().max().item(), 0)
+torch.cuda.synchronize()
+print("ROWOPS ALL OK" if ok_all else "ROWOPS SOME FAILED")

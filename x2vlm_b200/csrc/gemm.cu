@@ -1,0 +1,448 @@
+// gemm.cu — persistent, warp-specialised tcgen05 GEMM with fused epilogues for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] · B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Pipeline (one CTA per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per
+//               k-block; tcgen05.commit releases smem slots and signals the epilogue
+//   warps 2..9  epilogue: tcgen05.ld the fp32 accumulator (thread == output row), apply the fused
+//               epilogue (bias / GELU / GELU' / dropout / LayerScale / DropPath / residual /
+//               accumulate), vectorised global stores.  Two TMEM accumulator stages let the epilogue
+//               of tile i overlap the MMAs of tile i+1.
+// Operand majors: K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) for A and B,
+// selected through the UMMA instruction/smem descriptors — forward, dgrad and wgrad GEMMs all
+// read the tensors where they lie, no transposes are materialised.
+//
+// Replaces the F.linear(+bias+act+residual) sequences cited in include/x2k.h.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace x2k {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  int M, N, K;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* aux;
+  int64_t ld_aux;
+  __nv_bfloat16* preact_out;
+  int64_t ld_preact;
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
+  const float* gamma;
+  const float* row_scale;
+  int rows_per_scale;
+  const float* residual;
+  int64_t ld_res;
+  int accumulate;
+  __nv_bfloat16* out_bf16;
+  int64_t ld_out_bf16;
+  float* out_f32;
+  int64_t ld_out_f32;
+  // debug overrides for the MN-major smem descriptors (0 = defaults); env X2K_DBG_MN="lbo,sbo,kadv"
+  uint32_t dbg_lbo, dbg_sbo, dbg_kadv;
+};
+
+// Apply the fused epilogue to 32 consecutive columns [n0, n0+32) of row m.
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0, uint32_t (&acc)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  const bool full = (n0 + 32 <= p.N);
+  if (p.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+    }
+  }
+  if (p.preact_out) {
+    __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if (p.act == X2K_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == X2K_ACT_GELU_BWD) {
+    const __nv_bfloat16* src = p.aux + static_cast<int64_t>(m) * p.ld_aux + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + j));
+        v[j] *= gelu_erf_grad(bf16_lo(q.x)); v[j + 1] *= gelu_erf_grad(bf16_hi(q.x));
+        v[j + 2] *= gelu_erf_grad(bf16_lo(q.y)); v[j + 3] *= gelu_erf_grad(bf16_hi(q.y));
+        v[j + 4] *= gelu_erf_grad(bf16_lo(q.z)); v[j + 5] *= gelu_erf_grad(bf16_hi(q.z));
+        v[j + 6] *= gelu_erf_grad(bf16_lo(q.w)); v[j + 7] *= gelu_erf_grad(bf16_hi(q.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] *= gelu_erf_grad(__bfloat162float(src[j]));
+    }
+  }
+  if (p.dropout_p > 0.0f) {
+    const float inv_keep = 1.0f / (1.0f - p.dropout_p);
+    const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
+    // N is a multiple of 4 whenever dropout is used (checked on the host), so base % 4 == 0.
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const uint4 r = philox4x32(p.dropout_seed, p.dropout_offset + ((base + j) >> 2));
+      v[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
+      v[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
+      v[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
+      v[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+    }
+  }
+  if (p.gamma) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] *= __ldg(p.gamma + n0 + j);
+    }
+  }
+  if (p.row_scale) {
+    const float s = __ldg(p.row_scale + m / p.rows_per_scale);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= s;
+  }
+  if (p.residual) {
+    const float* src = p.residual + static_cast<int64_t>(m) * p.ld_res + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(src + j));
+        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += __ldg(src + j);
+    }
+  }
+  if (p.out_f32) {
+    float* dst = p.out_f32 + static_cast<int64_t>(m) * p.ld_out_f32 + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.accumulate) {
+          const float4 c = *reinterpret_cast<const float4*>(dst + j);
+          o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+    }
+  }
+  if (p.out_bf16) {
+    __nv_bfloat16* dst = p.out_bf16 + static_cast<int64_t>(m) * p.ld_out_bf16 + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+template <int BLOCK_N, int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const EpiParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BLOCK_M;
+        const int n0 = (tile % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (A_MN == 0) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc_stage * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t mn_lbo = p.dbg_lbo ? p.dbg_lbo : BLOCK_K * 128;
+            const uint32_t mn_sbo = p.dbg_sbo ? p.dbg_sbo : 1024;
+            const uint32_t mn_kadv = p.dbg_kadv ? p.dbg_kadv : UMMA_K * 128;
+            const uint64_t da = A_MN == 0 ? make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                          : make_smem_desc(sa + k * mn_kadv, mn_lbo, mn_sbo);
+            const uint64_t db = B_MN == 0 ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
+                                          : make_smem_desc(sb + k * mn_kadv, mn_lbo, mn_sbo);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full_bar[acc_stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;            // 0..7
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;           // which half of the BLOCK_N columns
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BLOCK_M;
+      const int n0 = (tile % n_tiles) * BLOCK_N;
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tc_fence_after();
+      const int m = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c, acc);
+        tmem_wait_ld();
+        const int n = n0 + half * COLS_PER_WARP + c;
+        if (m < p.M && n < p.N) epilogue_chunk(p, m, n, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int A_MN, int B_MN>
+int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (A_MN == 0)
+    rc = make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K);
+  else
+    rc = make_tmap_bf16_2d(&ta, a.A, a.K, a.M, a.lda, BLOCK_K, 64);
+  if (rc) return rc;
+  if (B_MN == 0)
+    rc = make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, BLOCK_N, BLOCK_K);
+  else
+    rc = make_tmap_bf16_2d(&tb, a.B, a.K, a.N, a.ldb, BLOCK_K, 64);
+  if (rc) return rc;
+
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;  // idempotent; racing writers set the same value
+  if (!attr_set) {
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  int ctas = sm_count();
+  if (a.max_ctas > 0 && a.max_ctas < ctas) ctas = a.max_ctas;
+  if (m_tiles * n_tiles < ctas) ctas = m_tiles * n_tiles;
+  kern<<<ctas, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_major(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  if (!a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 0, 0>(a, ep, stream);
+  if (!a.a_mn_major && a.b_mn_major) return launch<BLOCK_N, 0, 1>(a, ep, stream);
+  if (a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 1, 0>(a, ep, stream);
+  return launch<BLOCK_N, 1, 1>(a, ep, stream);
+}
+
+}  // namespace
+}  // namespace x2k
+
+extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
+  using namespace x2k;
+  X2K_REQUIRE(args != nullptr, "x2k_gemm: args is NULL");
+  const X2kGemmArgs& a = *args;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(a.A && a.B, "x2k_gemm: A/B is NULL");
+  X2K_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "x2k_gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  X2K_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "x2k_gemm: lda/ldb must be multiples of 8 (got %lld, %lld)",
+              (long long)a.lda, (long long)a.ldb);
+  X2K_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+              "x2k_gemm: A/B must be 16-byte aligned");
+  X2K_REQUIRE(a.out_bf16 || a.out_f32 || a.preact_out, "x2k_gemm: no output");
+  X2K_REQUIRE(!a.accumulate || a.out_f32, "x2k_gemm: accumulate needs out_f32");
+  X2K_REQUIRE(a.act != X2K_ACT_GELU_BWD || a.aux, "x2k_gemm: GELU_BWD needs aux");
+  X2K_REQUIRE(!(a.dropout_p > 0.f) || (a.N % 4 == 0 && a.dropout_p < 1.f), "x2k_gemm: dropout needs N%%4==0, p<1");
+  X2K_REQUIRE(!a.row_scale || a.rows_per_scale > 0, "x2k_gemm: rows_per_scale must be > 0");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  X2K_REQUIRE(al16(a.bias) && al16(a.gamma) && al16(a.residual) && al16(a.out_f32) && al16(a.out_bf16) &&
+                  al16(a.preact_out) && al16(a.aux),
+              "x2k_gemm: epilogue pointers must be 16-byte aligned");
+  X2K_REQUIRE((!a.out_bf16 || a.ld_out_bf16 % 8 == 0) && (!a.out_f32 || a.ld_out_f32 % 4 == 0) &&
+                  (!a.preact_out || a.ld_preact % 8 == 0) && (!a.aux || a.ld_aux % 8 == 0) &&
+                  (!a.residual || a.ld_res % 4 == 0),
+              "x2k_gemm: epilogue leading dimensions must keep 16-byte row alignment");
+
+  EpiParams ep;
+  ep.M = a.M; ep.N = a.N; ep.K = a.K;
+  ep.bias = a.bias; ep.act = a.act;
+  ep.aux = static_cast<const __nv_bfloat16*>(a.aux); ep.ld_aux = a.ld_aux;
+  ep.preact_out = static_cast<__nv_bfloat16*>(a.preact_out); ep.ld_preact = a.ld_preact;
+  ep.dropout_p = a.dropout_p; ep.dropout_seed = a.dropout_seed; ep.dropout_offset = a.dropout_offset;
+  ep.gamma = a.gamma; ep.row_scale = a.row_scale; ep.rows_per_scale = a.rows_per_scale;
+  ep.residual = a.residual; ep.ld_res = a.ld_res; ep.accumulate = a.accumulate;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); ep.ld_out_bf16 = a.ld_out_bf16;
+  ep.out_f32 = a.out_f32; ep.ld_out_f32 = a.ld_out_f32;
+  ep.dbg_lbo = ep.dbg_sbo = ep.dbg_kadv = 0;
+  if (const char* dbg = getenv("X2K_DBG_MN")) sscanf(dbg, "%u,%u,%u", &ep.dbg_lbo, &ep.dbg_sbo, &ep.dbg_kadv);
+
+  int tile_n = a.tile_n;
+  if (tile_n == 0) {
+    // Pick the tile width that minimises (waves x tile cost) over the SMs.
+    const int sms = sm_count();
+    const long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+    const long t256 = m_tiles * ((a.N + 255) / 256), t128 = m_tiles * ((a.N + 127) / 128);
+    const long cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = ((t128 + sms - 1) / sms) * 1;
+    tile_n = (a.N <= 128 || cost128 < cost256) ? 128 : 256;
+  }
+  X2K_REQUIRE(tile_n == 128 || tile_n == 256, "x2k_gemm: tile_n must be 0, 128 or 256");
+  return tile_n == 256 ? dispatch_major<256>(a, ep, stream) : dispatch_major<128>(a, ep, stream);
+}

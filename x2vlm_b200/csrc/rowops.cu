@@ -1,0 +1,429 @@
+// rowops.cu — HBM-bound kernels of the hot path: LayerNorm fwd/bwd, epilogue backward
+// (scale/cast/column-sum), bias-gradient column sums, casts, flat AdamW.  All are streaming
+// kernels: 16-byte vectorised, coalesced along the contiguous dimension, grids sized as multiples
+// of the SM count; reductions are warp-shuffle -> smem -> few atomics.
+#include "common.cuh"
+
+namespace x2k {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row cached in registers (D = 128 * VEC, VEC <= 8).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, int M, int D, float eps,
+                                                            __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    v[j] = xr[lane + 32 * j];
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+    q += a * a + c * c + d * d + e * e;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c4 = lane + 32 * j;
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c4);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + c4);
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * ww.x + bb.x;
+    o.y = (v[j].y - mean) * rstd * ww.y + bb.y;
+    o.z = (v[j].z - mean) * rstd * ww.z + bb.z;
+    o.w = (v[j].w - mean) * rstd * ww.w + bb.w;
+    if (y_f32) reinterpret_cast<float4*>(y_f32 + static_cast<int64_t>(row) * D)[c4] = o;
+    if (y_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(y_bf16 + static_cast<int64_t>(row) * D)[c4] = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward: warps stride over rows, keep per-column dw/db partials in registers,
+// reduce across the block's warps in smem, then one atomicAdd per column per block.
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16,
+                                                            const float* __restrict__ dy_f32, const float* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ dx_residual, int M, int D,
+                                                            float* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db) {
+  extern __shared__ float red[];  // [warps][2*D]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int gw = blockIdx.x * warps_per_block + wib;
+  const int total_warps = gridDim.x * warps_per_block;
+  float4 ww[VEC], adw[VEC], adb[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    ww[j] = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * j);
+    adw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = gw; row < M; row += total_warps) {
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
+    float4 xh[VEC], g[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c4 = lane + 32 * j;
+      const float4 xv = xr[c4];
+      float4 d;
+      if (dy_bf16) {
+        const uint2 pk = reinterpret_cast<const uint2*>(dy_bf16 + static_cast<int64_t>(row) * D)[c4];
+        d = make_float4(bf16_lo(pk.x), bf16_hi(pk.x), bf16_lo(pk.y), bf16_hi(pk.y));
+      } else {
+        d = reinterpret_cast<const float4*>(dy_f32 + static_cast<int64_t>(row) * D)[c4];
+      }
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      adb[j].x += d.x; adb[j].y += d.y; adb[j].z += d.z; adb[j].w += d.w;
+      adw[j].x += d.x * xh[j].x; adw[j].y += d.y * xh[j].y; adw[j].z += d.z * xh[j].z; adw[j].w += d.w * xh[j].w;
+      g[j] = make_float4(d.x * ww[j].x, d.y * ww[j].y, d.z * ww[j].z, d.w * ww[j].w);
+      s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+      s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+    }
+    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c4 = lane + 32 * j;
+      float4 o;
+      o.x = rs * (g[j].x - c1 - xh[j].x * c2);
+      o.y = rs * (g[j].y - c1 - xh[j].y * c2);
+      o.z = rs * (g[j].z - c1 - xh[j].z * c2);
+      o.w = rs * (g[j].w - c1 - xh[j].w * c2);
+      if (dx_residual) {
+        const float4 r = reinterpret_cast<const float4*>(dx_residual + static_cast<int64_t>(row) * D)[c4];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dx + static_cast<int64_t>(row) * D)[c4] = o;
+    }
+  }
+  // block reduction of dw/db partials
+  float4* red4 = reinterpret_cast<float4*>(red);
+  const int D4 = D / 4;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    red4[wib * 2 * D4 + lane + 32 * j] = adw[j];
+    red4[wib * 2 * D4 + D4 + lane + 32 * j] = adb[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float s = 0.f;
+    for (int ww_ = 0; ww_ < warps_per_block; ++ww_) s += red[ww_ * 2 * D + c];
+    if (c < D) atomicAdd(dw + c, s);
+    else atomicAdd(db + (c - D), s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale / cast / column sums: thread owns 4 columns, loops over a chunk of rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
+    const float* __restrict__ dx, int64_t ld_dx, int M, int N, const float* __restrict__ gamma,
+    const float* __restrict__ row_scale, int rows_per_scale, float dropout_p, uint64_t seed, uint64_t offset,
+    const __nv_bfloat16* __restrict__ y, int64_t ld_y, __nv_bfloat16* __restrict__ g, int64_t ld_g,
+    float* __restrict__ dbias, float* __restrict__ dgamma, int rows_per_block) {
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;  // column group
+  const int n = c4 * 4;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (gamma) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
+  const float inv_keep = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int m = r0; m < r1; ++m) {
+    float4 d = *reinterpret_cast<const float4*>(dx + static_cast<int64_t>(m) * ld_dx + n);
+    if (row_scale) {
+      const float s = __ldg(row_scale + m / rows_per_scale);
+      d.x *= s; d.y *= s; d.z *= s; d.w *= s;
+    }
+    if (dgamma) {
+      const uint2 pk = *reinterpret_cast<const uint2*>(y + static_cast<int64_t>(m) * ld_y + n);
+      sg.x += d.x * bf16_lo(pk.x); sg.y += d.y * bf16_hi(pk.x); sg.z += d.z * bf16_lo(pk.y); sg.w += d.w * bf16_hi(pk.y);
+    }
+    d.x *= gm.x; d.y *= gm.y; d.z *= gm.z; d.w *= gm.w;
+    if (dropout_p > 0.f) {
+      const uint64_t idx = static_cast<uint64_t>(m) * static_cast<uint64_t>(N) + static_cast<uint64_t>(n);
+      const uint4 r = philox4x32(seed, offset + (idx >> 2));
+      d.x *= dropout_keep(r.x, dropout_p, inv_keep);
+      d.y *= dropout_keep(r.y, dropout_p, inv_keep);
+      d.z *= dropout_keep(r.z, dropout_p, inv_keep);
+      d.w *= dropout_keep(r.w, dropout_p, inv_keep);
+    }
+    sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
+    if (g) {
+      uint2 pk;
+      pk.x = pack_bf16x2(d.x, d.y);
+      pk.y = pack_bf16x2(d.z, d.w);
+      *reinterpret_cast<uint2*>(g + static_cast<int64_t>(m) * ld_g + n) = pk;
+    }
+  }
+  if (dbias) {
+    atomicAdd(dbias + n, sb.x); atomicAdd(dbias + n + 1, sb.y); atomicAdd(dbias + n + 2, sb.z); atomicAdd(dbias + n + 3, sb.w);
+  }
+  if (dgamma) {
+    atomicAdd(dgamma + n, sg.x); atomicAdd(dgamma + n + 1, sg.y); atomicAdd(dgamma + n + 2, sg.z); atomicAdd(dgamma + n + 3, sg.w);
+  }
+}
+
+// thread owns 8 bf16 columns (16 B)
+__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
+                                                          float* __restrict__ dcol, int rows_per_block) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int m = r0; m < r1; ++m) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + n);
+    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dcol + n + j, s[j]);
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int64_t n) {
+  const int64_t n8 = n / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 q;
+    q.x = pack_bf16x2(a.x, a.y); q.y = pack_bf16x2(a.z, a.w); q.z = pack_bf16x2(b.x, b.y); q.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = q;
+  }
+  // tail
+  for (int64_t i = n8 * 8 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const int64_t n4 = n / 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int64_t i = n4 * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) s += g[i] * g[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+// Flat AdamW (decoupled weight decay, torch.optim.AdamW semantics):
+//   p *= 1 - lr*wd;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;
+//   p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         __nv_bfloat16* __restrict__ p_bf16, int64_t n,
+                                                         const int64_t* __restrict__ seg_end,
+                                                         const float* __restrict__ seg_lr,
+                                                         const float* __restrict__ seg_wd, int n_seg, float beta1,
+                                                         float beta2, float eps, int step,
+                                                         const int32_t* __restrict__ step_dev,
+                                                         const float* __restrict__ grad_scale_dev) {
+  const float gs = grad_scale_dev ? *grad_scale_dev : 1.0f;
+  const float stepf = static_cast<float>(step_dev ? *step_dev : step);
+  const float bc1 = 1.0f - powf(beta1, stepf);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, stepf));
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int lo = 0, hi = n_seg - 1;  // first segment with seg_end > i
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(seg_end + mid) > i) hi = mid; else lo = mid + 1;
+    }
+    const float lr = __ldg(seg_lr + lo), wd = __ldg(seg_wd + lo);
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+template <typename F>
+int dispatch_vec(int D, F&& f) {
+  switch (D / 128) {
+    case 1: return f(std::integral_constant<int, 1>{});
+    case 2: return f(std::integral_constant<int, 2>{});
+    case 3: return f(std::integral_constant<int, 3>{});
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 5: return f(std::integral_constant<int, 5>{});
+    case 6: return f(std::integral_constant<int, 6>{});
+    case 7: return f(std::integral_constant<int, 7>{});
+    case 8: return f(std::integral_constant<int, 8>{});
+  }
+  return X2K_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+}  // namespace x2k
+
+using namespace x2k;
+
+extern "C" int x2k_layernorm_fwd(const float* x, const float* w, const float* b, int32_t M, int32_t D, float eps,
+                                 void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(x && w && b && (y_bf16 || y_f32), "x2k_layernorm_fwd: NULL argument");
+  X2K_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "x2k_layernorm_fwd: D=%d must be a multiple of 128, <= 1024", D);
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  return dispatch_vec(D, [&](auto vec) {
+    layernorm_fwd_kernel<decltype(vec)::value><<<grid, 256, 0, stream>>>(
+        x, w, b, M, D, eps, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd);
+    X2K_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return X2K_OK;
+  });
+}
+
+extern "C" int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* w,
+                                 const float* mean, const float* rstd, const float* dx_residual, int32_t M, int32_t D,
+                                 float* dx, float* dw, float* db, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "x2k_layernorm_bwd: exactly one of dy_bf16/dy_f32");
+  X2K_REQUIRE(x && w && mean && rstd && dx && dw && db, "x2k_layernorm_bwd: NULL argument");
+  X2K_REQUIRE(M > 0 && D % 128 == 0 && D <= 1024, "x2k_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
+  const int warps = 8;
+  int grid = sm_count() * 2;
+  if (grid * warps > M) grid = (M + warps - 1) / warps;
+  const size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
+  return dispatch_vec(D, [&](auto vec) {
+    auto kern = layernorm_bwd_kernel<decltype(vec)::value>;
+    if (smem > 48 * 1024) X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, w, mean, rstd,
+                                             dx_residual, M, D, dx, dw, db);
+    X2K_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return X2K_OK;
+  });
+}
+
+extern "C" int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, int32_t N, const float* gamma,
+                                     const float* row_scale, int32_t rows_per_scale, float dropout_p,
+                                     uint64_t dropout_seed, uint64_t dropout_offset, const void* y_bf16, int64_t ld_y,
+                                     void* g_bf16, int64_t ld_g, float* dbias, float* dgamma, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(dx && M > 0 && N > 0 && N % 4 == 0 && ld_dx % 4 == 0, "x2k_scale_cast_colsum: bad dx/shape");
+  X2K_REQUIRE(!dgamma || (y_bf16 && ld_y % 4 == 0), "x2k_scale_cast_colsum: dgamma needs y");
+  X2K_REQUIRE(!g_bf16 || ld_g % 4 == 0, "x2k_scale_cast_colsum: ld_g must be a multiple of 4");
+  X2K_REQUIRE(!row_scale || rows_per_scale > 0, "x2k_scale_cast_colsum: rows_per_scale");
+  X2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "x2k_scale_cast_colsum: dropout_p");
+  const int col_blocks = (N / 4 + 127) / 128;
+  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  if (rows_per_block < 8) rows_per_block = 8;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  scale_cast_colsum_kernel<<<dim3(col_blocks, row_blocks), 128, 0, stream>>>(
+      dx, ld_dx, M, N, gamma, row_scale, rows_per_scale, dropout_p, dropout_seed, dropout_offset,
+      static_cast<const __nv_bfloat16*>(y_bf16), ld_y, static_cast<__nv_bfloat16*>(g_bf16), ld_g, dbias, dgamma,
+      rows_per_block);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_colsum_bf16(const void* x_bf16, int64_t ld, int32_t M, int32_t N, float* dcol, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(x_bf16 && dcol && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "x2k_colsum_bf16: bad arguments");
+  const int col_blocks = (N / 8 + 127) / 128;
+  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  if (rows_per_block < 8) rows_per_block = 8;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), ld, M,
+                                                                       N, dcol, rows_per_block);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(src && dst_bf16 && n > 0, "x2k_cast_f32_bf16: bad arguments");
+  X2K_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0,
+              "x2k_cast_f32_bf16: pointers must be 16-byte aligned");
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), n);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_sumsq(const float* g, int64_t n, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(g && out && n > 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "x2k_sumsq: bad arguments");
+  int64_t blocks = (n / 4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(g, n, out);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                              const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int32_t n_seg,
+                              float beta1, float beta2, float eps, int32_t step, const int32_t* step_dev,
+                              const float* grad_scale_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && n_seg > 0 && (step > 0 || step_dev),
+              "x2k_adamw_flat: bad arguments");
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n,
+                                                                   seg_end, seg_lr, seg_wd, n_seg, beta1, beta2, eps,
+                                                                   step, step_dev, grad_scale_dev);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}

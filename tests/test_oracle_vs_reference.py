@@ -1,0 +1,114 @@
+"""Pin oracle/restate.py against the UNMODIFIED reference (run through oracle/ref_shim.py).
+
+The reference ships no tests/golden vectors, so its own execution is the pin.
+These tests only run where /root/reference exists (build container)."""
+import pytest
+import torch
+
+from oracle import ref_shim, restate
+from x2vlm_b200 import synth
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    m = ref_shim.build_reference_xvlm(seed=0)
+    # exercise paths whose parameters initialise to constants (rel-pos table = 0, gamma = 0.1)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "relative_position_bias_table" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif "gamma_" in n:
+                p.copy_(0.1 + torch.randn(p.shape, generator=g) * 0.05)
+            elif n.endswith(".bias") or "q_bias" in n or "v_bias" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    m.eval()
+    return m
+
+
+def _sd(m):
+    return {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def test_relative_position_index(ref):
+    idx = restate.relative_position_index((14, 14))
+    assert torch.equal(idx, ref.vision_encoder.blocks[0].attn.relative_position_index)
+
+
+def test_beit_block_and_vision(ref):
+    sd = _sd(ref)
+    b = synth.image_text_batch(2, 30, seed=1)
+    with torch.no_grad():
+        x = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(3))
+        y_ref, p_ref = ref.vision_encoder.blocks[3](x)
+        y, p = restate.beit_block(x, sd, "vision_encoder.blocks.3.", 12)
+        assert torch.allclose(y, y_ref, atol=1e-5, rtol=1e-5)
+        assert torch.allclose(p, p_ref, atol=1e-6)
+        e_ref = ref.vision_encoder(b["image"])
+        e = restate.vision_forward(b["image"], sd, "vision_encoder.", 12, 12)
+        assert torch.allclose(e, e_ref, atol=2e-4, rtol=1e-4)
+
+
+def test_vision_region_mode(ref):
+    sd = _sd(ref)
+    rb = synth.region_batch(3, 8, 30, seed=2)
+    with torch.no_grad():
+        r_ref, f_ref = ref.vision_encoder(rb["image"], idx_to_group_img=rb["idx_to_group_img"], image_atts=rb["image_atts"])
+        r, f = restate.vision_forward(rb["image"], sd, "vision_encoder.", 12, 12, rb["idx_to_group_img"], rb["image_atts"])
+    assert torch.allclose(r, r_ref, atol=2e-4, rtol=1e-4) and torch.allclose(f, f_ref, atol=2e-4, rtol=1e-4)
+
+
+def test_text_and_fusion(ref):
+    sd = _sd(ref)
+    b = synth.image_text_batch(2, 30, seed=1)
+    atts = b["text_atts"].clone()
+    atts[1, 20:] = 0  # padded caption
+    kw = dict(sd=sd, pfx="text_encoder.bert.", num_heads=12, fusion_layer=12, num_layers=18)
+    with torch.no_grad():
+        ie, ia = ref.get_vision_embeds(b["image"])
+        te_ref = ref.get_text_embeds(b["text_ids"], atts)
+        te = restate.bert_model(input_ids=b["text_ids"], attention_mask=atts, mode="text", **kw)
+        assert torch.allclose(te, te_ref, atol=2e-4, rtol=1e-4)
+        ce_ref = ref.get_cross_embeds(ie, ia, text_embeds=te_ref, text_atts=atts)
+        ce = restate.bert_model(encoder_embeds=te_ref, attention_mask=atts, enc_hidden=ie, enc_mask=ia, mode="fusion", **kw)
+        assert torch.allclose(ce, ce_ref, atol=3e-4, rtol=1e-4)
+        # 3-D self-attention mask (captioning layout, models/model_generation.py:122-123)
+        m3 = torch.tril(torch.ones(30, 30)).unsqueeze(0).expand(2, -1, -1).contiguous()
+        o_ref = ref.text_encoder.bert(b["text_ids"], attention_mask=m3, mode="text", return_dict=True).last_hidden_state
+        o = restate.bert_model(input_ids=b["text_ids"], attention_mask=m3, mode="text", **kw)
+        assert torch.allclose(o, o_ref, atol=2e-4, rtol=1e-4)
+
+
+def test_pretrain_losses_match_reference(ref, monkeypatch):
+    sd = _sd(ref)
+    B = 4
+    b = synth.image_text_batch(B, 30, seed=11)
+    ineg, tneg = synth.hard_negative_indices(B, seed=3)
+    monkeypatch.setattr(ref, "get_hard_negatives", lambda *a, **k: (ineg.tolist(), tneg.tolist()))
+    with torch.no_grad():
+        l_ref = ref(b["image"], b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"],
+                    masked_pos=b["masked_pos"], masked_ids=b["masked_ids"])
+        l = restate.pretrain_forward(sd, restate.Shapes(), b["image"], b["text_ids"], b["text_atts"], b["text_ids_masked"],
+                                     b["masked_pos"], b["masked_ids"], ineg, tneg)
+    for k in ("loss_itc", "loss_itm", "loss_mlm"):
+        assert abs(float(l[k]) - float(l_ref[k])) < 2e-4 * max(1.0, abs(float(l_ref[k]))), k
+
+
+def test_pretrain_bbox_losses_match_reference(ref, monkeypatch):
+    sd = _sd(ref)
+    rb = synth.region_batch(3, 6, 30, seed=21)
+    ineg, tneg = synth.hard_negative_indices(6, seed=4)
+    monkeypatch.setattr(ref, "get_hard_negatives", lambda *a, **k: (ineg.tolist(), tneg.tolist()))
+    with torch.no_grad():
+        l_ref = ref(rb["image"], rb["text_ids"], rb["text_atts"], text_ids_masked=rb["text_ids_masked"],
+                    masked_pos=rb["masked_pos"], masked_ids=rb["masked_ids"], image_atts=rb["image_atts"],
+                    idx_to_group_img=rb["idx_to_group_img"], target_bbox=rb["target_bbox"], is_image=rb["is_image"],
+                    ret_bbox_loss=True)
+        l = restate.pretrain_forward(sd, restate.Shapes(), rb["image"], rb["text_ids"], rb["text_atts"], rb["text_ids_masked"],
+                                     rb["masked_pos"], rb["masked_ids"], ineg, tneg, image_atts=rb["image_atts"],
+                                     idx_to_group_img=rb["idx_to_group_img"], target_bbox=rb["target_bbox"],
+                                     is_image=rb["is_image"], ret_bbox_loss=True)
+    for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou"):
+        assert abs(float(l[k]) - float(l_ref[k])) < 2e-4 * max(1.0, abs(float(l_ref[k]))), k

@@ -109,7 +109,8 @@ int x2k_gemm(const X2kGemmArgs* args, void* stream);
  *   Replaces nn.LayerNorm at models/beit2.py:193,201,207,411 (eps 1e-6) and
  *   models/xbert.py:212,430,514 (eps 1e-12).
  * x2k_layernorm_bwd: dx = LN'(dy) (+ dx_residual if given); dw/db are ACCUMULATED (+=) into
- *   fp32 [D] buffers.  dy may be bf16 (dy_bf16) or fp32 (dy_f32) — exactly one non-NULL.
+ *   fp32 [D] buffers.  dy = dy_f32 + dy_bf16 (either may be NULL, not both) — the fp32 term is
+ *   the residual-stream gradient, the bf16 term a branch gradient produced by a dgrad GEMM.
  * ------------------------------------------------------------------------------------------ */
 int x2k_layernorm_fwd(const float* x, const float* w, const float* b, int32_t M, int32_t D, float eps,
                       void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
@@ -135,6 +136,12 @@ int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, int32_t N, 
 /* dcol[n] += sum_m x[m,n] for a bf16 matrix (bias gradients of Linear layers). */
 int x2k_colsum_bf16(const void* x_bf16, int64_t ld, int32_t M, int32_t N, float* dcol, void* stream);
 
+/* out[s,:] = sum_{b: index[b]==s} in[b,:] (bf16 in/out, fp32 accumulate; row_elems % 8 == 0).
+ * Reduces the per-query-sequence dK/dV of cross-attention onto the shared image K/V
+ * (the K/V cache across the ITM/MLM/bbox passes of models/xvlm.py:859-925). */
+int x2k_segment_sum_bf16(const void* in_bf16, const int32_t* index, int32_t n_rows, int64_t row_elems,
+                         int32_t n_seg, void* out_bf16, void* stream);
+
 /* dst_bf16[i] = bf16(src_f32[i]), i < n (weight shadow copies, activation casts). */
 int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 
@@ -142,45 +149,61 @@ int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream)
  * Attention on tcgen05:  O = softmax(scale·Q·Kᵀ + bias[h] + mask[b]) · V   per (batch b, head h).
  *
  * Q rows of sequence b live at q + (b*Lq + i)*ld_q + h*64 (bf16, head_dim 64 only); K/V rows of
- * sequence b at k + (kv_index ? kv_index[b] : b)*Lk*ld_k + j*ld_k + h*64 — i.e. the kernels read
+ * sequence b at k + ((kv_index ? kv_index[b] : b)*Lk + j)*ld_k + h*64 — i.e. the kernels read
  * the packed QKV projection output in place ([B·L, 3D] for BEiT/BERT self-attention, separate
  * Q and KV buffers for cross-attention) and several query sequences may share one K/V sequence
  * (the image K/V cache across the ITM/MLM passes, models/xvlm.py:859-899).
- * bias: fp32 [H, Lq, Lk] or NULL (BEiT relative position bias, already gathered).
- * mask: fp32 additive, [B, Lk] (mask_q_stride = 0) or [B, Lq, Lk] (mask_q_stride = Lk), or NULL.
- * dropout on probabilities (BERT attention_probs_dropout) via Philox, as in x2k_gemm.
- * Outputs: O bf16 at o + (b*Lq+i)*ld_o + h*64, lse fp32 [B,H,Lq].  Lk <= 256.
+ * Let Lk_pad = Lk rounded up to 16 (Lk <= 256).
+ * bias: fp32, element (h,i,j) at bias[h*bias_h_stride + i*bias_q_stride + j] (BEiT relative
+ *   position bias already gathered), or NULL.  Strides are multiples of 4, q stride >= Lk_pad.
+ * mask: fp32 additive, element (b,i,j) at mask[b*mask_b_stride + i*mask_q_stride + j]
+ *   (mask_q_stride = 0 for a key mask [B,Lk]), or NULL.  Same stride rules.
+ * dropout on probabilities (BERT attention_probs_dropout) via Philox4x32-10, counter =
+ *   offset + (((b*H+h)*Lq + i)*Lk_pad + j)/4.
+ * Outputs: O bf16 at o + (b*Lq+i)*ld_o + h*64, lse fp32 [B,H,Lq] (log2 domain: log2 sum exp2).
  * Replaces models/beit2.py:135-159 and models/xbert.py:364-410.
  *
- * x2k_attn_bwd: given dO, recomputes P from lse and produces dQ, dK, dV (bf16, same addressing
- * as q/k/v with their own pointers/ld; dK/dV are per *query batch* b — the caller reduces over
- * shared K/V) and, if dbias != NULL, accumulates dbias[h,i,j] += sum_b dS (fp32 atomics).
- * delta: fp32 workspace [B,H,Lq].
+ * x2k_attn_bwd: given dO (and the forward's o, lse), recomputes P and produces dQ, dK, dV (bf16,
+ * addressed like q/k/v through their own pointers/ld; dK/dV are per *query batch* b — the caller
+ * reduces over shared K/V).  If ds_out != NULL also exports dS (bf16) at
+ * ds_out[b*ds_b_stride + h*ds_h_stride + i*ds_q_stride + j] for the bias gradient.
  * ------------------------------------------------------------------------------------------ */
 typedef struct X2kAttnArgs {
   const void *q, *k, *v; /* bf16 */
   int64_t ld_q, ld_k, ld_v;
   int32_t B, H, Lq, Lk;
   const int32_t* kv_index; /* [B] or NULL */
+  int32_t n_kv;            /* number of K/V sequences behind k/v (0 = B) */
   float scale;
-  const float* bias;       /* [H,Lq,Lk] or NULL */
-  const float* mask;       /* see above, or NULL */
+  const float* bias;
+  int64_t bias_h_stride, bias_q_stride;
+  const float* mask;
   int64_t mask_b_stride, mask_q_stride;
   float dropout_p;
   uint64_t dropout_seed, dropout_offset;
-  void* o;                 /* bf16 */
+  void* o;                 /* bf16 (output of fwd, input of bwd) */
   int64_t ld_o;
-  float* lse;              /* [B,H,Lq] */
+  float* lse;              /* [B,H,Lq] (output of fwd, input of bwd) */
   /* backward only */
-  const void* d_o;         /* bf16, ld_o addressing */
+  const void* d_o;         /* bf16 */
+  int64_t ld_do;
   void *dq, *dk, *dv;      /* bf16 */
   int64_t ld_dq, ld_dk, ld_dv;
-  float* dbias;            /* [H,Lq,Lk] fp32 accumulate, or NULL */
-  float* delta;            /* [B,H,Lq] workspace */
+  void* ds_out;            /* bf16 or NULL */
+  int64_t ds_b_stride, ds_h_stride, ds_q_stride;
 } X2kAttnArgs;
 
 int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);
 int x2k_attn_bwd(const X2kAttnArgs* args, void* stream);
+
+/* BEiT relative position bias (models/beit2.py:138-143): out[h, i, j] = table[index[i*N+j], h]
+ * written with row stride ld_out (>= N, multiple of 4), h stride N*ld_out; and its backward:
+ * dtable[index[i*N+j], h] += sum_b ds[b,h,i,j]  (ds = bf16 dS exported by x2k_attn_bwd). */
+int x2k_relpos_bias_gather(const float* table, const int64_t* index, int32_t N, int32_t H,
+                           float* out, int64_t ld_out, void* stream);
+int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H, int32_t N, int64_t ds_b_stride,
+                            int64_t ds_h_stride, int64_t ds_q_stride, const int64_t* index,
+                            float* dtable, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flat-buffer optimizer step (replaces optim.py:26-104 AdamW +

@@ -1,0 +1,165 @@
+"""CPU tests of the host side: C-ABI exports, drop-in module surface (names / state_dict keys / parameter
+counts of SURVEY.md App. A.6), flat parameter arena, and the bucketed all-reduce over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol():
+    from x2vlm_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "x2k.h")).read()
+    declared = set(re.findall(r"\b(x2k_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.SYMBOLS), (declared ^ set(_capi.SYMBOLS))
+    lib = _capi.lib()  # loads libx2k.so and resolves every symbol (AttributeError otherwise)
+    assert lib.x2k_version() == 100
+    assert ctypes.sizeof(_capi.X2kGemmArgs) > 0
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "x2vlm_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_ops_refuse_cpu_tensors():
+    from x2vlm_b200 import _capi, ops
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(_capi.X2kError):
+        ops.gemm(a, a, 128, 128, 64, out_bf16=torch.zeros(128, 128, dtype=torch.bfloat16))
+
+
+def _build_xvlm():
+    from x2vlm_b200 import pretrain
+    torch.manual_seed(0)
+    return pretrain.XVLM(pretrain.base_config())
+
+
+@pytest.fixture(scope="module")
+def xvlm():
+    return _build_xvlm()
+
+
+def test_state_dict_surface_matches_reference(xvlm):
+    sd = xvlm.state_dict()
+    assert len(sd) == 587
+    assert sum(p.numel() for p in xvlm.parameters()) == 254758401
+    for k, shape in {"temp": (), "vision_encoder.cls_token": (1, 1, 768),
+                     "vision_encoder.patch_embed.proj.weight": (768, 3, 16, 16),
+                     "vision_encoder.blocks.11.attn.relative_position_bias_table": (732, 12),
+                     "vision_encoder.blocks.0.attn.relative_position_index": (197, 197),
+                     "vision_encoder.blocks.3.attn.qkv.weight": (2304, 768), "vision_encoder.blocks.3.gamma_1": (768,),
+                     "vision_encoder.fc_norm.weight": (768,),
+                     "text_encoder.bert.embeddings.position_ids": (1, 512),
+                     "text_encoder.bert.embeddings.word_embeddings.weight": (30522, 768),
+                     "text_encoder.bert.encoder.layer.0.attention.self.query.weight": (768, 768),
+                     "text_encoder.bert.encoder.layer.12.crossattention.self.key.weight": (768, 768),
+                     "text_encoder.bert.encoder.layer.17.output.LayerNorm.bias": (768,),
+                     "text_encoder.cls.predictions.decoder.weight": (30522, 768),
+                     "text_encoder.cls.predictions.decoder.bias": (30522,), "text_encoder.cls.predictions.bias": (30522,),
+                     "vision_proj.weight": (256, 768), "itm_head.3.weight": (2, 1536), "bbox_head.0.weight": (1536, 768)}.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert "text_encoder.bert.encoder.layer.11.crossattention.self.key.weight" not in sd
+    # tied decoder
+    assert xvlm.text_encoder.cls.predictions.decoder.weight is xvlm.text_encoder.bert.embeddings.word_embeddings.weight
+    assert sd["vision_encoder.blocks.0.attn.relative_position_index"].dtype == torch.int64
+
+
+@pytest.mark.reference
+def test_state_dict_keys_identical_to_reference(xvlm):
+    from oracle import ref_shim
+    ref = ref_shim.build_reference_xvlm()
+    rsd, sd = ref.state_dict(), xvlm.state_dict()
+    assert list(rsd.keys()) == list(sd.keys()) or set(rsd.keys()) == set(sd.keys())
+    for k in rsd:
+        assert rsd[k].shape == sd[k].shape and rsd[k].dtype == sd[k].dtype, k
+    assert torch.equal(rsd["vision_encoder.blocks.0.attn.relative_position_index"],
+                       sd["vision_encoder.blocks.0.attn.relative_position_index"])
+    missing, unexpected = xvlm.load_state_dict(rsd, strict=True)
+    assert not missing and not unexpected
+
+
+def test_arena_layout_and_views(xvlm):
+    import copy
+    from x2vlm_b200.params import ParamArena
+    m = copy.deepcopy(xvlm.text_encoder.bert.encoder.layer[12])  # a fusion layer
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    arena = ParamArena(m)
+    for n, p in m.named_parameters():
+        assert torch.equal(p, before[n]), n
+        s, e = arena.span(p)
+        assert p.data_ptr() == arena.flat[s:e].data_ptr() and p.grad.data_ptr() == arena.grad[s:e].data_ptr()
+        assert s % 8 == 0 or any(p is q for sh in arena.shadows for q in sh.params[1:])
+    at = m.attention.self
+    q, k, v = (arena.span(x.weight)[0] for x in (at.query, at.key, at.value))
+    assert k == q + at.query.weight.numel() and v == k + at.key.weight.numel()  # packed QKV weights are adjacent
+    sh = m._x2k["qkv"]
+    assert sh.arena is arena and sh.grad_sink().shape == (3 * 768, 768)
+    assert sh.grad_sink().data_ptr() == at.query.weight.grad.data_ptr()
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from x2vlm_b200.accelerator import GradBucketer
+    from x2vlm_b200.params import ParamArena
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.GELU(), torch.nn.Linear(256, 64), torch.nn.LayerNorm(64))
+    arena = ParamArena(m)
+    b = GradBucketer(arena, world, bucket_mb=0.05)
+    assert len(b.buckets) >= 2
+    torch.manual_seed(100 + rank)
+    x = torch.randn(16, 64)
+    arena.zero_grad()
+    m(x).pow(2).sum().backward()
+    local = arena.grad.clone()
+    order = b.finalize()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    want = sum(gathered) / world
+    ok = torch.allclose(arena.grad, want, atol=1e-6) and sorted(order) == list(range(len(b.buckets)))
+    # second backward accumulates on top of the averaged gradient (two-backward video pattern, Pretrain.py:193-247)
+    m(x).pow(2).sum().backward()
+    b.finalize()
+    ok = ok and torch.allclose(arena.grad, 2 * want, atol=1e-5)
+    q.put((rank, bool(ok), order))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(30) for p in procs]
+    assert all(ok for _, ok, _ in res), res
+    # buckets complete in reverse parameter order (last layer first): overlap-friendly launch order
+    assert res[0][2][0] == max(res[0][2])
+
+
+def test_flat_adamw_groups(xvlm):
+    import copy
+    from x2vlm_b200.accelerator import FlatAdamW
+    from x2vlm_b200.params import ParamArena
+    m = copy.deepcopy(xvlm.text_encoder.bert.encoder.layer[0])
+    arena = ParamArena(m)
+    opt = FlatAdamW(m, arena, lr=1e-4, weight_decay=0.01)
+    wds = sorted({g["weight_decay"] for g in opt.param_groups})
+    assert wds == [0.0, 0.01]
+    nd = [p for g in opt.param_groups if g["weight_decay"] == 0.0 for p in g["params"]]
+    names = {id(p): n for n, p in m.named_parameters()}
+    assert all(("bias" in names[id(p)] or "LayerNorm" in names[id(p)]) for p in nd)
+    assert int(opt.seg_end[-1]) == arena.numel

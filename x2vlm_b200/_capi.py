@@ -46,20 +46,19 @@ class X2kAttnArgs(ctypes.Structure):
         ("q", c_void_p), ("k", c_void_p), ("v", c_void_p),
         ("ld_q", c_int64), ("ld_k", c_int64), ("ld_v", c_int64),
         ("B", c_int32), ("H", c_int32), ("Lq", c_int32), ("Lk", c_int32),
-        ("kv_index", c_void_p),
+        ("kv_index", c_void_p), ("n_kv", c_int32),
         ("scale", c_float),
-        ("bias", c_void_p),
-        ("mask", c_void_p),
-        ("mask_b_stride", c_int64), ("mask_q_stride", c_int64),
+        ("bias", c_void_p), ("bias_h_stride", c_int64), ("bias_q_stride", c_int64),
+        ("mask", c_void_p), ("mask_b_stride", c_int64), ("mask_q_stride", c_int64),
         ("dropout_p", c_float),
         ("dropout_seed", c_uint64), ("dropout_offset", c_uint64),
         ("o", c_void_p), ("ld_o", c_int64),
         ("lse", c_void_p),
-        ("d_o", c_void_p),
+        ("d_o", c_void_p), ("ld_do", c_int64),
         ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("ld_dq", c_int64), ("ld_dk", c_int64), ("ld_dv", c_int64),
-        ("dbias", c_void_p),
-        ("delta", c_void_p),
+        ("ds_out", c_void_p),
+        ("ds_b_stride", c_int64), ("ds_h_stride", c_int64), ("ds_q_stride", c_int64),
     ]
 
 
@@ -80,9 +79,13 @@ SYMBOLS = {
                                              c_int32, c_float, c_uint64, c_uint64, c_void_p, c_int64,
                                              c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "x2k_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "x2k_segment_sum_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "x2k_cast_f32_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "x2k_attn_fwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
     "x2k_attn_bwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
+    "x2k_relpos_bias_gather": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "x2k_relpos_bias_scatter": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64,
+                                               c_void_p, c_void_p, c_void_p]),
     "x2k_sumsq": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "x2k_adamw_flat": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_float,

@@ -1,0 +1,251 @@
+"""Data-parallel runtime for the flat-arena model: bucketed NCCL all-reduce overlapped with backward,
+fused global-norm clipping and a one-kernel AdamW.
+
+`X2kDDPAccelerator` keeps the four-method surface of the reference's
+accelerators/apex_ddp_accelerator.py:ApexDDPAccelerator (`set_up`, `broadcast`, `backward_step`,
+`optimizer_step`; called from Pretrain.py:576-578, :67-72) and the wrapped model exposes `.module`
+(Pretrain.py:328).  Differences, all deliberate:
+
+* apex DDP with ``delay_allreduce=True`` issues ONE un-overlapped all-reduce of 1.02 GB after the last
+  gradient.  Here the flat fp32 gradient buffer of `ParamArena` is cut into contiguous
+  buckets; a bucket is all-reduced (SUM then 1/W, apex's ``gradient_average``) on a side stream the
+  moment its last gradient has been written, so communication hides under the rest of backward.
+  The wgrad GEMMs accumulate directly into that buffer — there are no per-parameter gradient
+  tensors and no bucket copies.
+* bf16 needs no loss scaler, so `backward_step` is a plain backward.
+* `optimizer_step` computes the global gradient norm on the device and leaves the clip coefficient
+  in device memory for the fused AdamW kernel (no host sync).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .params import ParamArena
+
+NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.weight", "norm1.bias", "norm1.weight",
+            "norm2.bias", "norm2.weight")
+
+
+class FlatAdamW:
+    """AdamW(eps=1e-8, betas=(0.9, 0.98)) over the arena's flat buffers with the reference's name-based
+    parameter groups (optim.py:26-104: decay / no-decay x {default, init_params·lr_mult, vision, text, cross})."""
+
+    def __init__(self, model, arena, lr=1e-4, weight_decay=0.01, lr_mult=1.0, vision_lr=None, text_lr=None, cross_lr=None,
+                 betas=(0.9, 0.98), eps=1e-8):
+        self.arena = arena
+        self.betas, self.eps = betas, eps
+        names = {id(p): n for n, p in model.named_parameters()}
+        init_params = set(getattr(model, "init_params", []) or [])
+        if cross_lr is None:
+            cross_lr = text_lr
+        self.param_groups = []
+        group_of = {}
+
+        def group(lr_, wd_):
+            key = (lr_, wd_)
+            if key not in group_of:
+                group_of[key] = len(self.param_groups)
+                self.param_groups.append({"params": [], "lr": lr_, "weight_decay": wd_, "initial_lr": lr_})
+            return self.param_groups[group_of[key]]
+
+        for p in arena.params:
+            n = names.get(id(p), "")
+            if not p.requires_grad:
+                continue
+            wd_ = 0.0 if any(nd in n for nd in NO_DECAY) else weight_decay
+            if vision_lr is not None and n.startswith("vision_encoder"):
+                lr_ = vision_lr
+            elif text_lr is not None and n.startswith("text_encoder"):
+                lr_ = text_lr
+            elif cross_lr is not None and n.startswith("cross_encoder"):
+                lr_ = cross_lr
+            elif n in init_params:
+                lr_ = lr * lr_mult
+            else:
+                lr_ = lr
+            group(lr_, wd_)["params"].append(p)
+        dev = arena.flat.device
+        # one segment per parameter (arena order == ascending offsets)
+        seg_end, self._seg_group = [], []
+        gid = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        for p in arena.params:
+            seg_end.append(arena.span(p)[1])
+            self._seg_group.append(gid.get(id(p), -1))
+        seg_end[-1] = arena.numel
+        self.seg_end = torch.tensor(seg_end, dtype=torch.int64, device=dev)
+        self.seg_lr = torch.zeros(len(seg_end), dtype=torch.float32, device=dev)
+        self.seg_wd = torch.zeros(len(seg_end), dtype=torch.float32, device=dev)
+        self._seg_group_t = torch.tensor([g if g >= 0 else len(self.param_groups) for g in self._seg_group], device=dev)
+        self.exp_avg = torch.zeros_like(arena.flat)
+        self.exp_avg_sq = torch.zeros_like(arena.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.grad_scale = torch.ones(1, dtype=torch.float32, device=dev)
+        self._lr_host = None
+        self._upload_hparams()
+
+    def _upload_hparams(self):
+        lrs = [g["lr"] for g in self.param_groups] + [0.0]   # frozen parameters: lr 0, wd 0
+        wds = [g["weight_decay"] for g in self.param_groups] + [0.0]
+        if self._lr_host == (lrs, wds):
+            return
+        self._lr_host = (list(lrs), list(wds))
+        dev = self.seg_lr.device
+        self.seg_lr.copy_(torch.tensor(lrs, dtype=torch.float32, device=dev)[self._seg_group_t])
+        self.seg_wd.copy_(torch.tensor(wds, dtype=torch.float32, device=dev)[self._seg_group_t])
+
+    def zero_grad(self, set_to_none=False):
+        self.arena.zero_grad()
+
+    def step(self):
+        self._upload_hparams()  # picks up LambdaLR-style mutations of param_groups[i]['lr']
+        self.step_dev += 1
+        a = self.arena
+        ops.adamw_flat(a.flat, a.grad, self.exp_avg, self.exp_avg_sq, a.bf16, a.numel, self.seg_end, self.seg_lr, self.seg_wd,
+                       self.betas[0], self.betas[1], self.eps, step_dev=self.step_dev, grad_scale=self.grad_scale)
+        self.grad_scale.fill_(1.0)
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_dev,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+
+class DDPModel(torch.nn.Module):
+    """Thin wrapper exposing `.module` like apex / torch DDP."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+class GradBucketer:
+    """Contiguous buckets over the arena's flat gradient; all-reduce each as soon as it is complete."""
+
+    def __init__(self, arena, world_size, bucket_mb=48.0, process_group=None):
+        self.arena, self.world_size, self.pg = arena, world_size, process_group
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets = []  # [start, end, [params]]
+        cur = None
+        for p in arena.params:
+            if not p.requires_grad:
+                continue
+            s, e = arena.span(p)
+            if cur is None or (e - cur[0]) > cap:
+                cur = [s, e, []]
+                self.buckets.append(cur)
+            cur[1] = e
+            cur[2].append(p)
+        self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b[2]}
+        # notifications needed before a parameter's gradient is final in one backward
+        self.need = {}
+        auto = {id(p) for p in arena.autograd_params}
+        for p in arena.params:
+            if p.requires_grad:
+                self.need[id(p)] = int(id(p) in arena.sink_param_ids) + int(id(p) in auto)
+        self.is_cuda = arena.grad.is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.is_cuda else None
+        self.launch_order = []
+        self.reset()
+        arena.on_grad_ready = self.on_grad_ready
+
+    def reset(self):
+        self.remaining = dict(self.need)
+        self.bucket_left = [len(b[2]) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
+        self.launch_order = []
+
+    def on_grad_ready(self, params):
+        for p in params:
+            k = id(p)
+            if k not in self.remaining:
+                continue
+            self.remaining[k] -= 1
+            if self.remaining[k] == 0:
+                bi = self.bucket_of[k]
+                self.bucket_left[bi] -= 1
+                if self.bucket_left[bi] == 0:
+                    self._launch(bi)
+
+    def _launch(self, bi):
+        if self.launched[bi]:
+            return
+        self.launched[bi] = True
+        self.launch_order.append(bi)
+        if self.world_size <= 1:
+            return
+        s, e, _ = self.buckets[bi]
+        view = self.arena.grad[s:e]
+        if self.is_cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+                view.mul_(1.0 / self.world_size)
+        else:  # gloo (CPU tests of the bucket logic)
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+            view.mul_(1.0 / self.world_size)
+
+    def finalize(self):
+        """Reduce whatever did not complete (parameters without gradient this step) and join the streams."""
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        if self.is_cuda and self.world_size > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        order = self.launch_order
+        self.reset()
+        return order
+
+
+class X2kDDPAccelerator:
+    def __init__(self, cfg=None, logger=None):
+        self.cfg = cfg or {}
+        self.logger = logger
+        self.arena = None
+        self.bucketer = None
+        self.norm_sq = None
+
+    def set_up(self, model, optimizer, lr_scheduler, local_rank, world_size, rank):
+        """Move the model to cuda:local_rank, join the NCCL group, flatten parameters, broadcast rank 0's weights and
+        arm the bucketed all-reduce.  `optimizer` may be None: a FlatAdamW over the arena is then created from
+        self.cfg (lr, weight_decay, ...)."""
+        torch.cuda.set_device(local_rank)
+        model = model.cuda()
+        if world_size > 1 and not dist.is_initialized():
+            addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+            port = int(os.environ.get("MASTER_PORT", 34171))
+            dist.init_process_group(backend="nccl", init_method="tcp://{}:{}".format(addr, port), world_size=world_size,
+                                    rank=rank)
+        self.world_size = world_size
+        self.arena = ParamArena(model)
+        if world_size > 1:
+            self.broadcast(model)
+        self.bucketer = GradBucketer(self.arena, world_size, float(self.cfg.get("bucket_mb", 48.0)))
+        if optimizer is None:
+            optimizer = FlatAdamW(model, self.arena, **{k: v for k, v in self.cfg.items()
+                                                        if k in ("lr", "weight_decay", "lr_mult", "vision_lr", "text_lr",
+                                                                 "cross_lr")})
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=self.arena.flat.device)
+        return DDPModel(model), optimizer, lr_scheduler
+
+    def broadcast(self, model, src=0):
+        """One broadcast of the flat parameter buffer (the reference loops over 587 state_dict tensors)."""
+        dist.broadcast(self.arena.flat, src)
+        for b in model.buffers():
+            dist.broadcast(b, src)
+        self.arena.mark_dirty()
+
+    def backward_step(self, loss, optimizer=None):
+        loss.backward()
+        return self.bucketer.finalize()
+
+    def optimizer_step(self, optimizer, model, grad_norm):
+        """Global-norm clip (torch.nn.utils.clip_grad_norm_ semantics) folded into the optimizer's gradient scale.
+        Returns the total norm as a 0-dim device tensor."""
+        self.norm_sq.zero_()
+        ops.sumsq(self.arena.grad, self.norm_sq, self.arena.numel)
+        total_norm = self.norm_sq.sqrt()
+        optimizer.grad_scale.copy_(torch.clamp(float(grad_norm) / (total_norm + 1e-6), max=1.0))
+        return total_norm[0]

@@ -1,4 +1,629 @@
-// attn.cu — placeholder until the tcgen05 attention kernels land (next commit).
+// attn.cu — attention forward / backward on tcgen05 for sm_100a (head_dim 64, Lk <= 256).
+//
+// One design serves BEiT self-attention (N = 197, dense per-head relative-position bias), BERT text
+// self-attention (L <= 64, key / 3-D masks, probability dropout) and the fusion layers'
+// cross-attention (text queries over 197 image keys, shared K/V through kv_index):
+//   * Q, K, V tiles are TMA-loaded (128B swizzle) straight out of the packed projection output;
+//   * S = Q·Kᵀ runs as one tcgen05.mma chain (M = 128 query rows, N = padded key count) into TMEM;
+//   * softmax: thread i of the CTA owns query row i (tcgen05.ld 32x32b puts TMEM lane i in thread
+//     i), so row max / sum need no shuffles; scores never leave the SM;
+//   * P is written to shared memory in the K-major 128B-swizzled UMMA layout and O = P·V runs as a
+//     second MMA chain with V consumed MN-major (no transpose);
+//   * backward recomputes P from the saved log-sum-exp, and forms dQ, dK, dV with five MMA chains
+//     per (query block, key block) tile, reusing the P / dS shared-memory tiles both K-major
+//     (dQ = dS·K) and MN-major (dK = dSᵀ·Q, dV = Pᵀ·dO); TMEM holds S, dP, dQ[2], dK, dV = 512 cols.
+// Replaces models/beit2.py:135-159 and models/xbert.py:364-410 (+ autograd).
 #include "common.cuh"
-extern "C" int x2k_attn_fwd(const X2kAttnArgs*, void*) { x2k::set_error("x2k_attn_fwd: not built yet"); return X2K_ERR_UNSUPPORTED; }
-extern "C" int x2k_attn_bwd(const X2kAttnArgs*, void*) { x2k::set_error("x2k_attn_bwd: not built yet"); return X2K_ERR_UNSUPPORTED; }
+
+namespace x2k {
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnParams {
+  int B, H, Lq, Lk, Lk_pad;
+  const int32_t* kv_index;
+  float scale_log2;  // scale * log2(e)
+  float scale;
+  const float* bias;
+  int64_t bias_h_stride, bias_q_stride;
+  const float* mask;
+  int64_t mask_b_stride, mask_q_stride;
+  float dropout_p;
+  uint64_t seed, offset;
+  __nv_bfloat16* o;
+  int64_t ld_o;
+  float* lse;
+  const __nv_bfloat16* d_o;
+  int64_t ld_do;
+  __nv_bfloat16 *dq, *dk, *dv;
+  int64_t ld_dq, ld_dk, ld_dv;
+  __nv_bfloat16* ds_out;
+  int64_t ds_b_stride, ds_h_stride, ds_q_stride;
+};
+
+// byte offset of the 16-byte chunk holding elements [k0, k0+8) of row `row` inside a K-major,
+// 128B-swizzled tile made of [128 rows x 64 elements] blocks (block stride 16 KB).
+__device__ __forceinline__ uint32_t swz_off(int row, int k0) {
+  const int blk = k0 >> 6, c = (k0 & 63) >> 3;
+  return blk * 16384 + row * 128 + ((c ^ (row & 7)) << 4);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// additive term (bias + mask) * log2e for 16 consecutive keys starting at k0 of query row q.
+__device__ __forceinline__ void load_additive(const AttnParams& p, const float* bias_row, const float* mask_row, int k0,
+                                              float (&add)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) add[j] = 0.f;
+  if (bias_row) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + k0 + j));
+      add[j] += b.x; add[j + 1] += b.y; add[j + 2] += b.z; add[j + 3] += b.w;
+    }
+  }
+  if (mask_row) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + k0 + j));
+      add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) add[j] *= kLog2e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: grid (q tiles, H, B), 128 threads, 2 CTAs / SM (TMEM 256 columns each)
+// ---------------------------------------------------------------------------------------------
+constexpr int FWD_REGION0 = 65536;  // Q (16 KB) + K (<= 32 KB) during S; P (4 x 16 KB) afterwards
+constexpr int FWD_SMEM = FWD_REGION0 + 32768 + 1024 + 128;
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sP = smem;  // aliases Q/K once S has been computed
+  uint8_t* sV = smem + FWD_REGION0;
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + FWD_REGION0 + 32768);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_mma = bar_qk + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_qk + 3);
+
+  const int warp = threadIdx.x >> 5, row = threadIdx.x;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+  const int Lk_pad = p.Lk_pad;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_qk, 16384 + Lk_pad * 128);
+    tma_load_2d(sQ, &tmap_q, bar_qk, h * 64, b * p.Lq + qt * 128);
+    tma_load_2d(sK, &tmap_k, bar_qk, h * 64, kvb * p.Lk);
+    mbar_arrive_expect_tx(bar_v, Lk_pad * 128);
+    tma_load_2d(sV, &tmap_v, bar_v, h * 64, kvb * p.Lk);
+    // S = Q · Kᵀ
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, Lk_pad, 0, 0);
+    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc, k != 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  // ---- softmax over the row owned by this thread ----
+  const int q = qt * 128 + row;
+  const bool qvalid = q < p.Lq;
+  const float* bias_row = (p.bias && qvalid) ? p.bias + h * p.bias_h_stride + q * p.bias_q_stride : nullptr;
+  const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int nchunk = Lk_pad >> 4;
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t s[16];
+    tmem_ld_32x16(trow + c * 16, s);
+    float add[16];
+    load_additive(p, bias_row, mask_row, c * 16, add);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t = (c * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]) : -INFINITY;
+      mx = fmaxf(mx, t);
+    }
+  }
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+  const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * Lk_pad;
+  const uint32_t sP_addr = smem_u32(sP);
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t s[16];
+    tmem_ld_32x16(trow + c * 16, s);
+    float add[16];
+    load_additive(p, bias_row, mask_row, c * 16, add);
+    tmem_wait_ld();
+    float pr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t = (c * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]) : -INFINITY;
+      pr[j] = exp2f(t - mx);
+      sum += pr[j];
+    }
+    if (p.dropout_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + c * 16 + j) >> 2));
+        pr[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
+        pr[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
+        pr[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
+        pr[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+      }
+    }
+    st_shared_v4(sP_addr + swz_off(row, c * 16), pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
+                 pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
+    st_shared_v4(sP_addr + swz_off(row, c * 16 + 8), pack_bf16x2(pr[8], pr[9]), pack_bf16x2(pr[10], pr[11]),
+                 pack_bf16x2(pr[12], pr[13]), pack_bf16x2(pr[14], pr[15]));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- O = P · V (accumulator aliases the first 64 S columns, all S reads are complete) ----
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t av = smem_u32(sV);
+    for (int ks = 0; ks < nchunk; ++ks) {
+      const uint64_t da = make_smem_desc(sP_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+      const uint64_t db = make_smem_desc(av + ks * 2048, 8192, 1024);
+      umma_bf16(tmem, da, db, idesc, ks != 0);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  {
+    const float inv = 1.0f / sum;
+    uint32_t o[16];
+    __nv_bfloat16* dst = p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_32x16(trow + c * 16, o);
+      tmem_wait_ld();
+      if (qvalid) {
+        uint4 v0, v1;
+        v0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        v0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        v0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        v0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        v1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        v1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        v1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        v1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        *reinterpret_cast<uint4*>(dst + c * 16) = v0;
+        *reinterpret_cast<uint4*>(dst + c * 16 + 8) = v1;
+      }
+    }
+    if (qvalid) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = mx + log2f(sum);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: grid (H, B), 128 threads, 1 CTA / SM (TMEM 512 columns)
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD_SQ = 0, BWD_SDO = 32768, BWD_SK = 65536, BWD_SV = 81920, BWD_SP = 98304, BWD_SDS = 131072;
+constexpr int BWD_BARS = 163840;
+constexpr int BWD_SMEM = BWD_BARS + 1024 + 128;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t tcol_addr, float mul, bool valid) {
+  uint32_t o[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_32x16(tcol_addr + c * 16, o);
+    tmem_wait_ld();
+    if (valid) {
+      uint4 v0, v1;
+      v0.x = pack_bf16x2(__uint_as_float(o[0]) * mul, __uint_as_float(o[1]) * mul);
+      v0.y = pack_bf16x2(__uint_as_float(o[2]) * mul, __uint_as_float(o[3]) * mul);
+      v0.z = pack_bf16x2(__uint_as_float(o[4]) * mul, __uint_as_float(o[5]) * mul);
+      v0.w = pack_bf16x2(__uint_as_float(o[6]) * mul, __uint_as_float(o[7]) * mul);
+      v1.x = pack_bf16x2(__uint_as_float(o[8]) * mul, __uint_as_float(o[9]) * mul);
+      v1.y = pack_bf16x2(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
+      v1.z = pack_bf16x2(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
+      v1.w = pack_bf16x2(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
+      *reinterpret_cast<uint4*>(dst + c * 16) = v0;
+      *reinterpret_cast<uint4*>(dst + c * 16 + 8) = v1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + BWD_BARS);
+  uint64_t* bar_kv = bar_q + 1;
+  uint64_t* bar_mma = bar_q + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 3);
+
+  const int warp = threadIdx.x >> 5, row = threadIdx.x;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+  const int nqb = (p.Lq + 127) >> 7, nkb = (p.Lk + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t sbase = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_q, nqb * 2 * 16384);
+    for (int qb = 0; qb < nqb; ++qb) {
+      tma_load_2d(smem + BWD_SQ + qb * 16384, &tmap_q, bar_q, h * 64, b * p.Lq + qb * 128);
+      tma_load_2d(smem + BWD_SDO + qb * 16384, &tmap_do, bar_q, h * 64, b * p.Lq + qb * 128);
+    }
+  }
+
+  // per-row statistics: lse (log2 domain) and delta = rowsum(dO ∘ O), for each query block
+  float lse2[2] = {0.f, 0.f}, delta[2] = {0.f, 0.f};
+  for (int qb = 0; qb < nqb; ++qb) {
+    const int q = qb * 128 + row;
+    if (q < p.Lq) {
+      lse2[qb] = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q];
+      const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_do + h * 64);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+        acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+               bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+               bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+      }
+      delta[qb] = acc;
+    }
+  }
+
+  const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  uint32_t mma_phase = 0;
+  const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
+  const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2 * 16384);
+      tma_load_2d(smem + BWD_SK, &tmap_k, bar_kv, h * 64, kvb * p.Lk + kb * 128);
+      tma_load_2d(smem + BWD_SV, &tmap_v, bar_kv, h * 64, kvb * p.Lk + kb * 128);
+    }
+    for (int qb = 0; qb < nqb; ++qb) {
+      if (threadIdx.x == 0) {
+        if (qb == 0) mbar_wait(bar_kv, kb & 1);
+        if (kb == 0 && qb == 0) mbar_wait(bar_q, 0);
+        tc_fence_after();
+        const uint32_t aq = sbase + BWD_SQ + qb * 16384, ado = sbase + BWD_SDO + qb * 16384;
+        const uint32_t ak = sbase + BWD_SK, av = sbase + BWD_SV;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + TM_S, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
+                    k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + TM_DP, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024),
+                    idesc_s, k != 0);
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+      mbar_wait(bar_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+
+      // ---- P and dS for this (q block, key block) tile; thread == query row ----
+      const int q = qb * 128 + row;
+      const bool qvalid = q < p.Lq;
+      const float* bias_row = (p.bias && qvalid) ? p.bias + h * p.bias_h_stride + q * p.bias_q_stride : nullptr;
+      const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
+      const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad;
+      __nv_bfloat16* ds_row =
+          (p.ds_out && qvalid) ? p.ds_out + b * p.ds_b_stride + h * p.ds_h_stride + q * p.ds_q_stride : nullptr;
+      const float my_lse = lse2[qb], my_delta = delta[qb];
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        const int k0 = kb * 128 + c * 16;
+        uint32_t s[16], dp[16];
+        tmem_ld_32x16(trow + TM_S + c * 16, s);
+        tmem_ld_32x16(trow + TM_DP + c * 16, dp);
+        float pr[16], ds[16];
+        const bool chunk_live = qvalid && (k0 < p.Lk);
+        if (chunk_live) {
+          float add[16];
+          load_additive(p, bias_row, mask_row, k0, add);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t = fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]);
+            pr[j] = (k0 + j < p.Lk) ? exp2f(t - my_lse) : 0.f;
+            ds[j] = __uint_as_float(dp[j]);
+          }
+          if (p.dropout_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + k0 + j) >> 2));
+              const float k0_ = dropout_keep(r.x, p.dropout_p, inv_keep), k1_ = dropout_keep(r.y, p.dropout_p, inv_keep);
+              const float k2_ = dropout_keep(r.z, p.dropout_p, inv_keep), k3_ = dropout_keep(r.w, p.dropout_p, inv_keep);
+              ds[j] *= k0_; ds[j + 1] *= k1_; ds[j + 2] *= k2_; ds[j + 3] *= k3_;
+              // dS uses the un-dropped P; the P that feeds dV is the dropped one
+              const float p0 = pr[j], p1 = pr[j + 1], p2 = pr[j + 2], p3 = pr[j + 3];
+              ds[j] = p0 * (ds[j] - my_delta); ds[j + 1] = p1 * (ds[j + 1] - my_delta);
+              ds[j + 2] = p2 * (ds[j + 2] - my_delta); ds[j + 3] = p3 * (ds[j + 3] - my_delta);
+              pr[j] = p0 * k0_; pr[j + 1] = p1 * k1_; pr[j + 2] = p2 * k2_; pr[j + 3] = p3 * k3_;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
+          }
+        } else {
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
+        }
+        uint32_t pk[8], dk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
+          dk[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
+        }
+        const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
+        st_shared_v4(sbase + BWD_SP + o0, pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(sbase + BWD_SP + o1, pk[4], pk[5], pk[6], pk[7]);
+        st_shared_v4(sbase + BWD_SDS + o0, dk[0], dk[1], dk[2], dk[3]);
+        st_shared_v4(sbase + BWD_SDS + o1, dk[4], dk[5], dk[6], dk[7]);
+        if (ds_row && k0 < p.Lk_pad) {
+          *reinterpret_cast<uint4*>(ds_row + k0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+          *reinterpret_cast<uint4*>(ds_row + k0 + 8) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+
+      if (threadIdx.x == 0) {
+        const uint32_t aq = sbase + BWD_SQ + qb * 16384, ado = sbase + BWD_SDO + qb * 16384;
+        const uint32_t ak = sbase + BWD_SK;
+        const uint32_t ap = sbase + BWD_SP, ads = sbase + BWD_SDS;
+        // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tmem + TM_DQ + qb * 64, make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                    make_smem_desc(ak + ks * 2048, 8192, 1024), idesc_dq, (kb | ks) != 0);
+        // dK += dSᵀ · Q[qb]         (A: dS MN-major over keys, K = query rows; B: Q tile MN-major)
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tmem + TM_DK, make_smem_desc(ads + ks * 2048, 16384, 1024), make_smem_desc(aq + ks * 2048, 8192, 1024),
+                    idesc_dkv, (qb | ks) != 0);
+        // dV += Pᵀ · dO[qb]
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tmem + TM_DV, make_smem_desc(ap + ks * 2048, 16384, 1024), make_smem_desc(ado + ks * 2048, 8192, 1024),
+                    idesc_dkv, (qb | ks) != 0);
+        if (qb == nqb - 1) umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    // ---- drain dK / dV of this key block; thread == key row ----
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    {
+      const int key = kb * 128 + row;
+      const bool kvalid = key < p.Lk;
+      const int64_t r = static_cast<int64_t>(b) * p.Lk + key;
+      store_row64_bf16(p.dk + r * p.ld_dk + h * 64, trow + TM_DK, p.scale, kvalid);
+      store_row64_bf16(p.dv + r * p.ld_dv + h * 64, trow + TM_DV, 1.0f, kvalid);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  // ---- drain dQ (all MMAs retired: the last commit covered them) ----
+  for (int qb = 0; qb < nqb; ++qb) {
+    const int q = qb * 128 + row;
+    store_row64_bf16(p.dq + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_dq + h * 64, trow + TM_DQ + qb * 64, p.scale,
+                     q < p.Lq);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// relative-position bias gather / scatter (HBM-bound, tiny)
+// ---------------------------------------------------------------------------------------------
+__global__ void relpos_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ index, int N, int H,
+                                     float* __restrict__ out, int64_t ld_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // key (column, padded)
+  const int i = blockIdx.y, h = blockIdx.z;
+  if (j >= ld_out) return;
+  float v = 0.f;
+  if (j < N) v = __ldg(table + __ldg(index + static_cast<int64_t>(i) * N + j) * H + h);
+  out[(static_cast<int64_t>(h) * N + i) * ld_out + j] = v;
+}
+
+__global__ void relpos_scatter_kernel(const __nv_bfloat16* __restrict__ ds, int B, int H, int N, int64_t sb, int64_t sh,
+                                      int64_t sq, const int64_t* __restrict__ index, float* __restrict__ dtable) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y, h = blockIdx.z;
+  if (j >= N) return;
+  const __nv_bfloat16* src = ds + h * sh + i * sq + j;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += __bfloat162float(src[b * sb]);
+  atomicAdd(dtable + __ldg(index + static_cast<int64_t>(i) * N + j) * H + h, s);
+}
+
+int check_common(const X2kAttnArgs& a, const char* who) {
+  X2K_REQUIRE(a.q && a.k && a.v && a.o && a.lse, "%s: NULL q/k/v/o/lse", who);
+  X2K_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "%s: bad shape", who);
+  X2K_REQUIRE(a.Lk <= 256, "%s: Lk=%d > 256 is not supported by this kernel", who, a.Lk);
+  X2K_REQUIRE(a.ld_q % 8 == 0 && a.ld_k % 8 == 0 && a.ld_v % 8 == 0 && a.ld_o % 8 == 0, "%s: ld must be multiples of 8", who);
+  const int Lk_pad = (a.Lk + 15) & ~15;
+  X2K_REQUIRE(!a.bias || (a.bias_q_stride % 4 == 0 && a.bias_h_stride % 4 == 0 && a.bias_q_stride >= Lk_pad),
+              "%s: bias strides must be multiples of 4 and >= Lk_pad=%d", who, Lk_pad);
+  X2K_REQUIRE(!a.mask || (a.mask_b_stride % 4 == 0 && a.mask_q_stride % 4 == 0 &&
+                          (a.mask_q_stride == 0 ? a.mask_b_stride >= Lk_pad : a.mask_q_stride >= Lk_pad)),
+              "%s: mask strides must be multiples of 4 and cover Lk_pad=%d", who, Lk_pad);
+  X2K_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "%s: dropout_p", who);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  X2K_REQUIRE(al16(a.q) && al16(a.k) && al16(a.v) && al16(a.o) && al16(a.bias) && al16(a.mask), "%s: 16-byte alignment", who);
+  return X2K_OK;
+}
+
+void fill_params(const X2kAttnArgs& a, AttnParams& p) {
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.Lk_pad = (a.Lk + 15) & ~15;
+  p.kv_index = a.kv_index;
+  p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
+  p.bias = a.bias; p.bias_h_stride = a.bias_h_stride; p.bias_q_stride = a.bias_q_stride;
+  p.mask = a.mask; p.mask_b_stride = a.mask_b_stride; p.mask_q_stride = a.mask_q_stride;
+  p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset;
+  p.o = static_cast<__nv_bfloat16*>(a.o); p.ld_o = a.ld_o; p.lse = a.lse;
+  p.d_o = static_cast<const __nv_bfloat16*>(a.d_o); p.ld_do = a.ld_do;
+  p.dq = static_cast<__nv_bfloat16*>(a.dq); p.dk = static_cast<__nv_bfloat16*>(a.dk); p.dv = static_cast<__nv_bfloat16*>(a.dv);
+  p.ld_dq = a.ld_dq; p.ld_dk = a.ld_dk; p.ld_dv = a.ld_dv;
+  p.ds_out = static_cast<__nv_bfloat16*>(a.ds_out);
+  p.ds_b_stride = a.ds_b_stride; p.ds_h_stride = a.ds_h_stride; p.ds_q_stride = a.ds_q_stride;
+}
+
+}  // namespace
+}  // namespace x2k
+
+using namespace x2k;
+
+extern "C" int x2k_attn_fwd(const X2kAttnArgs* args, void* stream_) {
+  X2K_REQUIRE(args != nullptr, "x2k_attn_fwd: args is NULL");
+  const X2kAttnArgs& a = *args;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_common(a, "x2k_attn_fwd")) return rc;
+  AttnParams p;
+  fill_params(a, p);
+  const int n_kv = a.n_kv > 0 ? a.n_kv : a.B;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, a.q, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_q, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, a.k, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_k, p.Lk_pad, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, a.v, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_v, p.Lk_pad, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((a.Lq + 127) / 128, a.H, a.B);
+  attn_fwd_kernel<<<grid, 128, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
+  X2K_REQUIRE(args != nullptr, "x2k_attn_bwd: args is NULL");
+  const X2kAttnArgs& a = *args;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_common(a, "x2k_attn_bwd")) return rc;
+  X2K_REQUIRE(a.d_o && a.dq && a.dk && a.dv, "x2k_attn_bwd: NULL d_o/dq/dk/dv");
+  X2K_REQUIRE(a.Lq <= 256, "x2k_attn_bwd: Lq=%d > 256 is not supported by this kernel", a.Lq);
+  X2K_REQUIRE(a.ld_do % 8 == 0 && a.ld_dq % 8 == 0 && a.ld_dk % 8 == 0 && a.ld_dv % 8 == 0, "x2k_attn_bwd: ld alignment");
+  X2K_REQUIRE(!a.ds_out || (a.ds_q_stride % 8 == 0 && a.ds_h_stride % 8 == 0 && a.ds_b_stride % 8 == 0 &&
+                            a.ds_q_stride >= ((a.Lk + 15) & ~15)),
+              "x2k_attn_bwd: ds_out strides must be multiples of 8 and cover Lk_pad");
+  AttnParams p;
+  fill_params(a, p);
+  const int n_kv = a.n_kv > 0 ? a.n_kv : a.B;
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, a.q, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_q, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, a.k, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_k, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, a.v, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_v, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, a.d_o, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_do, 128, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(a.H, a.B);
+  attn_bwd_kernel<<<grid, 128, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_relpos_bias_gather(const float* table, const int64_t* index, int32_t N, int32_t H, float* out,
+                                      int64_t ld_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(table && index && out && N > 0 && H > 0 && ld_out >= N, "x2k_relpos_bias_gather: bad arguments");
+  dim3 grid((ld_out + 127) / 128, N, H);
+  relpos_gather_kernel<<<grid, 128, 0, stream>>>(table, index, N, H, out, ld_out);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H, int32_t N, int64_t ds_b_stride,
+                                       int64_t ds_h_stride, int64_t ds_q_stride, const int64_t* index, float* dtable,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(ds_bf16 && index && dtable && B > 0 && H > 0 && N > 0, "x2k_relpos_bias_scatter: bad arguments");
+  dim3 grid((N + 127) / 128, N, H);
+  relpos_scatter_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(ds_bf16), B, H, N, ds_b_stride,
+                                                  ds_h_stride, ds_q_stride, index, dtable);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}

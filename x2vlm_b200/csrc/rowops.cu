@@ -98,12 +98,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int j = 0; j < VEC; ++j) {
       const int c4 = lane + 32 * j;
       const float4 xv = xr[c4];
-      float4 d;
-      if (dy_bf16) {
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy_f32) d = reinterpret_cast<const float4*>(dy_f32 + static_cast<int64_t>(row) * D)[c4];
+      if (dy_bf16) {  // both given: dy = dy_f32 + dy_bf16 (residual-stream grad + branch grad)
         const uint2 pk = reinterpret_cast<const uint2*>(dy_bf16 + static_cast<int64_t>(row) * D)[c4];
-        d = make_float4(bf16_lo(pk.x), bf16_hi(pk.x), bf16_lo(pk.y), bf16_hi(pk.y));
-      } else {
-        d = reinterpret_cast<const float4*>(dy_f32 + static_cast<int64_t>(row) * D)[c4];
+        d.x += bf16_lo(pk.x); d.y += bf16_hi(pk.x); d.z += bf16_lo(pk.y); d.w += bf16_hi(pk.y);
       }
       xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       adb[j].x += d.x; adb[j].y += d.y; adb[j].z += d.z; adb[j].w += d.w;
@@ -285,6 +284,33 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
   }
 }
 
+// out[s, :] = sum over rows b with index[b] == s of in[b, :]   (fp32 accumulate, bf16 in/out)
+__global__ void __launch_bounds__(128) segment_sum_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                               const int32_t* __restrict__ index, int n_rows,
+                                                               int64_t row_elems, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ int32_t members[];  // rows of this segment
+  __shared__ int n_members;
+  const int seg = blockIdx.y;
+  if (threadIdx.x == 0) n_members = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < n_rows; b += blockDim.x)
+    if (index[b] == seg) members[atomicAdd(&n_members, 1)] = b;
+  __syncthreads();
+  const int nm = n_members;
+  const int64_t c8 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (c8 >= row_elems) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < nm; ++i) {
+    const uint4 q = *reinterpret_cast<const uint4*>(in + static_cast<int64_t>(members[i]) * row_elems + c8);
+    acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+    acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + static_cast<int64_t>(seg) * row_elems + c8) = o;
+}
+
 template <typename F>
 int dispatch_vec(int D, F&& f) {
   switch (D / 128) {
@@ -325,7 +351,7 @@ extern "C" int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
                                  const float* mean, const float* rstd, const float* dx_residual, int32_t M, int32_t D,
                                  float* dx, float* dw, float* db, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  X2K_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "x2k_layernorm_bwd: exactly one of dy_bf16/dy_f32");
+  X2K_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "x2k_layernorm_bwd: dy_bf16 and/or dy_f32 must be given");
   X2K_REQUIRE(x && w && mean && rstd && dx && dw && db, "x2k_layernorm_bwd: NULL argument");
   X2K_REQUIRE(M > 0 && D % 128 == 0 && D <= 1024, "x2k_layernorm_bwd: D=%d must be a multiple of 128, <= 1024", D);
   const int warps = 8;
@@ -423,6 +449,20 @@ extern "C" int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void
   adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n,
                                                                    seg_end, seg_lr, seg_wd, n_seg, beta1, beta2, eps,
                                                                    step, step_dev, grad_scale_dev);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+
+extern "C" int x2k_segment_sum_bf16(const void* in_bf16, const int32_t* index, int32_t n_rows, int64_t row_elems,
+                                    int32_t n_seg, void* out_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(in_bf16 && index && out_bf16 && n_rows > 0 && n_seg > 0 && row_elems > 0 && row_elems % 8 == 0,
+              "x2k_segment_sum_bf16: bad arguments");
+  X2K_REQUIRE(static_cast<size_t>(n_rows) * sizeof(int32_t) <= 48 * 1024, "x2k_segment_sum_bf16: n_rows too large");
+  dim3 grid(static_cast<unsigned>((row_elems / 8 + 127) / 128), n_seg);
+  segment_sum_bf16_kernel<<<grid, 128, n_rows * sizeof(int32_t), stream>>>(
+      static_cast<const __nv_bfloat16*>(in_bf16), index, n_rows, row_elems, static_cast<__nv_bfloat16*>(out_bf16));
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;

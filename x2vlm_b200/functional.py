@@ -1,0 +1,490 @@
+"""Autograd functions of the hot path, each a fixed sequence of libx2k kernel launches.
+
+One function per transformer block (BEiT block, BERT text/fusion layer) plus a generic fused Linear:
+forward and backward are written out by hand (dgrad / wgrad GEMMs read activations and weights where
+they lie through K-major / MN-major UMMA descriptors; LayerNorm, GELU', dropout, LayerScale, DropPath
+and residual adds live in kernel prologues/epilogues), so autograd sees ONE node per block instead of
+the reference's ~34 (BEiT) / ~56 (fusion) ATen ops per block.
+
+Semantics restated from models/beit2.py:125-209 and models/xbert.py:322-625; parity is checked in
+tests/ against oracle/restate.py (itself pinned against the unmodified reference).
+"""
+import math
+import threading
+
+import torch
+
+from . import ops
+from ._capi import ACT_GELU, ACT_GELU_BWD, ACT_NONE
+
+
+# ----------------------------------------------------------------------------------------------
+# dropout bookkeeping: every dropout site gets a unique Philox (seed, offset) range
+# ----------------------------------------------------------------------------------------------
+class _DropoutState:
+    def __init__(self):
+        self.seed = 0x5EED5EED
+        self.offset = 0
+        self.lock = threading.Lock()
+
+    def manual_seed(self, seed):
+        self.seed, self.offset = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+    def take(self, n_elems):
+        with self.lock:
+            off = self.offset
+            self.offset += (int(n_elems) + 3) // 4 + 1
+        return self.seed, off
+
+
+dropout_state = _DropoutState()
+
+
+def manual_seed(seed):
+    """Seed the Philox stream of the in-kernel dropout masks."""
+    dropout_state.manual_seed(seed)
+
+
+def _zeros(n, dev):
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+def _empty_bf16(*shape, dev):
+    return torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+
+
+def _wgrad(shadow, dy_bf16, x_bf16, n_out, n_in, rows):
+    """dW[n_out, n_in] = dyᵀ · x over `rows`; into the arena's flat gradient (accumulating) or a new tensor.
+    Returns the list of per-parameter grads to hand to autograd (None when the sink took them)."""
+    sink = shadow.grad_sink()
+    if sink is not None:
+        ops.gemm(dy_bf16, x_bf16, n_out, n_in, rows, a_mn=True, b_mn=True, out_f32=sink, accumulate=True)
+        shadow.grads_done()
+        return [None] * len(shadow.params)
+    g = torch.empty(n_out, n_in, dtype=torch.float32, device=dy_bf16.device)
+    ops.gemm(dy_bf16, x_bf16, n_out, n_in, rows, a_mn=True, b_mn=True, out_f32=g)
+    return shadow.split_grad(g)
+
+
+# ----------------------------------------------------------------------------------------------
+# generic fused Linear:  y = act(x · Wᵀ + b)
+# ----------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, shadow, gelu, out_bf16, *weights):
+        # x: [M, K] fp32 or bf16; weights only listed so autograd tracks them
+        dev = x.device
+        M, K = x.shape
+        N = shadow.total_rows
+        xb = x if x.dtype == torch.bfloat16 else ops.to_bf16(x)
+        if xb.stride(-1) != 1 or xb.stride(0) % 8 != 0:
+            xb = xb.contiguous()
+        w = shadow.get()
+        ld = (N + 7) // 8 * 8
+        pre = _empty_bf16(M, ld, dev=dev) if gelu else None
+        if out_bf16:
+            y = _empty_bf16(M, ld, dev=dev)
+            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU if gelu else ACT_NONE, preact_out=pre, out_bf16=y)
+        else:
+            y = torch.empty(M, ld, dtype=torch.float32, device=dev)
+            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU if gelu else ACT_NONE, preact_out=pre, out_f32=y)
+        ctx.shadow, ctx.gelu, ctx.dims, ctx.x_dtype = shadow, gelu, (M, N, K, ld), x.dtype
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xb, pre)
+        return y[:, :N] if ld != N else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, pre = ctx.saved_tensors
+        M, N, K, ld = ctx.dims
+        dev = dy.device
+        shadow = ctx.shadow
+        # dy -> bf16 [M, ld] (zero padded columns)
+        if ld != N:
+            dyb = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
+            dyb[:, :N].copy_(dy)
+        elif dy.dtype == torch.bfloat16 and dy.is_contiguous():
+            dyb = dy
+        else:
+            dyb = ops.to_bf16(dy.float() if dy.dtype != torch.float32 else dy)
+        if ctx.gelu:
+            # dpre = dy * gelu'(pre): identity GEMM is wasteful, so do it elementwise in torch (small uses only)
+            p = pre[:, :N].float()
+            dpre = dyb[:, :N].float() * (0.5 * (1 + torch.erf(p * 0.7071067811865476)) +
+                                         p * torch.exp(-0.5 * p * p) * 0.3989422804014327)
+            dyb = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
+            dyb[:, :N].copy_(dpre)
+        dbias = None
+        if ctx.has_bias:
+            dbias = dyb[:, :N].float().sum(0)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w = shadow.get_nograd()
+            if ctx.x_dtype == torch.bfloat16:
+                dx = _empty_bf16(M, K, dev=dev)
+                ops.gemm(dyb, w, M, K, N, b_mn=True, out_bf16=dx)
+            else:
+                dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+                ops.gemm(dyb, w, M, K, N, b_mn=True, out_f32=dx)
+        wg = _wgrad(shadow, dyb, xb, N, K, M)
+        return (dx, dbias, None, None, None, *wg)
+
+
+def linear(x, shadow, bias=None, gelu=False, out_bf16=False):
+    """y[M,N] = act(x[M,K] · Wᵀ + b) on the tcgen05 GEMM; x fp32 or bf16, W given by its Shadow."""
+    return _LinearFn.apply(x, bias, shadow, gelu, out_bf16, *shadow.params)
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm (stand-alone, fp32 in -> fp32 out)
+# ----------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        M, D = x2.shape
+        y = torch.empty_like(x2)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        ops.layernorm_fwd(x2, w, b, eps, y_f32=y, mean=mean, rstd=rstd)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        M, D = x2.shape
+        dy2 = dy.reshape(M, D).contiguous()
+        dx = torch.empty_like(x2)
+        dw, db = _zeros(D, dy.device), _zeros(D, dy.device)
+        ops.layernorm_bwd(dy2, x2, w, mean, rstd, dx, dw, db)
+        return dx.view(dy.shape), dw, db, None
+
+
+def layer_norm(x, w, b, eps):
+    return _LayerNormFn.apply(x, w, b, eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# BEiT block (models/beit2.py:191-209)
+# ----------------------------------------------------------------------------------------------
+class _BeitBlockFn(torch.autograd.Function):
+    """x += dp·γ1·proj(attn(LN1(x)));  x += dp·γ2·fc2(GELU(fc1(LN2(x))))."""
+
+    @staticmethod
+    def forward(ctx, x, dp_scale, blk, n1w, n1b, qkv_bias, table, projb, g1, n2w, n2b, fc1b, fc2b, g2, *weights):
+        B, N, D = x.shape
+        H = blk.attn.num_heads
+        M = B * N
+        dev = x.device
+        x2 = x.contiguous().view(M, D)
+        sh = blk._x2k
+        mean1, rstd1 = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ln1 = _empty_bf16(M, D, dev=dev)
+        ops.layernorm_fwd(x2, n1w, n1b, 1e-6, y_bf16=ln1, mean=mean1, rstd=rstd1)
+        qkv = _empty_bf16(M, 3 * D, dev=dev)
+        ops.gemm(ln1, sh["qkv"].get(), M, 3 * D, D, bias=qkv_bias, out_bf16=qkv)
+        ldb = ops.pad16(N)
+        bias_g = None
+        if table is not None:
+            bias_g = torch.empty(H, N, ldb, dtype=torch.float32, device=dev)
+            ops.relpos_bias_gather(table, blk.attn.relative_position_index, N, H, bias_g)
+        attn_o = _empty_bf16(M, D, dev=dev)
+        lse = torch.empty(B, H, N, dtype=torch.float32, device=dev)
+        scale = blk.attn.scale
+        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, scale, attn_o, lse, bias=bias_g)
+        y1 = _empty_bf16(M, D, dev=dev)
+        x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.gemm(attn_o, sh["proj"].get(), M, D, D, bias=projb, preact_out=y1, gamma=g1, row_scale=dp_scale,
+                 rows_per_scale=N, residual=x2, out_f32=x1)
+        mean2, rstd2 = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ln2 = _empty_bf16(M, D, dev=dev)
+        ops.layernorm_fwd(x1, n2w, n2b, 1e-6, y_bf16=ln2, mean=mean2, rstd=rstd2)
+        Dh = sh["fc1"].total_rows
+        hpre = _empty_bf16(M, Dh, dev=dev)
+        act = _empty_bf16(M, Dh, dev=dev)
+        ops.gemm(ln2, sh["fc1"].get(), M, Dh, D, bias=fc1b, preact_out=hpre, act=ACT_GELU, out_bf16=act)
+        y2 = _empty_bf16(M, D, dev=dev)
+        out = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale,
+                 rows_per_scale=N, residual=x1, out_f32=out)
+        ctx.blk, ctx.dims, ctx.scale = blk, (B, N, D, H, Dh, ldb), scale
+        ctx.save_for_backward(x2, dp_scale, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1,
+                              mean2, rstd2, ln2, hpre, act, y2)
+        return out.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, dp_scale, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1, mean2, rstd2, ln2, hpre,
+         act, y2) = ctx.saved_tensors
+        blk = ctx.blk
+        sh = blk._x2k
+        B, N, D, H, Dh, ldb = ctx.dims
+        M = B * N
+        dev = dout.device
+        dx2 = dout.contiguous().view(M, D)
+        # ---- MLP branch ----
+        g2b = _empty_bf16(M, D, dev=dev)
+        d_fc2b, d_g2 = _zeros(D, dev), (_zeros(D, dev) if g2 is not None else None)
+        ops.scale_cast_colsum(dx2, M, D, g_bf16=g2b, gamma=g2, row_scale=dp_scale, rows_per_scale=N,
+                              y_bf16=y2 if g2 is not None else None, dbias=d_fc2b, dgamma=d_g2)
+        dh = _empty_bf16(M, Dh, dev=dev)
+        ops.gemm(g2b, sh["fc2"].get_nograd(), M, Dh, D, b_mn=True, act=ACT_GELU_BWD, aux=hpre, out_bf16=dh)
+        wg_fc2 = _wgrad(sh["fc2"], g2b, act, D, Dh, M)
+        del act, g2b
+        d_fc1b = _zeros(Dh, dev)
+        ops.colsum_bf16(dh, M, Dh, d_fc1b)
+        dln2 = _empty_bf16(M, D, dev=dev)
+        ops.gemm(dh, sh["fc1"].get_nograd(), M, D, Dh, b_mn=True, out_bf16=dln2)
+        wg_fc1 = _wgrad(sh["fc1"], dh, ln2, Dh, D, M)
+        del dh
+        dx1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_n2w, d_n2b = _zeros(D, dev), _zeros(D, dev)
+        ops.layernorm_bwd(dln2, x1, n2w, mean2, rstd2, dx1, d_n2w, d_n2b, dx_residual=dx2)
+        # ---- attention branch ----
+        g1b = _empty_bf16(M, D, dev=dev)
+        d_projb, d_g1 = _zeros(D, dev), (_zeros(D, dev) if g1 is not None else None)
+        ops.scale_cast_colsum(dx1, M, D, g_bf16=g1b, gamma=g1, row_scale=dp_scale, rows_per_scale=N,
+                              y_bf16=y1 if g1 is not None else None, dbias=d_projb, dgamma=d_g1)
+        dattn = _empty_bf16(M, D, dev=dev)
+        ops.gemm(g1b, sh["proj"].get_nograd(), M, D, D, b_mn=True, out_bf16=dattn)
+        wg_proj = _wgrad(sh["proj"], g1b, attn_o, D, D, M)
+        dqkv = _empty_bf16(M, 3 * D, dev=dev)
+        ds_out = _empty_bf16(B, H, N, ldb, dev=dev) if table is not None else None
+        ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, ctx.scale, attn_o, lse, dattn, dqkv[:, :D],
+                     dqkv[:, D:2 * D], dqkv[:, 2 * D:], ds_out=ds_out, bias=bias_g)
+        d_table = None
+        if table is not None:
+            d_table = torch.zeros_like(table)
+            ops.relpos_bias_scatter(ds_out, B, H, N, blk.attn.relative_position_index, d_table)
+        d_qkvb = _zeros(3 * D, dev)
+        ops.colsum_bf16(dqkv, M, 3 * D, d_qkvb)
+        dln1 = _empty_bf16(M, D, dev=dev)
+        ops.gemm(dqkv, sh["qkv"].get_nograd(), M, D, 3 * D, b_mn=True, out_bf16=dln1)
+        wg_qkv = _wgrad(sh["qkv"], dqkv, ln1, 3 * D, D, M)
+        dx = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_n1w, d_n1b = _zeros(D, dev), _zeros(D, dev)
+        ops.layernorm_bwd(dln1, x2, n1w, mean1, rstd1, dx, d_n1w, d_n1b, dx_residual=dx1)
+        # weights were passed in the order qkv, proj, fc1, fc2
+        nig = ctx.needs_input_grad
+        return (dx.view(B, N, D), None, None, d_n1w, d_n1b, d_qkvb if nig[5] else None, d_table, d_projb,
+                d_g1 if nig[8] else None, d_n2w, d_n2b, d_fc1b, d_fc2b, d_g2 if nig[13] else None, *wg_qkv, *wg_proj,
+                *wg_fc1, *wg_fc2)
+
+
+def beit_block(x, blk, dp_scale=None):
+    """x: [B, N, D] fp32.  dp_scale: per-sample DropPath keep/(1-p) [B] fp32 or None."""
+    a = blk.attn
+    # K has no bias (beit2.py:129)
+    qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)) if a.q_bias is not None else None
+    sh = blk._x2k
+    weights = (*sh["qkv"].params, *sh["proj"].params, *sh["fc1"].params, *sh["fc2"].params)
+    return _BeitBlockFn.apply(x, dp_scale, blk, blk.norm1.weight, blk.norm1.bias, qkv_bias, a.relative_position_bias_table,
+                              a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias,
+                              blk.mlp.fc2.bias, blk.gamma_2, *weights)
+
+
+# ----------------------------------------------------------------------------------------------
+# BERT text / fusion layer (models/xbert.py:566-625), post-LN
+# ----------------------------------------------------------------------------------------------
+def _drop(p, train, n):
+    if train and p > 0.0:
+        seed, off = dropout_state.take(n)
+        return p, seed, off
+    return 0.0, 0, 0
+
+
+class _BertLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, xb, enc, encb, layer, cfg, b_qkv, b_o, ln1w, ln1b, b_qc, b_kvc, b_oc, lncw, lncb, b_i, b_out, ln2w,
+                ln2b, *weights):
+        """x [Bt,L,D] fp32 (+ optional bf16 copy xb).  cfg: dict(self_mask, self_mask_3d, cross_mask, kv_index, n_kv,
+        train, p_hidden, p_attn, eps).  enc [n_kv, Nk, Dv] fp32 / encb bf16 copy, or None (no cross-attention)."""
+        Bt, L, D = x.shape
+        M = Bt * L
+        dev = x.device
+        sh = layer._x2k
+        H = layer.attention.self.num_attention_heads
+        scale = 1.0 / math.sqrt(D // H)
+        train, p_h, p_a, eps = cfg["train"], cfg["p_hidden"], cfg["p_attn"], cfg["eps"]
+        x2 = x.contiguous().view(M, D)
+        xb2 = xb.view(M, D) if xb is not None else ops.to_bf16(x2)
+        sv = {}
+        # ---- self-attention ----
+        qkv = _empty_bf16(M, 3 * D, dev=dev)
+        ops.gemm(xb2, sh["qkv"].get(), M, 3 * D, D, bias=b_qkv, out_bf16=qkv)
+        ctx1 = _empty_bf16(M, D, dev=dev)
+        lse1 = torch.empty(Bt, H, L, dtype=torch.float32, device=dev)
+        d_a1 = _drop(p_a, train, Bt * H * L * ops.pad16(L))
+        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, L, L, scale, ctx1, lse1, mask=cfg["self_mask"],
+                     mask_per_query=cfg["self_mask_3d"], dropout_p=d_a1[0], dropout_seed=d_a1[1], dropout_offset=d_a1[2])
+        s1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_h1 = _drop(p_h, train, M * D)
+        ops.gemm(ctx1, sh["o"].get(), M, D, D, bias=b_o, dropout_p=d_h1[0], dropout_seed=d_h1[1], dropout_offset=d_h1[2],
+                 residual=x2, out_f32=s1)
+        x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        x1b = _empty_bf16(M, D, dev=dev)
+        m1, r1 = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ops.layernorm_fwd(s1, ln1w, ln1b, eps, y_bf16=x1b, y_f32=x1, mean=m1, rstd=r1)
+        has_cross = enc is not None
+        if has_cross:
+            n_kv, Nk, Dv = enc.shape
+            enc2 = encb.view(n_kv * Nk, Dv) if encb is not None else ops.to_bf16(enc.contiguous().view(n_kv * Nk, Dv))
+            qc = _empty_bf16(M, D, dev=dev)
+            ops.gemm(x1b, sh["qc"].get(), M, D, D, bias=b_qc, out_bf16=qc)
+            kvc = _empty_bf16(n_kv * Nk, 2 * D, dev=dev)
+            ops.gemm(enc2, sh["kvc"].get(), n_kv * Nk, 2 * D, Dv, bias=b_kvc, out_bf16=kvc)
+            ctx2 = _empty_bf16(M, D, dev=dev)
+            lse2 = torch.empty(Bt, H, L, dtype=torch.float32, device=dev)
+            d_a2 = _drop(p_a, train, Bt * H * L * ops.pad16(Nk))
+            ops.attn_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, ctx2, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
+                         mask=cfg["cross_mask"], dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
+            s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            d_h2 = _drop(p_h, train, M * D)
+            ops.gemm(ctx2, sh["oc"].get(), M, D, D, bias=b_oc, dropout_p=d_h2[0], dropout_seed=d_h2[1],
+                     dropout_offset=d_h2[2], residual=x1, out_f32=s2)
+            xa = torch.empty(M, D, dtype=torch.float32, device=dev)
+            xab = _empty_bf16(M, D, dev=dev)
+            mc, rc = torch.empty(M, device=dev), torch.empty(M, device=dev)
+            ops.layernorm_fwd(s2, lncw, lncb, eps, y_bf16=xab, y_f32=xa, mean=mc, rstd=rc)
+            sv.update(enc2=enc2, qc=qc, kvc=kvc, ctx2=ctx2, lse2=lse2, s2=s2, mc=mc, rc=rc, d_a2=d_a2, d_h2=d_h2,
+                      dims_c=(n_kv, Nk, Dv))
+        else:
+            xa, xab = x1, x1b
+        # ---- feed-forward ----
+        Di = sh["i"].total_rows
+        hpre = _empty_bf16(M, Di, dev=dev)
+        act = _empty_bf16(M, Di, dev=dev)
+        ops.gemm(xab, sh["i"].get(), M, Di, D, bias=b_i, preact_out=hpre, act=ACT_GELU, out_bf16=act)
+        s3 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_h3 = _drop(p_h, train, M * D)
+        ops.gemm(act, sh["out"].get(), M, D, Di, bias=b_out, dropout_p=d_h3[0], dropout_seed=d_h3[1], dropout_offset=d_h3[2],
+                 residual=xa, out_f32=s3)
+        y = torch.empty(M, D, dtype=torch.float32, device=dev)
+        yb = _empty_bf16(M, D, dev=dev)
+        m3, r3 = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ops.layernorm_fwd(s3, ln2w, ln2b, eps, y_bf16=yb, y_f32=y, mean=m3, rstd=r3)
+        sv.update(xb2=xb2, qkv=qkv, ctx1=ctx1, lse1=lse1, s1=s1, m1=m1, r1=r1, x1b=x1b, xab=xab, hpre=hpre, act=act, s3=s3,
+                  m3=m3, r3=r3, d_a1=d_a1, d_h1=d_h1, d_h3=d_h3, ln1w=ln1w, lncw=lncw, ln2w=ln2w)
+        ctx.sv, ctx.layer, ctx.cfg, ctx.has_cross = sv, layer, cfg, has_cross
+        ctx.dims = (Bt, L, D, H, Di, scale)
+        ctx.enc_needs_grad = has_cross and enc.requires_grad
+        ctx.mark_non_differentiable(yb)
+        return y.view(Bt, L, D), yb.view(Bt, L, D)
+
+    @staticmethod
+    def backward(ctx, dy, _dyb):
+        sv, layer, cfg = ctx.sv, ctx.layer, ctx.cfg
+        sh = layer._x2k
+        Bt, L, D, H, Di, scale = ctx.dims
+        M = Bt * L
+        dev = dy.device
+        dy2 = dy.contiguous().view(M, D)
+        # ---- feed-forward ----
+        ds3 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_ln2w, d_ln2b = _zeros(D, dev), _zeros(D, dev)
+        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, d_ln2w, d_ln2b)
+        g3 = _empty_bf16(M, D, dev=dev)
+        d_bout = _zeros(D, dev)
+        p, seed, off = sv["d_h3"]
+        ops.scale_cast_colsum(ds3, M, D, g_bf16=g3, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_bout)
+        dh = _empty_bf16(M, Di, dev=dev)
+        ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_GELU_BWD, aux=sv["hpre"], out_bf16=dh)
+        wg_out = _wgrad(sh["out"], g3, sv["act"], D, Di, M)
+        d_bi = _zeros(Di, dev)
+        ops.colsum_bf16(dh, M, Di, d_bi)
+        dxab = _empty_bf16(M, D, dev=dev)
+        ops.gemm(dh, sh["i"].get_nograd(), M, D, Di, b_mn=True, out_bf16=dxab)
+        wg_i = _wgrad(sh["i"], dh, sv["xab"], Di, D, M)
+        del dh, g3
+        d_bqc = d_bkvc = d_boc = d_lncw = d_lncb = d_enc = None
+        wg_qc, wg_kvc, wg_oc = [None] * len(sh["qc"].params) if "qc" in sh else [], \
+            [None] * len(sh["kvc"].params) if "kvc" in sh else [], [None] * len(sh["oc"].params) if "oc" in sh else []
+        if ctx.has_cross:
+            n_kv, Nk, Dv = sv["dims_c"]
+            ds2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+            d_lncw, d_lncb = _zeros(D, dev), _zeros(D, dev)
+            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, d_lncw, d_lncb)
+            g2 = _empty_bf16(M, D, dev=dev)
+            d_boc = _zeros(D, dev)
+            p, seed, off = sv["d_h2"]
+            ops.scale_cast_colsum(ds2, M, D, g_bf16=g2, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_boc)
+            dctx2 = _empty_bf16(M, D, dev=dev)
+            ops.gemm(g2, sh["oc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx2)
+            wg_oc = _wgrad(sh["oc"], g2, sv["ctx2"], D, D, M)
+            dqc = _empty_bf16(M, D, dev=dev)
+            dkv_seq = _empty_bf16(Bt * Nk, 2 * D, dev=dev)
+            p, seed, off = sv["d_a2"]
+            kvc = sv["kvc"]
+            ops.attn_bwd(sv["qc"], kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, sv["ctx2"], sv["lse2"], dctx2, dqc,
+                         dkv_seq[:, :D], dkv_seq[:, D:], kv_index=cfg["kv_index"], n_kv=n_kv, mask=cfg["cross_mask"],
+                         dropout_p=p, dropout_seed=seed, dropout_offset=off)
+            if cfg["kv_index"] is not None:
+                dkv = _empty_bf16(n_kv * Nk, 2 * D, dev=dev)
+                ops.segment_sum_bf16(dkv_seq.view(Bt, Nk * 2 * D), cfg["kv_index"], n_kv, dkv.view(n_kv, Nk * 2 * D))
+            else:
+                dkv = dkv_seq
+            d_bkvc = _zeros(2 * D, dev)
+            ops.colsum_bf16(dkv, n_kv * Nk, 2 * D, d_bkvc)
+            if ctx.enc_needs_grad:
+                d_enc = torch.empty(n_kv * Nk, Dv, dtype=torch.float32, device=dev)
+                ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=d_enc)
+                d_enc = d_enc.view(n_kv, Nk, Dv)
+            wg_kvc = _wgrad(sh["kvc"], dkv, sv["enc2"], 2 * D, Dv, n_kv * Nk)
+            d_bqc = _zeros(D, dev)
+            ops.colsum_bf16(dqc, M, D, d_bqc)
+            dx1b = _empty_bf16(M, D, dev=dev)
+            ops.gemm(dqc, sh["qc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dx1b)
+            wg_qc = _wgrad(sh["qc"], dqc, sv["x1b"], D, D, M)
+            res_f32, res_bf16 = ds2, dx1b
+        else:
+            res_f32, res_bf16 = ds3, dxab
+        # ---- self-attention ----
+        ds1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        d_ln1w, d_ln1b = _zeros(D, dev), _zeros(D, dev)
+        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, d_ln1w, d_ln1b)
+        g1 = _empty_bf16(M, D, dev=dev)
+        d_bo = _zeros(D, dev)
+        p, seed, off = sv["d_h1"]
+        ops.scale_cast_colsum(ds1, M, D, g_bf16=g1, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_bo)
+        dctx1 = _empty_bf16(M, D, dev=dev)
+        ops.gemm(g1, sh["o"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx1)
+        wg_o = _wgrad(sh["o"], g1, sv["ctx1"], D, D, M)
+        dqkv = _empty_bf16(M, 3 * D, dev=dev)
+        qkv = sv["qkv"]
+        p, seed, off = sv["d_a1"]
+        ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, L, L, scale, sv["ctx1"], sv["lse1"], dctx1,
+                     dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], mask=cfg["self_mask"],
+                     mask_per_query=cfg["self_mask_3d"], dropout_p=p, dropout_seed=seed, dropout_offset=off)
+        d_bqkv = _zeros(3 * D, dev)
+        ops.colsum_bf16(dqkv, M, 3 * D, d_bqkv)
+        dx = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.gemm(dqkv, sh["qkv"].get_nograd(), M, D, 3 * D, b_mn=True, residual=ds1, out_f32=dx)
+        wg_qkv = _wgrad(sh["qkv"], dqkv, sv["xb2"], 3 * D, D, M)
+        ctx.sv = None
+        # weight order: qkv(3), o, [qc, kvc(2), oc], i, out
+        return (dx.view(Bt, L, D), None, d_enc, None, None, None, d_bqkv, d_bo, d_ln1w, d_ln1b, d_bqc, d_bkvc, d_boc, d_lncw,
+                d_lncb, d_bi, d_bout, d_ln2w, d_ln2b, *wg_qkv, *wg_o, *wg_qc, *wg_kvc, *wg_oc, *wg_i, *wg_out)
+
+
+def bert_layer(x, xb, layer, cfg, enc=None, encb=None):
+    """One BertLayer.  Returns (y fp32 [Bt,L,D], y bf16 copy)."""
+    sh = layer._x2k
+    at, so = layer.attention.self, layer.attention.output
+    b_qkv = torch.cat((at.query.bias, at.key.bias, at.value.bias))
+    use_cross = enc is not None and layer.has_cross_attention
+    if use_cross:
+        ca, co = layer.crossattention.self, layer.crossattention.output
+        b_qc, b_kvc, b_oc = ca.query.bias, torch.cat((ca.key.bias, ca.value.bias)), co.dense.bias
+        lncw, lncb = co.LayerNorm.weight, co.LayerNorm.bias
+    else:
+        b_qc = b_kvc = b_oc = lncw = lncb = None
+        enc = encb = None
+    weights = [*sh["qkv"].params, *sh["o"].params]
+    if "qc" in sh:
+        weights += [*sh["qc"].params, *sh["kvc"].params, *sh["oc"].params]
+    weights += [*sh["i"].params, *sh["out"].params]
+    return _BertLayerFn.apply(x, xb, enc, encb, layer, cfg, b_qkv, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+                              b_qc, b_kvc, b_oc, lncw, lncb, layer.intermediate.dense.bias, layer.output.dense.bias,
+                              layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, *weights)

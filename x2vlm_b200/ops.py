@@ -1,0 +1,203 @@
+"""Thin Python wrappers over the C ABI (include/x2k.h).  Each wrapper validates torch tensors, hands
+raw device pointers + sizes to libx2k.so and launches on torch's current CUDA stream.  There is no
+fallback: CPU tensors or a missing library raise.
+"""
+import ctypes
+
+import torch
+
+from . import _capi as C
+
+_VP = ctypes.c_void_p
+
+
+def _stream():
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return _VP(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise C.X2kError("%s must be a CUDA tensor (the x2k kernels have no CPU path)" % name)
+    if t.dtype != dtype:
+        raise C.X2kError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _row_major(t, name):
+    if t is not None and t.dim() >= 2 and t.stride(-1) != 1:
+        raise C.X2kError("%s must have a contiguous last dimension" % name)
+
+
+def launch_count():
+    return int(C.lib().x2k_launch_count())
+
+
+def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=None, preact_out=None,
+         dropout_p=0.0, dropout_seed=0, dropout_offset=0, gamma=None, row_scale=None, rows_per_scale=0,
+         residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0):
+    """C[M,N] = epilogue(A·Bᵀ) — see x2k_gemm in include/x2k.h.  `a`/`b` are 2-D bf16 views whose
+    stride(0) is the leading dimension; MN-major operands are passed as their stored [K, M|N] matrix."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    _row_major(a, "a"); _row_major(b, "b")
+    for t, n in ((bias, "bias"), (gamma, "gamma"), (row_scale, "row_scale"), (residual, "residual"), (out_f32, "out_f32")):
+        _req(t, torch.float32, n)
+    for t, n in ((aux, "aux"), (preact_out, "preact_out"), (out_bf16, "out_bf16")):
+        _req(t, torch.bfloat16, n)
+    g = C.X2kGemmArgs()
+    g.A, g.B = a.data_ptr(), b.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb = a.stride(0), b.stride(0)
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    if bias is not None:
+        g.bias = bias.data_ptr()
+    g.act = act
+    if aux is not None:
+        g.aux, g.ld_aux = aux.data_ptr(), aux.stride(0)
+    if preact_out is not None:
+        g.preact_out, g.ld_preact = preact_out.data_ptr(), preact_out.stride(0)
+    g.dropout_p, g.dropout_seed, g.dropout_offset = float(dropout_p), int(dropout_seed), int(dropout_offset)
+    if gamma is not None:
+        g.gamma = gamma.data_ptr()
+    if row_scale is not None:
+        g.row_scale, g.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    if residual is not None:
+        g.residual, g.ld_res = residual.data_ptr(), residual.stride(0)
+    g.accumulate = int(accumulate)
+    if out_bf16 is not None:
+        g.out_bf16, g.ld_out_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if out_f32 is not None:
+        g.out_f32, g.ld_out_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    g.tile_n = tile_n
+    C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm")
+
+
+def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
+    _req(x, torch.float32, "x"); _req(w, torch.float32, "w"); _req(b, torch.float32, "b")
+    M, D = x.shape
+    C.check(C.lib().x2k_layernorm_fwd(_p(x), _p(w), _p(b), M, D, float(eps), _p(y_bf16), _p(y_f32), _p(mean), _p(rstd),
+                                      _stream()), "x2k_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, dx_residual=None):
+    """dy: bf16 or fp32 [M,D], or a (fp32, bf16) pair that is summed; dw/db are accumulated into."""
+    M, D = x.shape
+    if isinstance(dy, (tuple, list)):
+        dy_f, dy_b = dy
+    else:
+        dy_b = dy if dy.dtype == torch.bfloat16 else None
+        dy_f = dy if dy.dtype == torch.float32 else None
+    C.check(C.lib().x2k_layernorm_bwd(_p(dy_b), _p(dy_f), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_residual), M, D, _p(dx),
+                                      _p(dw), _p(db), _stream()), "x2k_layernorm_bwd")
+
+
+def scale_cast_colsum(dx, M, N, g_bf16=None, gamma=None, row_scale=None, rows_per_scale=0, dropout_p=0.0, dropout_seed=0,
+                      dropout_offset=0, y_bf16=None, dbias=None, dgamma=None):
+    _req(dx, torch.float32, "dx")
+    C.check(C.lib().x2k_scale_cast_colsum(
+        _p(dx), dx.stride(0), M, N, _p(gamma), _p(row_scale), int(rows_per_scale), float(dropout_p), int(dropout_seed),
+        int(dropout_offset), _p(y_bf16), y_bf16.stride(0) if y_bf16 is not None else 0, _p(g_bf16),
+        g_bf16.stride(0) if g_bf16 is not None else 0, _p(dbias), _p(dgamma), _stream()), "x2k_scale_cast_colsum")
+
+
+def colsum_bf16(x, M, N, dcol):
+    _req(x, torch.bfloat16, "x"); _req(dcol, torch.float32, "dcol")
+    C.check(C.lib().x2k_colsum_bf16(_p(x), x.stride(0), M, N, _p(dcol), _stream()), "x2k_colsum_bf16")
+
+
+def segment_sum_bf16(src, index, n_seg, out):
+    """out[s] = sum of src rows b with index[b] == s; src [n_rows, row_elems] bf16 contiguous."""
+    _req(src, torch.bfloat16, "src"); _req(index, torch.int32, "index"); _req(out, torch.bfloat16, "out")
+    n_rows = src.shape[0]
+    C.check(C.lib().x2k_segment_sum_bf16(_p(src), _p(index), n_rows, src.numel() // n_rows, int(n_seg), _p(out), _stream()),
+            "x2k_segment_sum_bf16")
+
+
+def cast_f32_bf16(src, dst, n=None):
+    _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+    C.check(C.lib().x2k_cast_f32_bf16(_p(src), _p(dst), int(n if n is not None else src.numel()), _stream()),
+            "x2k_cast_f32_bf16")
+
+
+def to_bf16(x):
+    """fp32 -> bf16 copy through the x2k cast kernel (contiguous tensors)."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        cast_f32_bf16(x, out)
+    return out
+
+
+def _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, kv_index=None, n_kv=0, bias=None, mask=None, mask_per_query=False,
+               dropout_p=0.0, dropout_seed=0, dropout_offset=0):
+    a = C.X2kAttnArgs()
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+        _req(t, torch.bfloat16, n)
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ld_q, a.ld_k, a.ld_v = q.stride(0), k.stride(0), v.stride(0)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    if kv_index is not None:
+        _req(kv_index, torch.int32, "kv_index")
+        a.kv_index = kv_index.data_ptr()
+    a.n_kv = int(n_kv)
+    a.scale = float(scale)
+    if bias is not None:  # [H, Lq, ld]
+        _req(bias, torch.float32, "bias")
+        a.bias, a.bias_h_stride, a.bias_q_stride = bias.data_ptr(), bias.stride(0), bias.stride(1)
+    if mask is not None:  # [B, ld] or [B, Lq, ld]
+        _req(mask, torch.float32, "mask")
+        a.mask, a.mask_b_stride = mask.data_ptr(), mask.stride(0)
+        a.mask_q_stride = mask.stride(1) if mask_per_query else 0
+    a.dropout_p, a.dropout_seed, a.dropout_offset = float(dropout_p), int(dropout_seed), int(dropout_offset)
+    a.o, a.ld_o = o.data_ptr(), o.stride(0)
+    a.lse = lse.data_ptr()
+    return a
+
+
+def attn_fwd(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw):
+    """q/k/v/o: 2-D bf16 views [rows, >= H*64] (rows = B*Lq or n_kv*Lk) with row stride = ld."""
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw)
+    C.check(C.lib().x2k_attn_fwd(ctypes.byref(a), _stream()), "x2k_attn_fwd")
+
+
+def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None, **kw):
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw)
+    for t, n in ((d_o, "d_o"), (dq, "dq"), (dk, "dk"), (dv, "dv"), (ds_out, "ds_out")):
+        _req(t, torch.bfloat16, n)
+    a.d_o, a.ld_do = d_o.data_ptr(), d_o.stride(0)
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.ld_dq, a.ld_dk, a.ld_dv = dq.stride(0), dk.stride(0), dv.stride(0)
+    if ds_out is not None:  # [B, H, Lq, ld]
+        a.ds_out = ds_out.data_ptr()
+        a.ds_b_stride, a.ds_h_stride, a.ds_q_stride = ds_out.stride(0), ds_out.stride(1), ds_out.stride(2)
+    C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd")
+
+
+def relpos_bias_gather(table, index, N, H, out):
+    _req(table, torch.float32, "table"); _req(index, torch.int64, "index"); _req(out, torch.float32, "out")
+    C.check(C.lib().x2k_relpos_bias_gather(_p(table), _p(index), N, H, _p(out), out.stride(1), _stream()),
+            "x2k_relpos_bias_gather")
+
+
+def relpos_bias_scatter(ds, B, H, N, index, dtable):
+    _req(ds, torch.bfloat16, "ds"); _req(dtable, torch.float32, "dtable")
+    C.check(C.lib().x2k_relpos_bias_scatter(_p(ds), B, H, N, ds.stride(0), ds.stride(1), ds.stride(2), _p(index), _p(dtable),
+                                            _stream()), "x2k_relpos_bias_scatter")
+
+
+def sumsq(g, out, n=None):
+    C.check(C.lib().x2k_sumsq(_p(g), int(n if n is not None else g.numel()), _p(out), _stream()), "x2k_sumsq")
+
+
+def adamw_flat(p, g, m, v, p_bf16, n, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step=0, step_dev=None, grad_scale=None):
+    C.check(C.lib().x2k_adamw_flat(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), int(n), _p(seg_end), _p(seg_lr), _p(seg_wd),
+                                   int(seg_end.numel()), float(beta1), float(beta2), float(eps), int(step), _p(step_dev),
+                                   _p(grad_scale), _stream()), "x2k_adamw_flat")
+
+
+def pad16(n):
+    return (n + 15) // 16 * 16

@@ -1,0 +1,333 @@
+"""X²-VLM pre-training model on the B200-native encoders.
+
+`XVLM` mirrors the reference's models/model_pretrain.py:XVLM / models/xvlm.py:XVLMBase surface for the
+pre-training path — same sub-module names (`vision_encoder`, `text_encoder`, `vision_proj`, `text_proj`,
+`temp`, `itm_head`, `bbox_head`), same state_dict keys (587 for base), same method names and `forward`
+keyword arguments — so reference checkpoints load and the reference's callers read the same losses.
+(In the build container the reference's own XVLMBase is also constructed on top of these encoders,
+tests/test_dropin_reference.py; the reference tree does not exist on the GPU box, hence this mirror.)
+
+Differences that are part of the B200-first design, none of which change results:
+  * hard negatives are drawn on the device (`torch.multinomial` over all rows at once) instead of
+    2·B host-synchronising `.item()` calls (models/xvlm.py:847-855);
+  * `forward_mixed` runs one image iteration + one region iteration (Pretrain.py:run_mixed_iter) with
+    every pass through a stack batched into ONE call: 1 vision call (images of both sub-batches),
+    1 text call (clean + masked captions of both), 1 fusion call (ITM pos / ITM neg / MLM / bbox of
+    both) in which sequences that look at the same image share its K/V projection (`encoder_kv_index`).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+from transformers import BertConfig
+
+from . import beit2, xbert
+
+BERT_BASE = dict(attention_probs_dropout_prob=0.1, hidden_act="gelu", hidden_dropout_prob=0.1, hidden_size=768,
+                 initializer_range=0.02, intermediate_size=3072, layer_norm_eps=1e-12, max_position_embeddings=512,
+                 num_attention_heads=12, num_hidden_layers=12, pad_token_id=0, type_vocab_size=2, vocab_size=30522)
+BERT_LARGE = dict(BERT_BASE, hidden_size=1024, intermediate_size=4096, num_attention_heads=16)
+
+
+def base_config(**over):
+    """Shape keys of configs/pretrain/x2vlm_base_*.yaml."""
+    cfg = dict(use_beit_v2=True, vision_config="configs/config_beit2_base.json", image_res=224, patch_size=16,
+               text_encoder="data/bert-base-uncased", text_num_hidden_layers=18, text_fusion_start_at=12, embed_dim=256,
+               temp=0.07)
+    cfg.update(over)
+    return cfg
+
+
+def large_config(**over):
+    """configs/pretrain/x2vlm_large_*.yaml: beit2-large + 12 text / 6 fusion layers of width 1024."""
+    cfg = base_config(vision_config="configs/config_beit2_large.json", text_encoder="data/bert-large-uncased-12l")
+    cfg.update(over)
+    return cfg
+
+
+class AllGather(torch.autograd.Function):
+    """all_gather whose backward keeps only the local slice of the gradient (models/xvlm.py:140-160)."""
+
+    @staticmethod
+    def forward(ctx, tensor, rank, world_size):
+        output = [torch.empty_like(tensor) for _ in range(world_size)]
+        dist.all_gather(output, tensor.contiguous())
+        ctx.rank, ctx.batch_size = rank, tensor.shape[0]
+        return torch.cat(output, 0)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output[ctx.batch_size * ctx.rank: ctx.batch_size * (ctx.rank + 1)], None, None
+
+
+def allgather(t):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return AllGather.apply(t, dist.get_rank(), dist.get_world_size())
+    return t
+
+
+def build_mlp(input_dim, output_dim):
+    return nn.Sequential(nn.Linear(input_dim, input_dim * 2), nn.LayerNorm(input_dim * 2), nn.GELU(),
+                         nn.Linear(input_dim * 2, output_dim))
+
+
+def box_cxcywh_to_xyxy(x):
+    cx, cy, w, h = x.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+
+
+def giou_pairs(b1, b2):
+    """Row-wise generalized IoU of xyxy boxes (the diagonal of models/box_ops.py:generalized_box_iou)."""
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    wh = (torch.min(b1[:, 2:], b2[:, 2:]) - torch.max(b1[:, :2], b2[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = a1 + a2 - inter
+    whc = (torch.max(b1[:, 2:], b2[:, 2:]) - torch.min(b1[:, :2], b2[:, :2])).clamp(min=0)
+    area = whc[:, 0] * whc[:, 1]
+    return inter / union - (area - union) / area
+
+
+class XVLM(nn.Module):
+    def __init__(self, config, load_vision_params=False, load_text_params=False, pretraining=True):
+        super().__init__()
+        if load_vision_params or load_text_params:
+            raise NotImplementedError("checkpoint loading goes through load_state_dict (no pretrained files offline)")
+        large = "large" in config.get("vision_config", "")
+        factory = beit2.beit_large_patch16 if large else beit2.beit_base_patch16
+        self.vision_encoder = factory(img_size=config["image_res"], drop_rate=0.0, drop_path_rate=0.1, attn_drop_rate=0.0,
+                                      use_mean_pooling=True, init_scale=0.001, use_rel_pos_bias=True, use_abs_pos_emb=False,
+                                      init_values=0.1, qkv_bias=True, local_attn_depth=config.get("local_attn_depth", -1),
+                                      vision_num_hidden_layers=config.get("vision_num_hidden_layers", -1))
+        self.vision_width = self.vision_encoder.vision_width = self.vision_encoder.embed_dim
+        tcfg = BertConfig(**(BERT_LARGE if "large" in config.get("text_encoder", "") else BERT_BASE))
+        tcfg.num_hidden_layers = config["text_num_hidden_layers"]
+        tcfg.fusion_layer = config["text_fusion_start_at"]
+        tcfg.embedding_dim = tcfg.hidden_size
+        tcfg.hidden_dropout_prob = config.get("dropout", tcfg.hidden_dropout_prob)
+        tcfg.encoder_width = self.vision_width
+        tcfg.text_drop_path_rate = config.get("text_drop_path_rate", 0.0)
+        tcfg.cross_drop_path_rate = config.get("cross_drop_path_rate", 0.0)
+        self.text_encoder = xbert.BertForMaskedLM(config=tcfg)
+        self.text_width = tcfg.hidden_size
+        self.embed_dim = config["embed_dim"]
+        self.vision_proj = nn.Linear(self.vision_width, self.embed_dim)
+        self.text_proj = nn.Linear(self.text_width, self.embed_dim)
+        self.temp = nn.Parameter(torch.ones([]) * config["temp"])
+        self.itm_head = build_mlp(input_dim=self.text_width, output_dim=2)
+        self.bbox_head = build_mlp(input_dim=self.text_width, output_dim=4)
+        self.init_params = []
+
+    # ------------------------------------------------------------------ reference-shaped methods
+    def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None):
+        """models/xvlm.py:663-713 (image case)."""
+        if idx_to_group_img is None:
+            image_embeds = self.vision_encoder(image)
+            return image_embeds, torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        image_embeds, full = self.vision_encoder(image, idx_to_group_img=idx_to_group_img, image_atts=image_atts)
+        return image_embeds, image_atts, full[idx_to_group_img]
+
+    def get_text_embeds(self, text_ids, text_atts):
+        return self.text_encoder.bert(text_ids, attention_mask=text_atts, return_dict=True, mode='text').last_hidden_state
+
+    def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None,
+                         encoder_kv_index=None):
+        assert text_atts is not None
+        enc = self.text_encoder.bert
+        if text_embeds is not None:
+            return enc(encoder_embeds=text_embeds, attention_mask=text_atts, encoder_hidden_states=image_embeds,
+                       encoder_attention_mask=image_atts, return_dict=True, mode='fusion',
+                       encoder_kv_index=encoder_kv_index).last_hidden_state
+        if text_ids is not None:
+            return enc(text_ids, attention_mask=text_atts, encoder_hidden_states=image_embeds,
+                       encoder_attention_mask=image_atts, return_dict=True,
+                       encoder_kv_index=encoder_kv_index).last_hidden_state
+        raise ValueError
+
+    def get_features(self, image_embeds=None, text_embeds=None):
+        if image_embeds is None:
+            return F.normalize(self.text_proj(text_embeds[:, 0, :]), dim=-1)
+        if text_embeds is None:
+            return F.normalize(self.vision_proj(image_embeds[:, 0, :]), dim=-1)
+        return F.normalize(self.vision_proj(image_embeds[:, 0, :]), dim=-1), \
+            F.normalize(self.text_proj(text_embeds[:, 0, :]), dim=-1)
+
+    def get_contrastive_loss(self, image_feat, text_feat, idx=None):
+        """models/xvlm.py:794-826 (idx=None case)."""
+        if idx is not None:
+            raise NotImplementedError("idx-grouped ITC labels")
+        image_feat_all, text_feat_all = allgather(image_feat), allgather(text_feat)
+        logits = image_feat_all @ text_feat_all.t() / self.temp
+        labels = torch.arange(logits.shape[0], device=logits.device)
+        return (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
+
+    def get_hard_negatives(self, image_feat, text_feat, idx=None):
+        """Same sampling law as models/xvlm.py:828-857 (multinomial over softmax(sim)+1e-5, diagonal zeroed), drawn
+        for all rows in one device call; returns index TENSORS (no host sync)."""
+        with torch.no_grad():
+            sim_i2t = image_feat @ text_feat.t() / self.temp
+            w_i2t = F.softmax(sim_i2t, dim=1) + 1e-5
+            w_t2i = F.softmax(sim_i2t.t(), dim=1) + 1e-5
+            w_i2t.fill_diagonal_(0)
+            w_t2i.fill_diagonal_(0)
+            image_neg_idx = torch.multinomial(w_t2i, 1).squeeze(1)
+            text_neg_idx = torch.multinomial(w_i2t, 1).squeeze(1)
+        return image_neg_idx, text_neg_idx
+
+    def get_matching_loss(self, image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=None,
+                          neg_idx=None):
+        """models/xvlm.py:859-899; the three ITM passes run as one fusion batch of 3·bs sequences that index the bs
+        image K/V sets."""
+        image_neg_idx, text_neg_idx = neg_idx if neg_idx is not None else self.get_hard_negatives(image_feat, text_feat, idx)
+        bs = image_feat.size(0)
+        ar = torch.arange(bs, device=image_feat.device)
+        kv_index = torch.cat([ar, image_neg_idx, ar]).to(torch.int32)
+        text_all = torch.cat([text_embeds, text_embeds, text_embeds[text_neg_idx]], dim=0)
+        tatt_all = torch.cat([text_atts, text_atts, text_atts[text_neg_idx]], dim=0)
+        iatt_all = torch.cat([image_atts, image_atts[image_neg_idx], image_atts], dim=0)
+        cross = self.get_cross_embeds(image_embeds, iatt_all, text_embeds=text_all, text_atts=tatt_all,
+                                      encoder_kv_index=kv_index)[:, 0, :]
+        output = self.itm_head(cross)
+        itm_labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)]).to(output.device)
+        return F.cross_entropy(output, itm_labels)
+
+    def get_mlm_loss(self, text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids):
+        return self.text_encoder(text_ids_masked, attention_mask=text_atts, encoder_hidden_states=image_embeds,
+                                 encoder_attention_mask=image_atts, return_dict=True, labels=masked_ids,
+                                 masked_pos=masked_pos).loss
+
+    def predict_bbox(self, image_embeds, text_embeds, text_atts):
+        assert image_embeds.size(0) == text_embeds.size(0)
+        cls = self.get_cross_embeds(image_embeds, torch.ones(image_embeds.shape[:2], device=image_embeds.device),
+                                    text_embeds=text_embeds, text_atts=text_atts)[:, 0, :]
+        return self.bbox_head(cls).sigmoid()
+
+    def get_bbox_loss(self, output_coord, target_bbox, is_image=None):
+        """L1 + GIoU; degenerate boxes zero the GIoU term without a host sync (models/xvlm.py:927-957)."""
+        loss_bbox = F.l1_loss(output_coord, target_bbox, reduction='none')
+        b1, b2 = box_cxcywh_to_xyxy(output_coord), box_cxcywh_to_xyxy(target_bbox)
+        degenerate = ((b1[:, 2:] < b1[:, :2]).any() | (b2[:, 2:] < b2[:, :2]).any())
+        loss_giou = torch.where(degenerate, torch.zeros_like(b1[:, 0]), 1 - giou_pairs(b1, b2))
+        if is_image is None:
+            num_boxes = target_bbox.size(0)
+        else:
+            num_boxes = torch.sum(1 - is_image)
+            loss_bbox = loss_bbox * (1 - is_image.view(-1, 1))
+            loss_giou = loss_giou * (1 - is_image)
+        return loss_bbox.sum() / num_boxes, loss_giou.sum() / num_boxes
+
+    def forward(self, image=None, text_ids=None, text_atts=None, text_ids_masked=None, masked_pos=None, masked_ids=None,
+                image_atts=None, idx_to_group_img=None, target_bbox=None, is_image=None, ret_bbox_loss=False,
+                ret_match_loss=True, neg_idx=None):
+        """models/model_pretrain.py:30-88 (image given), pass by pass like the reference."""
+        if image is None:
+            return {'loss_mlm': self.get_mlm_loss(text_ids_masked, text_atts, None, None, masked_pos, masked_ids)}
+        if ret_bbox_loss:
+            image_embeds, image_atts, image_embeds_fullatts = self.get_vision_embeds(image, image_atts, idx_to_group_img)
+        else:
+            image_embeds, image_atts = self.get_vision_embeds(image)
+        text_embeds = self.get_text_embeds(text_ids, text_atts)
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        loss = {'loss_itc': self.get_contrastive_loss(image_feat, text_feat)}
+        if ret_match_loss:
+            loss['loss_itm'] = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat,
+                                                      neg_idx=neg_idx)
+        else:
+            loss['loss_itm'] = torch.tensor(0.0)
+        loss['loss_mlm'] = self.get_mlm_loss(text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids)
+        if ret_bbox_loss:
+            coord = self.predict_bbox(image_embeds_fullatts, text_embeds, text_atts)
+            loss['loss_bbox'], loss['loss_giou'] = self.get_bbox_loss(coord, target_bbox, is_image=is_image)
+        return loss
+
+    # ------------------------------------------------------------------ batched mixed step
+    def forward_mixed(self, ib, rb=None, neg_idx_i=None, neg_idx_r=None, out=None):
+        """One image iteration (+ one region iteration) of Pretrain.py:run_mixed_iter with every stack called once.
+        ib / rb: dicts as produced by x2vlm_b200.synth.{image_text_batch, region_batch} (tensors on the device).
+        Returns {'image': losses, 'region': losses}."""
+        dev = ib["image"].device
+        bert = self.text_encoder.bert
+        Bi = ib["image"].shape[0]
+        has_r = rb is not None
+        Br = rb["text_ids"].shape[0] if has_r else 0
+        n_img_r = rb["image"].shape[0] if has_r else 0
+        # ---- vision: all images once ----
+        images = torch.cat([ib["image"], rb["image"]]) if has_r else ib["image"]
+        patches, x_cls, _ = self.vision_encoder.forward_features(images)
+        full = torch.cat([x_cls, patches], dim=1)  # [Bi + n_img_r, N, D]
+        emb_i = full[:Bi]
+        N = full.shape[1]
+        atts_i = torch.ones(Bi, N, dtype=torch.long, device=dev)
+        if has_r:
+            emb_r = self.vision_encoder.region_pool(patches[Bi:], rb["idx_to_group_img"], rb["image_atts"])
+            atts_r = rb["image_atts"]
+        # ---- text layers: clean + masked captions of both sub-batches once ----
+        ids = [ib["text_ids"], ib["text_ids_masked"]] + ([rb["text_ids"], rb["text_ids_masked"]] if has_r else [])
+        tat = [ib["text_atts"], ib["text_atts"]] + ([rb["text_atts"], rb["text_atts"]] if has_r else [])
+        tatts_all = torch.cat(tat)
+        t_all = bert(torch.cat(ids), attention_mask=tatts_all, return_dict=True, mode='text').last_hidden_state
+        te_i, tm_i = t_all[:Bi], t_all[Bi:2 * Bi]
+        if has_r:
+            te_r, tm_r = t_all[2 * Bi:2 * Bi + Br], t_all[2 * Bi + Br:]
+        # ---- ITC + hard negatives ----
+        losses = {"image": {}, "region": {}}
+        fi_i, ft_i = self.get_features(emb_i, te_i)
+        losses["image"]["loss_itc"] = self.get_contrastive_loss(fi_i, ft_i)
+        ineg_i, tneg_i = neg_idx_i if neg_idx_i is not None else self.get_hard_negatives(fi_i, ft_i)
+        if has_r:
+            fi_r, ft_r = self.get_features(emb_r, te_r)
+            losses["region"]["loss_itc"] = self.get_contrastive_loss(fi_r, ft_r)
+            ineg_r, tneg_r = neg_idx_r if neg_idx_r is not None else self.get_hard_negatives(fi_r, ft_r)
+        # ---- one fusion call: [ITM pos | ITM img-neg | ITM txt-neg | MLM] (image) + same (region) + bbox ----
+        ar_i = torch.arange(Bi, device=dev)
+        txt = [te_i, te_i, te_i[tneg_i], tm_i]
+        tatt = [ib["text_atts"], ib["text_atts"], ib["text_atts"][tneg_i], ib["text_atts"]]
+        kv = [ar_i, ineg_i, ar_i, ar_i]
+        iatt = [atts_i, atts_i[ineg_i], atts_i, atts_i]
+        enc = [emb_i]
+        if has_r:
+            ar_r = torch.arange(Br, device=dev)
+            txt += [te_r, te_r, te_r[tneg_r], tm_r, te_r]
+            tatt += [rb["text_atts"], rb["text_atts"], rb["text_atts"][tneg_r], rb["text_atts"], rb["text_atts"]]
+            kv += [Bi + ar_r, Bi + ineg_r, Bi + ar_r, Bi + ar_r, Bi + Br + rb["idx_to_group_img"]]
+            iatt += [atts_r, atts_r[ineg_r], atts_r, atts_r, torch.ones(Br, N, dtype=torch.long, device=dev)]
+            enc += [emb_r, full[Bi:]]
+        cross = self.get_cross_embeds(torch.cat(enc), torch.cat(iatt), text_embeds=torch.cat(txt), text_atts=torch.cat(tatt),
+                                      encoder_kv_index=torch.cat(kv).to(torch.int32))
+        labels_i = torch.cat([torch.ones(Bi, dtype=torch.long), torch.zeros(2 * Bi, dtype=torch.long)]).to(dev)
+        itm_logits_i = self.itm_head(cross[:3 * Bi, 0])
+        losses["image"]["loss_itm"] = F.cross_entropy(itm_logits_i, labels_i)
+        mlm_seq = [cross[3 * Bi:4 * Bi]]
+        mpos, mids = [ib["masked_pos"]], [ib["masked_ids"]]
+        if has_r:
+            o = 4 * Bi
+            labels_r = torch.cat([torch.ones(Br, dtype=torch.long), torch.zeros(2 * Br, dtype=torch.long)]).to(dev)
+            losses["region"]["loss_itm"] = F.cross_entropy(self.itm_head(cross[o:o + 3 * Br, 0]), labels_r)
+            mlm_seq.append(cross[o + 3 * Br:o + 4 * Br])
+            mpos.append(rb["masked_pos"]); mids.append(rb["masked_ids"])
+            coord = self.bbox_head(cross[o + 4 * Br:o + 5 * Br, 0]).sigmoid()
+            losses["region"]["loss_bbox"], losses["region"]["loss_giou"] = self.get_bbox_loss(
+                coord, rb["target_bbox"], is_image=rb["is_image"])
+        # ---- MLM head once over the masked positions of both sub-batches ----
+        seq = self.text_encoder.gather_seq_out_by_pos(torch.cat(mlm_seq), torch.cat(mpos))
+        logits = self.text_encoder.cls(seq)
+        V = logits.shape[-1]
+        losses["image"]["loss_mlm"] = F.cross_entropy(logits[:Bi].reshape(-1, V), mids[0].reshape(-1))
+        if has_r:
+            losses["region"]["loss_mlm"] = F.cross_entropy(logits[Bi:].reshape(-1, V), mids[1].reshape(-1))
+        if out is not None:
+            out.update(image_embeds=emb_i, text_embeds=te_i, image_feat=fi_i, text_feat=ft_i, itm_logits=itm_logits_i,
+                       mlm_logits=logits[:Bi], cross=cross)
+            if has_r:
+                out.update(bbox_coord=coord)
+        return losses
+
+    @staticmethod
+    def total_loss(losses):
+        """Sum of the image- and region-iteration losses (Pretrain.py:204-232, iter_perc = 1)."""
+        tot = sum(losses["image"].values())
+        if losses["region"]:
+            tot = tot + sum(losses["region"].values())
+        return tot

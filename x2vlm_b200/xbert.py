@@ -1,0 +1,516 @@
+"""Drop-in replacement of the reference's models/xbert.py hot path (BERT text encoder, cross-modal
+fusion layers, MLM head).
+
+Same class names, constructor arguments, attribute paths, forward keyword arguments and state_dict
+keys as the reference (`BertConfig`, `BertModel`, `BertForMaskedLM`, `BertOnlyMLMHead`,
+`BertLayer`, …; models/xbert.py:169-1687), so models/xvlm.py's
+`build_text_encoder` (:286-316) and `XVLMBase.get_text_embeds / get_cross_embeds / get_mlm_loss`
+construct and call it unchanged.  Each `BertLayer` executes as ONE autograd node of hand-written
+sm_100a kernels (x2vlm_b200.functional.bert_layer): packed QKV GEMM, tcgen05 attention with masks and
+in-kernel Philox dropout, dense+dropout+residual epilogues, LayerNorm kernels.
+
+One extension beyond the reference API: `encoder_kv_index` (int32 [B]) lets several text sequences
+attend to the SAME image's keys/values — the image K/V projection of a fusion layer is then computed
+once per image instead of once per (text, image) pair.
+
+Out of this round's scope (raise NotImplementedError): decoder KV-cache generation
+(past_key_values / use_cache), history_states, head pruning / head_mask, output_attentions.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from transformers import BertConfig  # noqa: F401  (re-exported, models/xvlm.py:25 imports it from here)
+from transformers.modeling_outputs import (BaseModelOutputWithPastAndCrossAttentions,
+                                           BaseModelOutputWithPoolingAndCrossAttentions, MaskedLMOutput)
+
+from . import functional as XF
+from . import ops
+from .params import Shadow
+
+
+class BertEmbeddings(nn.Module):
+    """word + position + token_type embeddings -> LayerNorm -> dropout (models/xbert.py:169-216)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
+        self.position_embedding_type = getattr(config, "position_embedding_type", "absolute")
+        self.config = config
+
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None, inputs_embeds=None, past_key_values_length=0):
+        input_shape = input_ids.size() if input_ids is not None else inputs_embeds.size()[:-1]
+        seq_length = input_shape[1]
+        if position_ids is None:
+            position_ids = self.position_ids[:, past_key_values_length: seq_length + past_key_values_length]
+        if token_type_ids is None:
+            token_type_ids = torch.zeros(input_shape, dtype=torch.long, device=self.position_ids.device)
+        if inputs_embeds is None:
+            inputs_embeds = self.word_embeddings(input_ids)
+        embeddings = inputs_embeds + self.token_type_embeddings(token_type_ids)
+        if self.position_embedding_type == "absolute":
+            embeddings = embeddings + self.position_embeddings(position_ids)
+        embeddings = XF.layer_norm(embeddings, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps)
+        return self.dropout(embeddings)
+
+
+class BertSelfAttention(nn.Module):
+    """Parameter holder (models/xbert.py:219-260); the math runs inside the fused layer."""
+
+    def __init__(self, config, is_cross_attention):
+        super().__init__()
+        self.config = config
+        if config.hidden_size % config.num_attention_heads != 0:
+            raise ValueError("hidden size %d is not a multiple of the number of heads %d"
+                             % (config.hidden_size, config.num_attention_heads))
+        self.fp16 = getattr(config, 'fp16', False)
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = config.hidden_size // config.num_attention_heads
+        if self.attention_head_size != 64:
+            raise NotImplementedError("x2k attention kernels are built for head_dim 64")
+        self.all_head_size = self.num_attention_heads * self.attention_head_size
+        self.query = nn.Linear(config.hidden_size, self.all_head_size)
+        kv_in = config.encoder_width if is_cross_attention else config.hidden_size
+        self.key = nn.Linear(kv_in, self.all_head_size)
+        self.value = nn.Linear(kv_in, self.all_head_size)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+        self.position_embedding_type = getattr(config, "position_embedding_type", "absolute")
+        if self.position_embedding_type != "absolute":
+            raise NotImplementedError("relative position embeddings (the reference raises too, xbert.py:381-382)")
+        self.save_attention = False
+
+
+def _check_drop_path(rate):
+    if rate > 1e-3:
+        # only configs/finetune/refcoco_grounding_large.yaml sets text/cross drop path
+        raise NotImplementedError("xbert per-position DropPath (text_drop_path_rate > 0) is not on the fused path yet")
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, config, drop_path_rate=0.0):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        _check_drop_path(drop_path_rate)
+        self.drop_path = nn.Identity()
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config, is_cross_attention=False, drop_path_rate=0.0):
+        super().__init__()
+        self.self = BertSelfAttention(config, is_cross_attention)
+        self.output = BertSelfOutput(config, drop_path_rate=drop_path_rate)
+        self.pruned_heads = set()
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        if config.hidden_act not in ("gelu", F.gelu):
+            raise NotImplementedError("fused FFN epilogue implements exact (erf) GELU only, got %r" % (config.hidden_act,))
+
+
+class BertOutput(nn.Module):
+    def __init__(self, config, drop_path_rate=0.0):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        _check_drop_path(drop_path_rate)
+        self.drop_path = nn.Identity()
+
+
+class BertLayer(nn.Module):
+    """self-attn -> (cross-attn when layer_num >= fusion_layer and encoder states are given) -> FFN
+    (models/xbert.py:551-625)."""
+
+    def __init__(self, config, layer_num, drop_path_rate=0.0):
+        super().__init__()
+        self.config = config
+        self.chunk_size_feed_forward = getattr(config, "chunk_size_feed_forward", 0)
+        self.seq_len_dim = 1
+        self.attention = BertAttention(config, drop_path_rate=drop_path_rate)
+        self.has_cross_attention = (layer_num >= config.fusion_layer)
+        if self.has_cross_attention:
+            self.layer_num = layer_num
+            self.crossattention = BertAttention(config, is_cross_attention=True, drop_path_rate=drop_path_rate)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config, drop_path_rate=drop_path_rate)
+        at = self.attention
+        sh = {"qkv": Shadow(at.self.query.weight, at.self.key.weight, at.self.value.weight),
+              "o": Shadow(at.output.dense.weight)}
+        if self.has_cross_attention:
+            ca = self.crossattention
+            sh.update(qc=Shadow(ca.self.query.weight), kvc=Shadow(ca.self.key.weight, ca.self.value.weight),
+                      oc=Shadow(ca.output.dense.weight))
+        sh.update(i=Shadow(self.intermediate.dense.weight), out=Shadow(self.output.dense.weight))
+        self._x2k = sh
+        self._x2k_shadows = list(sh.values())
+
+    def fused(self, x, xb, cfg, enc=None, encb=None):
+        return XF.bert_layer(x, xb, self, cfg, enc, encb)
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_value=None, output_attentions=False, split_lengths=None,
+                history_states=None):
+        """Reference-shaped entry point: extended additive masks in, tuple out."""
+        if head_mask is not None or past_key_value is not None or output_attentions or history_states is not None:
+            raise NotImplementedError("x2k BertLayer: head_mask / past_key_value / output_attentions / history_states")
+        cfg = _layer_cfg(self.config, self.training, attention_mask, encoder_attention_mask, None,
+                         hidden_states.shape[0], hidden_states.shape[1],
+                         encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0, hidden_states.device)
+        y, _ = self.fused(hidden_states, None, cfg, encoder_hidden_states)
+        return (y, None)
+
+
+def _pad_mask(ext_mask, B, Lq, Lk, device):
+    """Extended additive mask [B,1,1,Lk] / [B,1,Lq,Lk] (or None) -> (fp32 [B,(Lq,)pad16(Lk)] contiguous, is_3d)."""
+    if ext_mask is None:
+        return None, False
+    m = ext_mask.to(device=device, dtype=torch.float32)
+    if m.dim() == 4:
+        m = m[:, 0]
+    if m.dim() != 3:
+        raise ValueError("attention mask must be extended to [B,1,1|Lq,Lk], got %s" % (tuple(ext_mask.shape),))
+    if m.shape[0] != B:
+        m = m.expand(B, -1, -1)
+    per_query = m.shape[1] != 1
+    ld = ops.pad16(Lk)
+    out = torch.zeros(B, m.shape[1], ld, dtype=torch.float32, device=device)
+    out[:, :, :Lk] = m
+    return (out if per_query else out[:, 0].contiguous()), per_query
+
+
+def _layer_cfg(config, training, ext_self_mask, ext_cross_mask, kv_index, B, L, Nk, device):
+    self_mask, self_3d = _pad_mask(ext_self_mask, B, L, L, device)
+    cross_mask, cross_3d = _pad_mask(ext_cross_mask, B, L, Nk, device) if Nk else (None, False)
+    if cross_3d:
+        raise NotImplementedError("per-query cross-attention masks")
+    return dict(self_mask=self_mask, self_mask_3d=self_3d, cross_mask=cross_mask, kv_index=kv_index, n_kv=0,
+                train=bool(training), p_hidden=float(config.hidden_dropout_prob),
+                p_attn=float(config.attention_probs_dropout_prob), eps=float(config.layer_norm_eps))
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        text_dpr = getattr(config, 'text_drop_path_rate', 0.0)
+        cross_dpr = getattr(config, 'cross_drop_path_rate', 0.0)
+        if text_dpr > 0:
+            assert cross_dpr > 0
+            config.hidden_dropout_prob = 0.0  # the reference zeroes it when drop path is on (xbert.py:637-640)
+        n_text, n_cross = config.fusion_layer, config.num_hidden_layers - config.fusion_layer
+        dpr = [x.item() for x in torch.linspace(0, text_dpr, n_text)] + [x.item() for x in torch.linspace(0, cross_dpr, n_cross)]
+        assert len(dpr) == config.num_hidden_layers
+        self.layer = nn.ModuleList([BertLayer(config, i, dpr[i]) for i in range(config.num_hidden_layers)])
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_values=None, use_cache=None, output_attentions=False,
+                output_hidden_states=False, return_dict=True, mode='multi_modal', split_lengths=None, history_states=None,
+                encoder_kv_index=None):
+        if output_attentions or use_cache or past_key_values is not None or history_states is not None or split_lengths:
+            raise NotImplementedError("x2k BertEncoder: output_attentions / use_cache / past_key_values / history_states")
+        if head_mask is not None and any(h is not None for h in head_mask):
+            raise NotImplementedError("x2k BertEncoder: head_mask")
+        if mode == 'text':
+            start_layer, output_layer = 0, self.config.fusion_layer
+        elif mode == 'fusion':
+            start_layer, output_layer = self.config.fusion_layer, self.config.num_hidden_layers
+        elif mode == 'multi_modal':
+            start_layer, output_layer = 0, self.config.num_hidden_layers
+        else:
+            raise ValueError(f"mode {mode} is not supported")
+        B, L, _ = hidden_states.shape
+        enc = encoder_hidden_states
+        if isinstance(enc, list):
+            raise ValueError("no this case since we do not use ALBEF-NLVR anymore")
+        Nk = enc.shape[1] if enc is not None else 0
+        cfg = _layer_cfg(self.config, self.training, attention_mask, encoder_attention_mask, encoder_kv_index, B, L, Nk,
+                         hidden_states.device)
+        encb = None
+        if enc is not None:
+            enc = enc.float().contiguous()
+            if encoder_kv_index is None and enc.shape[0] != B:
+                raise ValueError("encoder_hidden_states batch %d != %d (pass encoder_kv_index to share K/V)" % (enc.shape[0], B))
+            cfg["n_kv"] = enc.shape[0]
+            if output_layer > self.config.fusion_layer:
+                encb = ops.to_bf16(enc)  # one bf16 copy feeds the K/V projection of every fusion layer
+        all_hidden_states = () if output_hidden_states else None
+        x, xb = hidden_states.float().contiguous(), None
+        for i in range(start_layer, output_layer):
+            if output_hidden_states:
+                all_hidden_states = all_hidden_states + (x,)
+            x, xb = self.layer[i].fused(x, xb, cfg, enc, encb)
+        if output_hidden_states:
+            all_hidden_states = all_hidden_states + (x,)
+        if not return_dict:
+            return tuple(v for v in [x, all_hidden_states] if v is not None)
+        return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=x, past_key_values=None,
+                                                         hidden_states=all_hidden_states, attentions=None,
+                                                         cross_attentions=None)
+
+
+class BertPooler(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.activation = nn.Tanh()
+
+    def forward(self, hidden_states):
+        return self.activation(self.dense(hidden_states[:, 0]))
+
+
+class BertPredictionHeadTransform(nn.Module):
+    """dense + GELU + LayerNorm (models/xbert.py:785-802)."""
+
+    def __init__(self, config):
+        super().__init__()
+        output_size = getattr(config, 'embedding_dim', config.hidden_size)
+        self.dense = nn.Linear(config.hidden_size, output_size)
+        self.LayerNorm = nn.LayerNorm(output_size, eps=config.layer_norm_eps)
+        self._shadow = Shadow(self.dense.weight)
+        self._x2k_shadows = [self._shadow]
+
+    def forward(self, hidden_states):
+        shp = hidden_states.shape
+        h = XF.linear(hidden_states.reshape(-1, shp[-1]), self._shadow, self.dense.bias, gelu=True)
+        h = XF.layer_norm(h, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps)
+        return h.reshape(*shp[:-1], -1)
+
+
+class BertLMPredictionHead(nn.Module):
+    """transform + decoder tied to the word embeddings + output-only bias (models/xbert.py:805-823)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        hidden_size = getattr(config, 'embedding_dim', config.hidden_size)
+        self.decoder = nn.Linear(hidden_size, config.vocab_size, bias=False)
+        self.bias = nn.Parameter(torch.zeros(config.vocab_size))
+        self.decoder.bias = self.bias  # same Parameter under both state_dict keys, as in the reference
+        self._shadow = None
+        self._x2k_shadows = []
+
+    def _x2k_refresh(self):
+        self._decoder_shadow()
+
+    def _decoder_shadow(self):
+        if self._shadow is None or self._shadow.params[0] is not self.decoder.weight:
+            self._shadow = Shadow(self.decoder.weight)
+            self._x2k_shadows = [self._shadow]
+        return self._shadow
+
+    def forward(self, hidden_states):
+        h = self.transform(hidden_states)
+        shp = h.shape
+        logits = XF.linear(h.reshape(-1, shp[-1]), self._decoder_shadow(), self.bias)
+        return logits.reshape(*shp[:-1], -1)
+
+
+class BertOnlyMLMHead(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.predictions = BertLMPredictionHead(config)
+
+    def forward(self, sequence_output):
+        return self.predictions(sequence_output)
+
+
+class BertPreTrainedModel(nn.Module):
+    """Weight init of the reference's BertPreTrainedModel (models/xbert.py:859-881) without the HF
+    `PreTrainedModel` machinery (from_pretrained is not used by X2-VLM: weights arrive via load_state_dict)."""
+    config_class = BertConfig
+    base_model_prefix = "bert"
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+
+    def _init_weights(self, module):
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+    def init_weights(self):
+        self.apply(self._init_weights)
+        self.tie_weights()
+
+    def tie_weights(self):
+        out = self.get_output_embeddings() if hasattr(self, "get_output_embeddings") else None
+        if out is not None and getattr(self.config, "tie_word_embeddings", True):
+            out.weight = self.get_input_embeddings().weight
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def get_head_mask(self, head_mask, num_hidden_layers, *a, **k):
+        if head_mask is not None:
+            raise NotImplementedError("head_mask")
+        return [None] * num_hidden_layers
+
+    def get_extended_attention_mask(self, attention_mask, input_shape, device, is_decoder):
+        """(1 - m) * -10000, broadcastable to [B, heads, Lq, Lk]; causal when is_decoder (models/xbert.py:1013-1073)."""
+        if attention_mask.dim() == 3:
+            ext = attention_mask[:, None, :, :]
+        elif attention_mask.dim() == 2:
+            if is_decoder:
+                batch_size, seq_length = input_shape
+                seq_ids = torch.arange(seq_length, device=device)
+                causal = (seq_ids[None, None, :].repeat(batch_size, seq_length, 1) <= seq_ids[None, :, None]).to(attention_mask.dtype)
+                if causal.shape[1] < attention_mask.shape[1]:
+                    prefix = attention_mask.shape[1] - causal.shape[1]
+                    causal = torch.cat([torch.ones((batch_size, seq_length, prefix), device=device, dtype=causal.dtype), causal], dim=-1)
+                ext = causal[:, None, :, :] * attention_mask[:, None, None, :]
+            else:
+                ext = attention_mask[:, None, None, :]
+        else:
+            raise ValueError("Wrong shape for input_ids (shape {}) or attention_mask (shape {})".format(
+                input_shape, attention_mask.shape))
+        return (1.0 - ext.to(dtype=torch.float32)) * -10000.0
+
+    def invert_attention_mask(self, encoder_attention_mask):
+        """Additive mask for cross-attention keys (HF invert_attention_mask; any large negative value gives
+        identical probabilities as long as one key is visible — SURVEY.md §8c)."""
+        if encoder_attention_mask.dim() == 3:
+            ext = encoder_attention_mask[:, None, :, :]
+        elif encoder_attention_mask.dim() == 2:
+            ext = encoder_attention_mask[:, None, None, :]
+        else:
+            raise ValueError("encoder_attention_mask must be 2-D or 3-D")
+        return (1.0 - ext.to(dtype=torch.float32)) * -10000.0
+
+
+class BertModel(BertPreTrainedModel):
+    def __init__(self, config, add_pooling_layer=True, add_embeddings_layer=True):
+        super().__init__(config)
+        if add_embeddings_layer:
+            self.embeddings = BertEmbeddings(config)
+        self.encoder = BertEncoder(config)
+        self.pooler = BertPooler(config) if add_pooling_layer else None
+        self.init_weights()
+
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    def set_input_embeddings(self, value):
+        self.embeddings.word_embeddings = value
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
+                inputs_embeds=None, encoder_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None,
+                past_key_values=None, history_states=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, is_decoder=False, mode='multi_modal', split_lengths=None, encoder_kv_index=None):
+        output_attentions = output_attentions if output_attentions is not None else getattr(self.config, "output_attentions", False)
+        output_hidden_states = output_hidden_states if output_hidden_states is not None else getattr(self.config, "output_hidden_states", False)
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        if past_key_values is not None or use_cache or history_states is not None:
+            raise NotImplementedError("x2k BertModel: past_key_values / use_cache / history_states (generation) — next round")
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        elif input_ids is not None:
+            input_shape, device = input_ids.size(), input_ids.device
+        elif inputs_embeds is not None:
+            input_shape, device = inputs_embeds.size()[:-1], inputs_embeds.device
+        elif encoder_embeds is not None:
+            input_shape, device = encoder_embeds.size()[:-1], encoder_embeds.device
+        else:
+            raise ValueError("You have to specify either input_ids or inputs_embeds or encoder_embeds")
+        batch_size, seq_length = input_shape
+        if attention_mask is None:
+            attention_mask = torch.ones((batch_size, seq_length), device=device)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros(input_shape, dtype=torch.long, device=device)
+        extended_attention_mask = self.get_extended_attention_mask(attention_mask, input_shape, device, is_decoder)
+        if encoder_hidden_states is not None:
+            if isinstance(encoder_hidden_states, list):
+                raise ValueError("list encoder_hidden_states are not supported")
+            n_enc, enc_len, _ = encoder_hidden_states.size()
+            if encoder_attention_mask is None:
+                encoder_attention_mask = torch.ones((batch_size if encoder_kv_index is not None else n_enc, enc_len), device=device)
+            encoder_extended_attention_mask = self.invert_attention_mask(encoder_attention_mask)
+        else:
+            encoder_extended_attention_mask = None
+        head_mask = self.get_head_mask(head_mask, self.config.num_hidden_layers)
+        if encoder_embeds is None:
+            embedding_output = self.embeddings(input_ids=input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
+                                               inputs_embeds=inputs_embeds, past_key_values_length=0)
+        else:
+            embedding_output = encoder_embeds
+        encoder_outputs = self.encoder(embedding_output, attention_mask=extended_attention_mask, head_mask=head_mask,
+                                       encoder_hidden_states=encoder_hidden_states,
+                                       encoder_attention_mask=encoder_extended_attention_mask,
+                                       output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                                       return_dict=return_dict, mode=mode, encoder_kv_index=encoder_kv_index)
+        sequence_output = encoder_outputs[0]
+        pooled_output = self.pooler(sequence_output) if self.pooler is not None else None
+        if not return_dict:
+            return (sequence_output, pooled_output) + encoder_outputs[1:]
+        return BaseModelOutputWithPoolingAndCrossAttentions(
+            last_hidden_state=sequence_output, pooler_output=pooled_output, past_key_values=None,
+            hidden_states=encoder_outputs.hidden_states, attentions=None, cross_attentions=None)
+
+
+class BertForMaskedLM(BertPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.bert = BertModel(config, add_pooling_layer=False)
+        self.cls = BertOnlyMLMHead(config)
+        self.init_weights()
+        self.bert.embeddings.word_embeddings.weight._x2k_autograd_too = True  # embedding lookup + tied decoder GEMM
+
+    def get_input_embeddings(self):
+        return self.bert.embeddings.word_embeddings
+
+    def get_output_embeddings(self):
+        return self.cls.predictions.decoder
+
+    def set_output_embeddings(self, new_embeddings):
+        self.cls.predictions.decoder = new_embeddings
+
+    def gather_seq_out_by_pos(self, seq, pos):
+        return torch.gather(seq, 1, pos.unsqueeze(2).expand(-1, -1, seq.size(-1)))
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
+                inputs_embeds=None, encoder_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, labels=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None, is_decoder=False, mode='multi_modal',
+                return_logits=False, masked_pos=None, reduction='mean', split_lengths=None, past_key_values=None,
+                encoder_kv_index=None):
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        outputs = self.bert(input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids, position_ids=position_ids,
+                            head_mask=head_mask, inputs_embeds=inputs_embeds, encoder_embeds=encoder_embeds,
+                            encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=encoder_attention_mask,
+                            output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                            return_dict=return_dict, is_decoder=is_decoder, mode=mode, split_lengths=split_lengths,
+                            past_key_values=past_key_values, encoder_kv_index=encoder_kv_index)
+        sequence_output = outputs[0]
+        if masked_pos is None:
+            raise NotImplementedError("need check!")  # as in the reference (xbert.py:1650)
+        sequence_output = self.gather_seq_out_by_pos(sequence_output, masked_pos)
+        prediction_scores = self.cls(sequence_output)
+        if return_logits:
+            return prediction_scores
+        masked_lm_loss = None
+        if labels is not None:
+            masked_lm_loss = F.cross_entropy(prediction_scores.view(-1, self.config.vocab_size), labels.view(-1))
+        if not return_dict:
+            output = (prediction_scores,) + outputs[2:]
+            return ((masked_lm_loss,) + output) if masked_lm_loss is not None else output
+        return MaskedLMOutput(loss=masked_lm_loss, logits=prediction_scores, hidden_states=outputs.hidden_states,
+                              attentions=None)

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — X2VLM-base pre-training step (ITC + ITM + MLM + bbox) on synthetic data, bf16, N GPUs of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework
+    torchrun ... bench.py --gpus N --steps K --warmup W      # one rank per GPU, NCCL
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port)
+
+One "step" = Pretrain.py:run_mixed_iter semantics on one synthetic batch per GPU:
+zero_grad -> image iteration (64 image-text pairs: ITC+ITM+MLM) + region iteration (64 region-text samples over
+26 images: ITC+ITM+MLM+bbox) summed -> one backward (bucketed all-reduce overlapped) -> clip 1.0 -> AdamW.
+pairs/step/GPU = 128.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs (fwd+bwd, 2 FLOP / MAC) of the reference algorithm, SURVEY.md §8d
+FLOP_IMAGE_PAIR = 231.4e9            # image iteration, per pair
+FLOP_REGION_SAMPLE = 3 * 48.92e9     # region iteration, per region-text sample (text x2, fusion x5, head)
+FLOP_VISION_IMAGE = 3 * 35.13e9      # + vision once per unique region image
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batches(batch, n_img, rank, pin):
+    from x2vlm_b200 import synth
+    ib = synth.image_text_batch(batch, 40, seed=1234 + rank)
+    rb = synth.region_batch(n_img, batch, 40, seed=4321 + rank)
+    if pin:
+        ib = {k: v.pin_memory() for k, v in ib.items()}
+        rb = {k: v.pin_memory() for k, v in rb.items()}
+    return ib, rb
+
+
+def to_dev(d, dev):
+    return {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+
+
+def nbytes(d):
+    return sum(v.numel() * v.element_size() for v in d.values())
+
+
+def run_ours(args):
+    from x2vlm_b200 import accelerator, ops, pretrain
+    from x2vlm_b200 import functional as XF
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = pretrain.XVLM(pretrain.base_config())
+    acc = accelerator.X2kDDPAccelerator({"lr": 1e-4, "weight_decay": 0.01, "bucket_mb": args.bucket_mb})
+    ddp, opt, _ = acc.set_up(model, None, None, local, world, rank)
+    ddp.train()
+    XF.manual_seed(1234 + rank)
+    B, n_img = args.batch, args.region_images
+    ib_h, rb_h = make_batches(B, n_img, rank, pin=True)
+    if args.image_only:
+        rb_h = None
+
+    def step(ib, rb, read_loss):
+        with torch.no_grad():
+            ddp.module.temp.clamp_(0.001, 0.5)  # Pretrain.py:327-328
+        opt.zero_grad()
+        losses = ddp.module.forward_mixed(ib, rb)
+        loss = ddp.module.total_loss(losses)
+        acc.backward_step(loss, opt)
+        acc.optimizer_step(opt, ddp, 1.0)
+        opt.step()
+        return float(loss) if read_loss else loss
+
+    def timed(n, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        st.record()
+        last = None
+        for _ in range(n):
+            if e2e:
+                last = step(to_dev(ib_h, dev), to_dev(rb_h, dev) if rb_h is not None else None, True)
+            else:
+                last = step(ib_d, rb_d, False)
+        en.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([st.elapsed_time(en)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ops.launch_count() - l0, float(last)
+
+    ib_d, rb_d = to_dev(ib_h, dev), (to_dev(rb_h, dev) if rb_h is not None else None)
+    for _ in range(max(args.warmup, 3)):
+        step(ib_d, rb_d, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, loss_v = timed(args.steps, e2e=False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, loss_e = timed(args.steps, e2e=True)
+
+    pairs_per_step = (B + (B if rb_h is not None else 0)) * world
+    value = pairs_per_step * args.steps / (ms / 1e3)
+    e2e_value = pairs_per_step * args.steps / (ms_e2e / 1e3)
+    flop_step_gpu = B * FLOP_IMAGE_PAIR + ((B * FLOP_REGION_SAMPLE + n_img * FLOP_VISION_IMAGE) if rb_h is not None else 0.0)
+    burst, sustained, hbm, src = peaks()
+    step_tflops = flop_step_gpu * args.steps / (ms / 1e3) / 1e12  # per GPU (ms is the max over ranks)
+
+    out = None
+    if rank == 0:
+        roof = dominant_kernel_roofline(dev, B + (n_img if rb_h is not None else 0), burst, src)
+        cpu = cpu_baseline(sample_steps=2) if (world == 1 and not args.no_cpu_baseline) else None
+        out = {
+            "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; "
+                                   "random-init weights" % (B, "" if rb_h is not None else " image iteration only"),
+                       "global_batch": B * world, "pairs_per_step_per_gpu": pairs_per_step // world,
+                       "region_images_per_gpu": n_img if rb_h is not None else 0, "seq_len": 40, "image_res": 224,
+                       "parallelism": "dp%d" % world, "optimizer": "AdamW + clip 1.0 (flat fused)",
+                       "l2": "per-step working set (tens of GB of activations, 3 GB params/grads) >> 126 MB L2; no flush needed",
+                       "loss_last_step": loss_v,
+                       "algorithmic_tflop_per_step_per_gpu": flop_step_gpu / 1e12,
+                       "step_tflops_per_gpu": step_tflops,
+                       "step_frac_of_%s_sustained_bf16_peak" % src: step_tflops / sustained},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": nbytes(ib_h) + (nbytes(rb_h) if rb_h is not None else 0), "d2h_bytes_per_step": 4,
+                    "loss_last_step": loss_e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def dominant_kernel_roofline(dev, n_images, peak_burst, src):
+    """The dominant kernel is the tcgen05 GEMM; time its largest instance of the step (vision fc1:
+    [n_images*197, 768] x [768 -> 3072], bias + GELU + pre-activation epilogue) live with CUDA events."""
+    from x2vlm_b200 import ops
+    from x2vlm_b200._capi import ACT_GELU
+    M, N, K = n_images * 197, 3072, 768
+    a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev)
+    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(o)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(13):
+        flush.zero_()  # > L2: cold operands each launch
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        ops.gemm(a, w, M, N, K, bias=bias, act=ACT_GELU, preact_out=pre, out_bf16=o)
+        en.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(st.elapsed_time(en))
+    ms = statistics.median(times)
+    tf = 2.0 * M * N * K / (ms / 1e3) / 1e12
+    return {"kernel": "x2k gemm_tcgen05_kernel<256,K,K> vision fc1 %dx%dx%d bias+GELU" % (M, N, K), "bound": "tensor",
+            "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst, "peak_source": src + " (burst)",
+            "launch_ms": ms, "traffic": None}
+
+
+def oracle_step_fn(batch_i, batch_r, threads):
+    """fwd + bwd + AdamW of the reference algorithm (oracle/restate.py, fp32, torch CPU) on a small mixed batch."""
+    from oracle import restate
+    from x2vlm_b200 import pretrain, synth
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = pretrain.XVLM(pretrain.base_config())  # parameter container only (CPU, never forwarded)
+    sd = {k: v for k, v in m.state_dict().items()}
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    full = dict(sd); full.update(leaves)
+    full["text_encoder.cls.predictions.decoder.weight"] = full["text_encoder.bert.embeddings.word_embeddings.weight"]
+    full["text_encoder.cls.predictions.decoder.bias"] = full["text_encoder.cls.predictions.bias"]
+    params = list({id(v): v for v in leaves.values()}.values())
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
+    ib = synth.image_text_batch(batch_i, 40, seed=1234)
+    rb = synth.region_batch(max(1, batch_r // 2), batch_r, 40, seed=4321) if batch_r else None
+    shp = restate.Shapes()
+
+    def step():
+        opt.zero_grad()
+        li = restate.pretrain_forward(full, shp, ib["image"], ib["text_ids"], ib["text_atts"], ib["text_ids_masked"],
+                                      ib["masked_pos"], ib["masked_ids"], *synth.hard_negative_indices(batch_i, 1), train=True)
+        loss = sum(li.values())
+        if rb is not None:
+            lr_ = restate.pretrain_forward(full, shp, rb["image"], rb["text_ids"], rb["text_atts"], rb["text_ids_masked"],
+                                           rb["masked_pos"], rb["masked_ids"], *synth.hard_negative_indices(batch_r, 2),
+                                           image_atts=rb["image_atts"], idx_to_group_img=rb["idx_to_group_img"],
+                                           target_bbox=rb["target_bbox"], is_image=rb["is_image"], ret_bbox_loss=True, train=True)
+            loss = loss + sum(lr_.values())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return float(loss)
+
+    return step, batch_i + batch_r
+
+
+def cpu_baseline(sample_steps=2, batch_i=4, batch_r=4):
+    threads = os.cpu_count() or 1
+    step, pairs = oracle_step_fn(batch_i, batch_r, threads)
+    step(); step()  # warm-up (first steps pay allocator / lazy-init costs)
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": pairs * sample_steps / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "%d steps of the mixed step at batch %d image + %d region pairs (fp32, torch CPU, oracle/restate.py: "
+                      "the reference is Python and cannot travel to the GPU box)" % (sample_steps, batch_i, batch_r)}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's own CPU path on this box's host cores.  /root/reference is a Python
+    tree that does not exist on the GPU box, so the timed code is the oracle port (oracle/restate.py), which
+    tests/test_oracle_vs_reference.py pins against the unmodified reference."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    bi, br = 4, (0 if args.image_only else 4)
+    step, pairs = oracle_step_fn(bi, br, threads)
+    for _ in range(min(args.warmup, 2)):
+        step()
+    n = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = time.perf_counter() - t0
+    v = pairs * n / dt
+    sample = "each step = mixed step on %d image + %d region pairs (bounded sample of the batch-64 workload), fp32, %d threads" % (bi, br, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": dt / n * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok; CPU sample", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--region-images", type=int, default=26)
+    ap.add_argument("--image-only", action="store_true")
+    ap.add_argument("--bucket-mb", type=float, default=48.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,255 @@
+"""GPU parity tests of the C-ABI kernels (called through x2vlm_b200.ops -> libx2k.so) against fp32 torch
+restatements of the cited reference lines and the numpy Philox oracle.  Tolerances: operands are bf16, all
+accumulation is fp32, so results are compared with the fp32 reference evaluated on the SAME bf16-rounded
+inputs; bound = a few bf16 ulps of the output magnitude (stated per test)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _bf(x):
+    return x.bfloat16()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 328, 200), (12608, 768, 768), (394, 2304, 768)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
+    from x2vlm_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = _bf(torch.randn(M, K, device=dev, generator=g)); B = _bf(torch.randn(N, K, device=dev, generator=g))
+    ref = A.float() @ B.float().t()
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    for tn in (128, 256):
+        out = torch.full((M, N), float("nan"), device=dev)
+        ops.gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, out_f32=out, tile_n=tn)
+        # fp32 accumulation of exact bf16 products: only summation-order error remains
+        assert (out - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() * math.sqrt(K / 64)
+
+
+def test_gemm_epilogues(dev):
+    from x2vlm_b200 import ops
+    from x2vlm_b200._capi import ACT_GELU, ACT_GELU_BWD
+    from oracle import philox
+    M, N, K = 394, 768, 768
+    g = torch.Generator(device=dev).manual_seed(0)
+    A = _bf(torch.randn(M, K, device=dev, generator=g)); W = _bf(torch.randn(N, K, device=dev, generator=g) * 0.05)
+    bias = torch.randn(N, device=dev, generator=g); gamma = torch.randn(N, device=dev, generator=g)
+    res = torch.randn(M, N, device=dev, generator=g); rs = torch.rand(2, device=dev, generator=g) + 0.5
+    acc = A.float() @ W.float().t()
+    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(o)
+    ops.gemm(A, W, M, N, K, bias=bias, act=ACT_GELU, preact_out=pre, out_bf16=o)
+    assert (pre.float() - (acc + bias)).abs().max() < 0.04  # bf16 rounding of |x| <= 8
+    assert (o.float() - torch.nn.functional.gelu(acc + bias)).abs().max() < 0.04
+    o32 = torch.empty(M, N, device=dev)
+    ops.gemm(A, W, M, N, K, bias=bias, gamma=gamma, row_scale=rs, rows_per_scale=197, residual=res, out_f32=o32)
+    ref = res + (acc + bias) * gamma * rs.repeat_interleave(197)[:, None]
+    assert (o32 - ref).abs().max() < 1e-4 * ref.abs().max()
+    h = _bf(torch.randn(M, N, device=dev, generator=g))
+    ops.gemm(A, W, M, N, K, act=ACT_GELU_BWD, aux=h, out_bf16=o)
+    hf = h.float().requires_grad_(True); torch.nn.functional.gelu(hf).sum().backward()
+    assert (o.float() - acc * hf.grad).abs().max() < 0.02 * (acc * hf.grad).abs().max()
+    o32b = o32.clone()
+    ops.gemm(A, W, M, N, K, accumulate=True, out_f32=o32b)
+    assert (o32b - (o32 + acc)).abs().max() < 1e-4 * o32.abs().max()
+    # dropout: the exact Philox mask of the oracle
+    ops.gemm(A, W, M, N, K, dropout_p=0.1, dropout_seed=1234, dropout_offset=77, out_f32=o32)
+    keep = torch.from_numpy(philox.keep_scale(1234, 77, M * N, 0.1)).view(M, N).to(dev)
+    assert (o32 - acc * keep).abs().max() < 1e-4 * acc.abs().max()
+
+
+@pytest.mark.parametrize("M,D,eps", [(12608, 768, 1e-6), (2560, 768, 1e-12), (333, 1024, 1e-6), (77, 128, 1e-5)])
+def test_layernorm(dev, M, D, eps):
+    from x2vlm_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M)
+    x = torch.randn(M, D, device=dev, generator=g) * 2 + 0.5
+    w = torch.randn(D, device=dev, generator=g); b = torch.randn(D, device=dev, generator=g)
+    yb = torch.empty(M, D, device=dev, dtype=torch.bfloat16); yf = torch.empty(M, D, device=dev)
+    mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
+    ops.layernorm_fwd(x, w, b, eps, y_bf16=yb, y_f32=yf, mean=mean, rstd=rstd)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), wr, br, eps)
+    assert (yf - ref).abs().max() < 1e-4 and (yb.float() - ref).abs().max() < 0.05
+    dy = torch.randn(M, D, device=dev, generator=g); dyb = _bf(torch.randn(M, D, device=dev, generator=g))
+    res = torch.randn(M, D, device=dev, generator=g)
+    ref.backward(dy + dyb.float())
+    dx = torch.empty(M, D, device=dev); dw = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
+    ops.layernorm_bwd((dy, dyb), x, w, mean, rstd, dx, dw, db, dx_residual=res)
+    assert (dx - (xr.grad + res)).abs().max() < 1e-3
+    assert (dw - wr.grad).abs().max() < 1e-3 * wr.grad.abs().max() and (db - br.grad).abs().max() < 1e-3 * br.grad.abs().max()
+
+
+def test_scale_cast_colsum_and_friends(dev):
+    from x2vlm_b200 import ops
+    from oracle import philox
+    M, N = 1970, 768
+    g = torch.Generator(device=dev).manual_seed(3)
+    dx = torch.randn(M, N, device=dev, generator=g); gamma = torch.randn(N, device=dev, generator=g)
+    rs = torch.rand(10, device=dev, generator=g) + 0.5; y = _bf(torch.randn(M, N, device=dev, generator=g))
+    gb = torch.empty(M, N, device=dev, dtype=torch.bfloat16); dbias = torch.zeros(N, device=dev); dgamma = torch.zeros(N, device=dev)
+    ops.scale_cast_colsum(dx, M, N, g_bf16=gb, gamma=gamma, row_scale=rs, rows_per_scale=197, dropout_p=0.1, dropout_seed=5,
+                          dropout_offset=9, y_bf16=y, dbias=dbias, dgamma=dgamma)
+    keep = torch.from_numpy(philox.keep_scale(5, 9, M * N, 0.1)).view(M, N).to(dev)
+    rsx = rs.repeat_interleave(197)[:, None]
+    gref = dx * rsx * gamma * keep
+    assert (gb.float() - gref).abs().max() <= 2 ** -8 * gref.abs().max()  # one bf16 rounding
+    assert (dbias - gref.sum(0)).abs().max() < 1e-3 * gref.sum(0).abs().max()
+    dgref = (dx * rsx * y.float()).sum(0)
+    assert (dgamma - dgref).abs().max() < 1e-3 * dgref.abs().max()
+    xb = _bf(torch.randn(5120, 2304, device=dev, generator=g)); dc = torch.zeros(2304, device=dev)
+    ops.colsum_bf16(xb, 5120, 2304, dc)
+    assert (dc - xb.float().sum(0)).abs().max() < 1e-3 * xb.float().sum(0).abs().max()
+    src = _bf(torch.randn(11, 197 * 64, device=dev, generator=g)); idx = torch.tensor([2, 0, 2, 1, 1, 2, 0, 0, 3, 2, 1], device=dev, dtype=torch.int32)
+    out = torch.empty(5, 197 * 64, device=dev, dtype=torch.bfloat16)
+    ops.segment_sum_bf16(src, idx, 5, out)
+    ref = torch.zeros(5, 197 * 64, device=dev).index_add_(0, idx.long(), src.float())
+    assert (out.float() - ref).abs().max() <= 2 ** -7 * ref.abs().max() and out[4].abs().max() == 0
+
+
+def _attn_ref(q, k, v, scale, bias=None, mask=None, keep=None):
+    """fp32 restatement of models/beit2.py:135-159 / models/xbert.py:364-410 on [B,H,L,64] tensors."""
+    s = (q @ k.transpose(-1, -2)) * scale
+    if bias is not None:
+        s = s + bias
+    if mask is not None:
+        s = s + mask
+    p = s.softmax(-1)
+    pd = p if keep is None else p * keep
+    return pd @ v, p
+
+
+def _heads(x, B, L, H):
+    return x.view(B, L, H, 64).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("case", ["beit", "text", "text3d", "cross_shared", "text_dropout", "n256"])
+def test_attention_fwd_bwd(dev, case):
+    from x2vlm_b200 import ops
+    from oracle import philox
+    g = torch.Generator(device=dev).manual_seed(11)
+    H = 12
+    kv_index = None
+    p_drop = 0.0
+    if case == "beit":
+        B, Lq, Lk, n_kv = 3, 197, 197, 3
+    elif case == "n256":
+        B, Lq, Lk, n_kv, H = 2, 256, 256, 2, 2
+    elif case == "cross_shared":
+        B, Lq, Lk, n_kv = 7, 40, 197, 3
+        kv_index = torch.tensor([0, 2, 1, 1, 0, 2, 2], device=dev, dtype=torch.int32)
+    else:
+        B, Lq, Lk, n_kv = 5, 40, 40, 5
+    if case == "text_dropout":
+        p_drop = 0.1
+    D = H * 64
+    ld = ops.pad16(Lk)
+    scale = 0.125
+    qkv = _bf(torch.randn(B * Lq, 3 * D, device=dev, generator=g))
+    if Lq == Lk and kv_index is None:
+        qv, kv_, vv = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    else:
+        kvbuf = _bf(torch.randn(n_kv * Lk, 2 * D, device=dev, generator=g))
+        qv, kv_, vv = qkv[:, :D], kvbuf[:, :D], kvbuf[:, D:]
+    bias = mask = None
+    per_query = False
+    if case in ("beit", "n256"):
+        bias = torch.zeros(H, Lq, ld, device=dev); bias[:, :, :Lk] = torch.randn(H, Lq, Lk, device=dev, generator=g)
+    if case in ("text", "text_dropout", "cross_shared"):
+        m01 = (torch.rand(B, Lk, device=dev, generator=g) > 0.3).float(); m01[:, 0] = 1
+        mask = torch.zeros(B, ld, device=dev); mask[:, :Lk] = (1 - m01) * -10000.0
+    if case == "text3d":
+        m01 = torch.tril(torch.ones(Lq, Lk, device=dev)).expand(B, -1, -1)
+        mask = torch.zeros(B, Lq, ld, device=dev); mask[:, :, :Lk] = (1 - m01) * -10000.0
+        per_query = True
+    o = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, Lq, device=dev)
+    kw = dict(kv_index=kv_index, n_kv=n_kv, bias=bias, mask=mask, mask_per_query=per_query, dropout_p=p_drop, dropout_seed=42,
+              dropout_offset=1000)
+    ops.attn_fwd(qv, kv_, vv, B, H, Lq, Lk, scale, o, lse, **kw)
+    # ---- fp32 reference on the same bf16 inputs ----
+    sel = kv_index.long() if kv_index is not None else torch.arange(B, device=dev)
+    qf = _heads(qv.float(), B, Lq, H).requires_grad_(True)
+    kf = _heads(kv_.float().reshape(n_kv, Lk, D)[sel].reshape(B * Lk, D), B, Lk, H).detach().requires_grad_(True)
+    vf = _heads(vv.float().reshape(n_kv, Lk, D)[sel].reshape(B * Lk, D), B, Lk, H).detach().requires_grad_(True)
+    bias_r = bias[:, :, :Lk].unsqueeze(0).clone().requires_grad_(True) if bias is not None else None
+    mask_r = None
+    if mask is not None:
+        mask_r = mask[:, None, :, :Lk] if per_query else mask[:, None, None, :Lk]
+    keep = None
+    if p_drop > 0:
+        keep = torch.from_numpy(philox.keep_scale(42, 1000, B * H * Lq * ld, p_drop)).view(B, H, Lq, ld)[..., :Lk].to(dev)
+    oref, pref = _attn_ref(qf, kf, vf, scale, bias_r, mask_r, keep)
+    o_cmp = _heads(o.float(), B, Lq, H)
+    tol = 2e-2  # P is rounded to bf16 before P·V: relative error ~2^-8 per term, outputs are O(1)
+    assert (o_cmp - oref).abs().max().item() < tol * max(1.0, oref.abs().max().item())
+    sref = (qf @ kf.transpose(-1, -2)) * scale + (bias_r if bias_r is not None else 0) + (mask_r if mask_r is not None else 0)
+    lse_ref = torch.logsumexp(sref, -1) / math.log(2.0)
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+    # ---- backward ----
+    do = _bf(torch.randn(B * Lq, D, device=dev, generator=g))
+    dq = torch.full((B * Lq, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    dkv = torch.full((B * Lk, 2 * D), float("nan"), device=dev, dtype=torch.bfloat16)
+    ds = torch.zeros(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if bias is not None else None
+    ops.attn_bwd(qv, kv_, vv, B, H, Lq, Lk, scale, o, lse, do, dq, dkv[:, :D], dkv[:, D:], ds_out=ds, **kw)
+    oref.backward(_heads(do.float(), B, Lq, H))
+    for name, got, want in (("dq", _heads(dq.float(), B, Lq, H), qf.grad), ("dk", _heads(dkv[:, :D].float(), B, Lk, H), kf.grad),
+                            ("dv", _heads(dkv[:, D:].float(), B, Lk, H), vf.grad)):
+        assert not torch.isnan(got).any(), name
+        err = (got - want).abs().max().item()
+        assert err < 3e-2 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
+    if bias is not None:
+        dbias = ds.float().sum(0)[:, :, :Lk]
+        want = bias_r.grad[0]
+        assert (dbias - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
+
+
+def test_relpos_gather_scatter(dev):
+    from x2vlm_b200 import ops
+    from oracle import restate
+    N, H, R = 197, 12, 732
+    g = torch.Generator(device=dev).manual_seed(2)
+    table = torch.randn(R, H, device=dev, generator=g)
+    index = restate.relative_position_index((14, 14)).to(dev)
+    out = torch.empty(H, N, 208, device=dev)
+    ops.relpos_bias_gather(table, index, N, H, out)
+    ref = table[index.view(-1)].view(N, N, H).permute(2, 0, 1)
+    assert torch.equal(out[:, :, :N], ref) and out[:, :, N:].abs().max() == 0
+    ds = _bf(torch.randn(4, H, N, 208, device=dev, generator=g))
+    dt = torch.zeros(R, H, device=dev)
+    ops.relpos_bias_scatter(ds, 4, H, N, index, dt)
+    want = torch.zeros(R, H, device=dev).index_add_(0, index.view(-1), ds.float().sum(0)[:, :, :N].permute(1, 2, 0).reshape(N * N, H))
+    assert (dt - want).abs().max() < 1e-3 * want.abs().max()
+
+
+def test_flat_adamw_matches_torch(dev):
+    from x2vlm_b200 import ops
+    n = 100000
+    g = torch.Generator(device=dev).manual_seed(4)
+    p = torch.randn(n, device=dev, generator=g); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    pb = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    cuts = [0, 30000, 70000, n]; lrs = [1e-3, 2e-3, 5e-4]; wds = [0.01, 0.0, 0.05]
+    prefs = [p[a:b].clone().requires_grad_(True) for a, b in zip(cuts[:-1], cuts[1:])]
+    opt = torch.optim.AdamW([{"params": [pp], "lr": lr, "weight_decay": wd} for pp, lr, wd in zip(prefs, lrs, wds)],
+                            betas=(0.9, 0.98), eps=1e-8)
+    seg_end = torch.tensor(cuts[1:], device=dev, dtype=torch.int64)
+    seg_lr = torch.tensor(lrs, device=dev); seg_wd = torch.tensor(wds, device=dev); gs = torch.tensor([0.5], device=dev)
+    step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+    for _ in range(3):
+        gr = torch.randn(n, device=dev, generator=g)
+        for pp, a, b in zip(prefs, cuts[:-1], cuts[1:]):
+            pp.grad = gr[a:b].clone() * 0.5
+        opt.step()
+        step_dev += 1
+        ops.adamw_flat(p, gr, m, v, pb, n, seg_end, seg_lr, seg_wd, 0.9, 0.98, 1e-8, step_dev=step_dev, grad_scale=gs)
+    assert (p - torch.cat([pp.detach() for pp in prefs])).abs().max() < 1e-5
+    assert torch.equal(pb, p.bfloat16())
+    out = torch.zeros(1, device=dev); ops.sumsq(p, out)
+    assert abs(out.item() - (p.double() ** 2).sum().item()) < 1e-4 * out.item()

@@ -384,10 +384,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x16(trow + TM_DP + c * 16, dp);
         float pr[16], ds[16];
         const bool chunk_live = qvalid && (k0 < p.Lk);
+        float add[16];
+        if (chunk_live) load_additive(p, bias_row, mask_row, k0, add);
+        tmem_wait_ld();  // .sync.aligned: must be reached by the whole warp, never inside a divergent branch
         if (chunk_live) {
-          float add[16];
-          load_additive(p, bias_row, mask_row, k0, add);
-          tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float t = fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]);
@@ -412,7 +412,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
           }
         } else {
-          tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
         }

@@ -23,6 +23,14 @@ def rel_l2(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
 
 
+def grad_ok(name, got, want, tol):
+    """rel-L2 check; gradients that are zero in exact arithmetic (the key bias: softmax is invariant to a per-row
+    shift of the scores, so d/d(key.bias) == 0) are held to an absolute bound instead."""
+    if "key.bias" in name or want.float().norm().item() < 1e-7 * want.numel() ** 0.5:
+        return got.float().abs().max().item() < 2e-3
+    return rel_l2(got, want) < tol
+
+
 @pytest.fixture(scope="module")
 def dev():
     return torch.device("cuda:0")
@@ -144,7 +152,7 @@ def test_bert_fusion_layer_backward_vs_oracle(dev):
     for n, p in layer.named_parameters():
         want = sd["bert.encoder.layer.2." + n].grad
         assert p.grad is not None, n
-        assert rel_l2(p.grad.cpu(), want) < 3e-2, (n, rel_l2(p.grad.cpu(), want))
+        assert grad_ok(n, p.grad.cpu(), want, 3e-2), (n, rel_l2(p.grad.cpu(), want))
 
 
 @pytest.fixture(scope="module")
@@ -236,10 +244,13 @@ def test_xvlm_gradients_vs_oracle(dev, xvlm_pair):
         if w is None or w.norm() == 0:
             continue
         assert p.grad is not None, n
+        if "key.bias" in n:
+            assert grad_ok(n, p.grad.cpu(), w, 0), n
+            continue
         r = rel_l2(p.grad.cpu(), w)
         worst = max(worst, (r, n))
         checked += 1
-    assert checked > 550
+    assert checked > 480
     assert worst[0] < 6e-2, worst  # 30 bf16 layers deep; per-layer checks above hold 3e-2
 
 

@@ -1,0 +1,71 @@
+"""2-GPU NCCL test of the bucketed, backward-overlapped gradient all-reduce (needs >= 2 CUDA devices; skipped otherwise).
+
+Oracle for DP: gradients after `backward_step` on W ranks == the mean over ranks of the gradients each
+rank computes locally with the all-reduce switched off (apex `gradient_average=True` semantics)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from x2vlm_b200 import accelerator, pretrain, synth
+    from x2vlm_b200 import functional as XF
+    torch.manual_seed(0)
+    m = pretrain.XVLM(pretrain.base_config())
+    acc = accelerator.X2kDDPAccelerator({"lr": 1e-4, "weight_decay": 0.01, "bucket_mb": 48.0})
+    ddp, opt, _ = acc.set_up(m, None, None, rank, world, rank)
+    ddp.eval()  # deterministic (no dropout / drop path): both passes see identical math
+    ib = {k: v.to(dev) for k, v in synth.image_text_batch(4, 40, seed=100 + rank).items()}
+    neg = tuple(t.to(dev) for t in synth.hard_negative_indices(4, 5))
+
+    def run(reduce):
+        opt.zero_grad()
+        loss = ddp.module.total_loss(ddp.module.forward_mixed(ib, None, neg))
+        if reduce:
+            order = acc.backward_step(loss, opt)
+        else:
+            ws, acc.bucketer.world_size = acc.bucketer.world_size, 1
+            order = acc.backward_step(loss, opt)
+            acc.bucketer.world_size = ws
+        torch.cuda.synchronize()
+        return acc.arena.grad.clone(), order
+
+    local, _ = run(False)
+    want = local.clone()
+    dist.all_reduce(want)
+    want /= world
+    got, order = run(True)
+    err = ((got - want).norm() / want.norm()).item()
+    # params were broadcast from rank 0: flat buffers identical across ranks
+    flat0 = acc.arena.flat.clone()
+    dist.broadcast(flat0, 0)
+    same = bool(torch.equal(flat0, acc.arena.flat))
+    q.put((rank, err, same, len(order), order[0], local.norm().item() > 0))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_bucketed_allreduce_nccl_2gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 100
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=600) for _ in procs]
+    [p.join(60) for p in procs]
+    for rank, err, same, n_buckets, first, nonzero in res:
+        assert nonzero and same
+        assert err < 1e-5, (rank, err)            # fp32 sum of two ranks, then x0.5: exact up to atomics order
+        assert n_buckets >= 15 and first > n_buckets // 2   # later parameters' buckets are reduced first (overlap)

@@ -97,6 +97,8 @@ typedef struct X2kGemmArgs {
   int64_t ld_out_f32;
   int32_t tile_n;          /* 0 = auto, else 128 or 256 */
   int32_t max_ctas;        /* 0 = all SMs */
+  int32_t split_k;         /* 0 = auto (split K over CTAs for wgrad-shaped GEMMs with a plain fp32 output,
+                              accumulated with atomics), 1 = never, n = force n slices */
 } X2kGemmArgs;
 
 int x2k_gemm(const X2kGemmArgs* args, void* stream);

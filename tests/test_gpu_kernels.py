@@ -36,6 +36,23 @@ def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
         assert (out - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() * math.sqrt(K / 64)
 
 
+def test_gemm_split_k_wgrad(dev):
+    """wgrad-shaped GEMM (small output, K = tokens): split-K with atomic fp32 accumulation."""
+    from x2vlm_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(7)
+    rows, n_out, n_in = 17730, 768, 768
+    dy = _bf(torch.randn(rows, n_out, device=dev, generator=g)); x = _bf(torch.randn(rows, n_in, device=dev, generator=g))
+    ref = dy.float().t() @ x.float()
+    base = torch.randn(n_out, n_in, device=dev, generator=g)
+    for split in (0, 1, 5):
+        out = base.clone()
+        ops.gemm(dy, x, n_out, n_in, rows, a_mn=True, b_mn=True, out_f32=out, accumulate=True, split_k=split)
+        assert (out - (base + ref)).abs().max().item() < 2e-3 * ref.abs().max().item(), split
+        out2 = torch.full((n_out, n_in), float("nan"), device=dev)
+        ops.gemm(dy, x, n_out, n_in, rows, a_mn=True, b_mn=True, out_f32=out2, split_k=split)
+        assert (out2 - ref).abs().max().item() < 2e-3 * ref.abs().max().item(), split
+
+
 def test_gemm_epilogues(dev):
     from x2vlm_b200 import ops
     from x2vlm_b200._capi import ACT_GELU, ACT_GELU_BWD

@@ -37,7 +37,7 @@ class X2kGemmArgs(ctypes.Structure):
         ("accumulate", c_int32),
         ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
         ("out_f32", c_void_p), ("ld_out_f32", c_int64),
-        ("tile_n", c_int32), ("max_ctas", c_int32),
+        ("tile_n", c_int32), ("max_ctas", c_int32), ("split_k", c_int32),
     ]
 
 

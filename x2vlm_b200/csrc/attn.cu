@@ -137,57 +137,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
 
   // ---- softmax over the row owned by this thread ----
+  // Pass 1 forms t = scale·qk + bias + mask (log2 domain) 64 columns at a time — all bias/mask loads of a
+  // super-chunk are issued together so their latency overlaps — tracks the row max and writes t back to TMEM;
+  // pass 2 re-reads t only (no second trip to global memory), exponentiates and emits P.
   const int q = qt * 128 + row;
   const bool qvalid = q < p.Lq;
+  const bool warp_live = (qt * 128 + warp * 32) < p.Lq;  // warp-uniform: dead warps own no valid query row
   const float* bias_row = (p.bias && qvalid) ? p.bias + h * p.bias_h_stride + q * p.bias_q_stride : nullptr;
   const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
   const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const int nchunk = Lk_pad >> 4;
-  float mx = -INFINITY;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t s[16];
-    tmem_ld_32x16(trow + c * 16, s);
-    float add[16];
-    load_additive(p, bias_row, mask_row, c * 16, add);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float t = (c * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]) : -INFINITY;
-      mx = fmaxf(mx, t);
-    }
-  }
-  if (mx == -INFINITY) mx = 0.f;
-  float sum = 0.f;
-  const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-  const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * Lk_pad;
   const uint32_t sP_addr = smem_u32(sP);
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t s[16];
-    tmem_ld_32x16(trow + c * 16, s);
-    float add[16];
-    load_additive(p, bias_row, mask_row, c * 16, add);
-    tmem_wait_ld();
-    float pr[16];
+  float mx = -INFINITY, sum = 0.f;
+  if (warp_live) {
+    for (int c0 = 0; c0 < nchunk; c0 += 4) {
+      uint32_t s[4][16];
+      float add[4][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float t = (c * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]) : -INFINITY;
-      pr[j] = exp2f(t - mx);
-      sum += pr[j];
-    }
-    if (p.dropout_p > 0.f) {
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < nchunk) tmem_ld_32x16(trow + (c0 + u) * 16, s[u]);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + c * 16 + j) >> 2));
-        pr[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
-        pr[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
-        pr[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
-        pr[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < nchunk) load_additive(p, bias_row, mask_row, (c0 + u) * 16, add[u]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c0 + u < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t = ((c0 + u) * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[u][j]), p.scale_log2, add[u][j]) : -INFINITY;
+            mx = fmaxf(mx, t);
+            s[u][j] = __float_as_uint(t);
+          }
+          tmem_st_32x16(trow + (c0 + u) * 16, s[u]);
+        }
       }
     }
-    st_shared_v4(sP_addr + swz_off(row, c * 16), pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
-                 pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
-    st_shared_v4(sP_addr + swz_off(row, c * 16 + 8), pack_bf16x2(pr[8], pr[9]), pack_bf16x2(pr[10], pr[11]),
-                 pack_bf16x2(pr[12], pr[13]), pack_bf16x2(pr[14], pr[15]));
+    tmem_wait_st();
+    if (mx == -INFINITY) mx = 0.f;
+    const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+    const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * Lk_pad;
+    for (int c0 = 0; c0 < nchunk; c0 += 2) {
+      uint32_t s[2][16];
+      tmem_ld_32x16(trow + c0 * 16, s[0]);
+      if (c0 + 1 < nchunk) tmem_ld_32x16(trow + (c0 + 1) * 16, s[1]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (c0 + u < nchunk) {
+          const int c = c0 + u;
+          float pr[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            pr[j] = exp2f(__uint_as_float(s[u][j]) - mx);
+            sum += pr[j];
+          }
+          if (p.dropout_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + c * 16 + j) >> 2));
+              pr[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
+              pr[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
+              pr[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
+              pr[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+            }
+          }
+          st_shared_v4(sP_addr + swz_off(row, c * 16), pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
+                       pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
+          st_shared_v4(sP_addr + swz_off(row, c * 16 + 8), pack_bf16x2(pr[8], pr[9]), pack_bf16x2(pr[10], pr[11]),
+                       pack_bf16x2(pr[12], pr[13]), pack_bf16x2(pr[14], pr[15]));
+        }
+      }
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -211,7 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   mbar_wait(bar_mma, 1);
   tc_fence_after();
   {
-    const float inv = 1.0f / sum;
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
     uint32_t o[16];
     __nv_bfloat16* dst = p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64;
 #pragma unroll
@@ -335,11 +356,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
   uint32_t mma_phase = 0;
-  const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
 
   for (int kb = 0; kb < nkb; ++kb) {
+    // valid keys of this block in 16-column chunks: S/dP are only formed (N = nkc*16) and consumed up to there
+    const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
+    const uint32_t idesc_skb = make_idesc_bf16(128, nkc * 16, 0, 0);
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(bar_kv, 2 * 16384);
       tma_load_2d(smem + BWD_SK, &tmap_k, bar_kv, h * 64, kvb * p.Lk + kb * 128);
@@ -354,12 +377,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t ak = sbase + BWD_SK, av = sbase + BWD_SV;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + TM_S, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
+          umma_bf16(tmem + TM_S, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_skb,
                     k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + TM_DP, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024),
-                    idesc_s, k != 0);
+                    idesc_skb, k != 0);
         umma_commit(bar_mma);
       }
       __syncwarp();
@@ -376,59 +399,78 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __nv_bfloat16* ds_row =
           (p.ds_out && qvalid) ? p.ds_out + b * p.ds_b_stride + h * p.ds_h_stride + q * p.ds_q_stride : nullptr;
       const float my_lse = lse2[qb], my_delta = delta[qb];
+      // rows of this q block that any MMA will read as a contraction index, in 16-row groups; a warp whose rows all
+      // lie beyond them has nothing to produce (its P/dS rows only feed dQ rows that are never stored)
+      const bool warp_live = (qb * 128 + warp * 32) < p.Lq;
+      // two 16-column chunks per iteration: their TMEM reads and bias/mask loads are all issued before the wait
+      if (warp_live) {
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int k0 = kb * 128 + c * 16;
-        uint32_t s[16], dp[16];
-        tmem_ld_32x16(trow + TM_S + c * 16, s);
-        tmem_ld_32x16(trow + TM_DP + c * 16, dp);
-        float pr[16], ds[16];
-        const bool chunk_live = qvalid && (k0 < p.Lk);
-        float add[16];
-        if (chunk_live) load_additive(p, bias_row, mask_row, k0, add);
-        tmem_wait_ld();  // .sync.aligned: must be reached by the whole warp, never inside a divergent branch
-        if (chunk_live) {
+        for (int c0 = 0; c0 < nkc; c0 += 2) {
+          uint32_t s[2][16], dp[2][16];
+          float add[2][16];
+          bool live[2];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float t = fmaf(__uint_as_float(s[j]), p.scale_log2, add[j]);
-            pr[j] = (k0 + j < p.Lk) ? exp2f(t - my_lse) : 0.f;
-            ds[j] = __uint_as_float(dp[j]);
-          }
-          if (p.dropout_p > 0.f) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + k0 + j) >> 2));
-              const float k0_ = dropout_keep(r.x, p.dropout_p, inv_keep), k1_ = dropout_keep(r.y, p.dropout_p, inv_keep);
-              const float k2_ = dropout_keep(r.z, p.dropout_p, inv_keep), k3_ = dropout_keep(r.w, p.dropout_p, inv_keep);
-              ds[j] *= k0_; ds[j + 1] *= k1_; ds[j + 2] *= k2_; ds[j + 3] *= k3_;
-              // dS uses the un-dropped P; the P that feeds dV is the dropped one
-              const float p0 = pr[j], p1 = pr[j + 1], p2 = pr[j + 2], p3 = pr[j + 3];
-              ds[j] = p0 * (ds[j] - my_delta); ds[j + 1] = p1 * (ds[j + 1] - my_delta);
-              ds[j + 2] = p2 * (ds[j + 2] - my_delta); ds[j + 3] = p3 * (ds[j + 3] - my_delta);
-              pr[j] = p0 * k0_; pr[j + 1] = p1 * k1_; pr[j + 2] = p2 * k2_; pr[j + 3] = p3 * k3_;
+          for (int u = 0; u < 2; ++u) {
+            if (c0 + u < nkc) {
+              tmem_ld_32x16(trow + TM_S + (c0 + u) * 16, s[u]);
+              tmem_ld_32x16(trow + TM_DP + (c0 + u) * 16, dp[u]);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
           }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
-        }
-        uint32_t pk[8], dk[8];
+          for (int u = 0; u < 2; ++u) {
+            live[u] = qvalid && (c0 + u < nkc);
+            if (live[u]) load_additive(p, bias_row, mask_row, kb * 128 + (c0 + u) * 16, add[u]);
+          }
+          tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
-          dk[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
-        }
-        const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
-        st_shared_v4(sbase + BWD_SP + o0, pk[0], pk[1], pk[2], pk[3]);
-        st_shared_v4(sbase + BWD_SP + o1, pk[4], pk[5], pk[6], pk[7]);
-        st_shared_v4(sbase + BWD_SDS + o0, dk[0], dk[1], dk[2], dk[3]);
-        st_shared_v4(sbase + BWD_SDS + o1, dk[4], dk[5], dk[6], dk[7]);
-        if (ds_row && k0 < p.Lk_pad) {
-          *reinterpret_cast<uint4*>(ds_row + k0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-          *reinterpret_cast<uint4*>(ds_row + k0 + 8) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+          for (int u = 0; u < 2; ++u) {
+            if (c0 + u >= nkc) continue;  // warp-uniform
+            const int c = c0 + u;
+            const int k0 = kb * 128 + c * 16;
+            float pr[16], ds[16];
+            if (live[u]) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float t = fmaf(__uint_as_float(s[u][j]), p.scale_log2, add[u][j]);
+                pr[j] = (k0 + j < p.Lk) ? exp2f(t - my_lse) : 0.f;
+                ds[j] = __uint_as_float(dp[u][j]);
+              }
+              if (p.dropout_p > 0.f) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + k0 + j) >> 2));
+                  const float k0_ = dropout_keep(r.x, p.dropout_p, inv_keep), k1_ = dropout_keep(r.y, p.dropout_p, inv_keep);
+                  const float k2_ = dropout_keep(r.z, p.dropout_p, inv_keep), k3_ = dropout_keep(r.w, p.dropout_p, inv_keep);
+                  // dS uses the un-dropped P; the P that feeds dV is the dropped one
+                  const float p0 = pr[j], p1 = pr[j + 1], p2 = pr[j + 2], p3 = pr[j + 3];
+                  ds[j] = p0 * (ds[j] * k0_ - my_delta); ds[j + 1] = p1 * (ds[j + 1] * k1_ - my_delta);
+                  ds[j + 2] = p2 * (ds[j + 2] * k2_ - my_delta); ds[j + 3] = p3 * (ds[j + 3] * k3_ - my_delta);
+                  pr[j] = p0 * k0_; pr[j + 1] = p1 * k1_; pr[j + 2] = p2 * k2_; pr[j + 3] = p3 * k3_;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
+            }
+            uint32_t pk[8], dk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
+              dk[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
+            }
+            const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
+            st_shared_v4(sbase + BWD_SP + o0, pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(sbase + BWD_SP + o1, pk[4], pk[5], pk[6], pk[7]);
+            st_shared_v4(sbase + BWD_SDS + o0, dk[0], dk[1], dk[2], dk[3]);
+            st_shared_v4(sbase + BWD_SDS + o1, dk[4], dk[5], dk[6], dk[7]);
+            if (ds_row) {
+              *reinterpret_cast<uint4*>(ds_row + k0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+              *reinterpret_cast<uint4*>(ds_row + k0 + 8) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+            }
+          }
         }
       }
       fence_proxy_async_smem();
@@ -441,15 +483,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t ak = sbase + BWD_SK;
         const uint32_t ap = sbase + BWD_SP, ads = sbase + BWD_SDS;
         // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
-        for (int ks = 0; ks < 8; ++ks)
+        const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
+        for (int ks = 0; ks < nkc; ++ks)
           umma_bf16(tmem + TM_DQ + qb * 64, make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                     make_smem_desc(ak + ks * 2048, 8192, 1024), idesc_dq, (kb | ks) != 0);
         // dK += dSᵀ · Q[qb]         (A: dS MN-major over keys, K = query rows; B: Q tile MN-major)
-        for (int ks = 0; ks < 8; ++ks)
+        for (int ks = 0; ks < nqc; ++ks)
           umma_bf16(tmem + TM_DK, make_smem_desc(ads + ks * 2048, 16384, 1024), make_smem_desc(aq + ks * 2048, 8192, 1024),
                     idesc_dkv, (qb | ks) != 0);
         // dV += Pᵀ · dO[qb]
-        for (int ks = 0; ks < 8; ++ks)
+        for (int ks = 0; ks < nqc; ++ks)
           umma_bf16(tmem + TM_DV, make_smem_desc(ap + ks * 2048, 16384, 1024), make_smem_desc(ado + ks * 2048, 8192, 1024),
                     idesc_dkv, (qb | ks) != 0);
         if (qb == nqb - 1) umma_commit(bar_mma);

@@ -185,6 +185,17 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// registers -> TMEM, same lane/column mapping as tmem_ld_32x16
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor, 128-byte swizzle (layout_type 2), descriptor version 1.
 //   lbo/sbo in bytes.  K-major tile [rows][64 bf16]: sbo = 1024 (8 rows x 128 B), lbo unused (1).
 //   MN-major tile, boxes of [k-rows][64 bf16 along MN]: sbo = 1024 (8 k-rows), lbo = byte stride

@@ -54,6 +54,7 @@ struct EpiParams {
   const float* residual;
   int64_t ld_res;
   int accumulate;
+  int split_k;  // >1: work unit = (tile, k-slice), fp32 output accumulated with atomics
   __nv_bfloat16* out_bf16;
   int64_t ld_out_bf16;
   float* out_f32;
@@ -168,6 +169,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.split_k > 1) {
+          atomicAdd(reinterpret_cast<float4*>(dst + j), o);  // red.global.add.v4.f32 (sm_90+)
+          continue;
+        }
         if (p.accumulate) {
           const float4 c = *reinterpret_cast<const float4*>(dst + j);
           o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
@@ -177,7 +182,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+        if (n0 + j < p.N) {
+          if (p.split_k > 1) atomicAdd(dst + j, v[j]);
+          else dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+        }
     }
   }
   if (p.out_bf16) {
@@ -218,8 +226,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int split_k = p.split_k > 1 ? p.split_k : 1;
+  const int kb_per = (k_blocks_total + split_k - 1) / split_k;
+  const int num_tiles = m_tiles * n_tiles * split_k;  // work units: unit = tile * split_k + k-slice
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -252,9 +262,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BLOCK_M;
-        const int n0 = (tile % n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int t = tile / split_k, ks = tile % split_k;
+        const int m0 = (t / n_tiles) * BLOCK_M;
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int kb_end = min(k_blocks_total, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
@@ -289,7 +301,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc_stage * BLOCK_N;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int ks = tile % split_k;
+      const int kb_begin = ks * kb_per, kb_end = min(k_blocks_total, (ks + 1) * kb_per);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -304,10 +318,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                           : make_smem_desc(sa + k * mn_kadv, mn_lbo, mn_sbo);
             const uint64_t db = B_MN == 0 ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
                                           : make_smem_desc(sb + k * mn_kadv, mn_lbo, mn_sbo);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(&tmem_full_bar[acc_stage]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full_bar[acc_stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -323,8 +337,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BLOCK_M;
-      const int n0 = (tile % n_tiles) * BLOCK_N;
+      const int t = tile / split_k;
+      const int m0 = (t / n_tiles) * BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const int m = m0 + quad * 32 + lane;
@@ -378,7 +393,8 @@ int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
   const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   int ctas = sm_count();
   if (a.max_ctas > 0 && a.max_ctas < ctas) ctas = a.max_ctas;
-  if (m_tiles * n_tiles < ctas) ctas = m_tiles * n_tiles;
+  const int units = m_tiles * n_tiles * (ep.split_k > 1 ? ep.split_k : 1);
+  if (units < ctas) ctas = units;
   kern<<<ctas, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -434,7 +450,30 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   ep.dbg_lbo = ep.dbg_sbo = ep.dbg_kadv = 0;
   if (const char* dbg = getenv("X2K_DBG_MN")) sscanf(dbg, "%u,%u,%u", &ep.dbg_lbo, &ep.dbg_sbo, &ep.dbg_kadv);
 
+  // split-K: a wgrad-shaped GEMM (small output, very long K) has fewer tiles than SMs; slice K across CTAs and
+  // accumulate the fp32 output with vector atomics.  Only for the pure (accumulating) fp32 epilogue.
+  ep.split_k = 1;
+  const bool plain_f32 = a.out_f32 && !a.out_bf16 && !a.preact_out && !a.bias && a.act == X2K_ACT_NONE &&
+                         !(a.dropout_p > 0.f) && !a.gamma && !a.row_scale && !a.residual;
+  if (plain_f32 && a.split_k != 1) {
+    const int sms = sm_count();
+    const long tiles = static_cast<long>((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + 127) / 128);  // at tile_n = 128
+    const int kbt = (a.K + BLOCK_K - 1) / BLOCK_K;
+    int s = a.split_k > 1 ? a.split_k : 1;
+    if (a.split_k == 0 && tiles < sms && kbt >= 32) {
+      s = static_cast<int>((2L * sms + tiles - 1) / tiles);
+      if (s > kbt / 8) s = kbt / 8;  // keep >= 8 k-blocks per slice
+      if (s < 1) s = 1;
+    }
+    if (s > 1) {
+      ep.split_k = s;
+      if (!a.accumulate)  // atomics need a defined starting value
+        X2K_CHECK_CUDA(cudaMemset2DAsync(a.out_f32, a.ld_out_f32 * sizeof(float), 0, static_cast<size_t>(a.N) * sizeof(float),
+                                         a.M, stream));
+    }
+  }
   int tile_n = a.tile_n;
+  if (ep.split_k > 1 && tile_n == 0) tile_n = 128;
   if (tile_n == 0) {
     // Pick the tile width that minimises (waves x tile cost) over the SMs.
     const int sms = sm_count();

@@ -161,14 +161,15 @@ __global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
   if (gamma) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
   const float inv_keep = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
   float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
   for (int m = r0; m < r1; ++m) {
-    float4 d = *reinterpret_cast<const float4*>(dx + static_cast<int64_t>(m) * ld_dx + n);
+    float4 d = __ldg(reinterpret_cast<const float4*>(dx + static_cast<int64_t>(m) * ld_dx + n));
     if (row_scale) {
       const float s = __ldg(row_scale + m / rows_per_scale);
       d.x *= s; d.y *= s; d.z *= s; d.w *= s;
     }
     if (dgamma) {
-      const uint2 pk = *reinterpret_cast<const uint2*>(y + static_cast<int64_t>(m) * ld_y + n);
+      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(y + static_cast<int64_t>(m) * ld_y + n));
       sg.x += d.x * bf16_lo(pk.x); sg.y += d.y * bf16_hi(pk.x); sg.z += d.z * bf16_lo(pk.y); sg.w += d.w * bf16_hi(pk.y);
     }
     d.x *= gm.x; d.y *= gm.y; d.z *= gm.z; d.w *= gm.w;
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* _
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
   for (int m = r0; m < r1; ++m) {
-    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + n);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + n));
     s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
     s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
   }

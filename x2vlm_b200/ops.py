@@ -39,7 +39,7 @@ def launch_count():
 
 def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=None, preact_out=None,
          dropout_p=0.0, dropout_seed=0, dropout_offset=0, gamma=None, row_scale=None, rows_per_scale=0,
-         residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0):
+         residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0, split_k=0):
     """C[M,N] = epilogue(A·Bᵀ) — see x2k_gemm in include/x2k.h.  `a`/`b` are 2-D bf16 views whose
     stride(0) is the leading dimension; MN-major operands are passed as their stored [K, M|N] matrix."""
     _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
@@ -73,6 +73,7 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
     if out_f32 is not None:
         g.out_f32, g.ld_out_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.tile_n = tile_n
+    g.split_k = split_k
     C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm")
 
 

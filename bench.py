@@ -236,6 +236,18 @@ def dominant_kernel_roofline(dev, n_images, peak_burst, src):
             "launch_ms": ms, "traffic": None}
 
 
+def host_threads():
+    """CPU threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def oracle_step_fn(batch_i, batch_r, threads):
     """fwd + bwd + AdamW of the reference algorithm (oracle/restate.py, fp32, torch CPU) on a small mixed batch."""
     from oracle import restate
@@ -275,7 +287,7 @@ def oracle_step_fn(batch_i, batch_r, threads):
 
 def cpu_baseline(budget_s=25.0, batch_i=4, batch_r=4):
     """Bounded sample: one warm-up step, then timed steps until ~budget_s of CPU work (at least one)."""
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     step, pairs = oracle_step_fn(batch_i, batch_r, threads)
     step()  # warm-up (the first step pays allocator / lazy-init costs)
     n, t0 = 0, time.perf_counter()
@@ -297,7 +309,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     bi, br = 2, (0 if args.image_only else 2)
     step, pairs = oracle_step_fn(bi, br, threads)
     for _ in range(min(args.warmup, 2)):

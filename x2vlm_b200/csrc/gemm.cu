@@ -465,6 +465,10 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
       if (s > kbt / 8) s = kbt / 8;  // keep >= 8 k-blocks per slice
       if (s < 1) s = 1;
     }
+    if (s > 1) {  // no slice may be empty (an MMA warp without k-blocks would never signal its epilogue)
+      const int per = (kbt + s - 1) / s;
+      s = (kbt + per - 1) / per;
+    }
     if (s > 1) {
       ep.split_k = s;
       if (!a.accumulate)  // atomics need a defined starting value

@@ -53,6 +53,43 @@ def _empty_bf16(*shape, dev):
     return torch.empty(*shape, dtype=torch.bfloat16, device=dev)
 
 
+class _G:
+    """Gradient slot of a small parameter (bias / LayerNorm / LayerScale / rel-pos table) inside a fused backward:
+    the arena's flat-gradient view — the kernel accumulates in place and autograd receives None — or, without an
+    arena, a fresh zero buffer that is returned to autograd."""
+    __slots__ = ("param", "buf", "direct")
+
+    def __init__(self, param, dev):
+        self.param = param
+        g = getattr(param, "_x2k_grad", None) if param is not None else None
+        if g is not None:
+            self.buf, self.direct = g.view(-1), True
+        else:
+            self.direct = False
+            self.buf = torch.zeros(param.numel(), dtype=torch.float32, device=dev) if param is not None else None
+
+    def ret(self):
+        if self.param is None:
+            return None
+        if self.direct:
+            self.param._x2k_arena.note_grad_written(self.param, [self.param])
+            return None
+        return self.buf.view(self.param.shape)
+
+
+def _note_uses(*objs):
+    """Count one forward use of each shadow / arena-managed parameter (only while autograd is recording), so the DDP
+    bucketer knows when the LAST gradient contribution of a step has been written."""
+    if not torch.is_grad_enabled():
+        return
+    for o in objs:
+        if o is None:
+            continue
+        a = getattr(o, "arena", None) if not isinstance(o, torch.Tensor) else getattr(o, "_x2k_arena", None)
+        if a is not None:
+            a.note_use(o)
+
+
 def _wgrad(shadow, dy_bf16, x_bf16, n_out, n_in, rows):
     """dW[n_out, n_in] = dyᵀ · x over `rows`; into the arena's flat gradient (accumulating) or a new tensor.
     Returns the list of per-parameter grads to hand to autograd (None when the sink took them)."""
@@ -132,6 +169,7 @@ class _LinearFn(torch.autograd.Function):
 
 def linear(x, shadow, bias=None, gelu=False, out_bf16=False):
     """y[M,N] = act(x[M,K] · Wᵀ + b) on the tcgen05 GEMM; x fp32 or bf16, W given by its Shadow."""
+    _note_uses(shadow)
     return _LinearFn.apply(x, bias, shadow, gelu, out_bf16, *shadow.params)
 
 
@@ -210,6 +248,7 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale,
                  rows_per_scale=N, residual=x1, out_f32=out)
         ctx.blk, ctx.dims, ctx.scale = blk, (B, N, D, H, Dh, ldb), scale
+        ctx.P = (n1w, n1b, table, projb, g1, n2w, n2b, fc1b, fc2b, g2)
         ctx.save_for_backward(x2, dp_scale, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1,
                               mean2, rstd2, ln2, hpre, act, y2)
         return out.view(B, N, D)
@@ -223,30 +262,27 @@ class _BeitBlockFn(torch.autograd.Function):
         B, N, D, H, Dh, ldb = ctx.dims
         M = B * N
         dev = dout.device
+        P_n1w, P_n1b, P_table, P_projb, P_g1, P_n2w, P_n2b, P_fc1b, P_fc2b, P_g2 = (_G(q, dev) for q in ctx.P)
         dx2 = dout.contiguous().view(M, D)
         # ---- MLP branch ----
         g2b = _empty_bf16(M, D, dev=dev)
-        d_fc2b, d_g2 = _zeros(D, dev), (_zeros(D, dev) if g2 is not None else None)
         ops.scale_cast_colsum(dx2, M, D, g_bf16=g2b, gamma=g2, row_scale=dp_scale, rows_per_scale=N,
-                              y_bf16=y2 if g2 is not None else None, dbias=d_fc2b, dgamma=d_g2)
+                              y_bf16=y2 if g2 is not None else None, dbias=P_fc2b.buf, dgamma=P_g2.buf)
         dh = _empty_bf16(M, Dh, dev=dev)
         ops.gemm(g2b, sh["fc2"].get_nograd(), M, Dh, D, b_mn=True, act=ACT_GELU_BWD, aux=hpre, out_bf16=dh)
         wg_fc2 = _wgrad(sh["fc2"], g2b, act, D, Dh, M)
         del act, g2b
-        d_fc1b = _zeros(Dh, dev)
-        ops.colsum_bf16(dh, M, Dh, d_fc1b)
+        ops.colsum_bf16(dh, M, Dh, P_fc1b.buf)
         dln2 = _empty_bf16(M, D, dev=dev)
         ops.gemm(dh, sh["fc1"].get_nograd(), M, D, Dh, b_mn=True, out_bf16=dln2)
         wg_fc1 = _wgrad(sh["fc1"], dh, ln2, Dh, D, M)
         del dh
         dx1 = torch.empty(M, D, dtype=torch.float32, device=dev)
-        d_n2w, d_n2b = _zeros(D, dev), _zeros(D, dev)
-        ops.layernorm_bwd(dln2, x1, n2w, mean2, rstd2, dx1, d_n2w, d_n2b, dx_residual=dx2)
+        ops.layernorm_bwd(dln2, x1, n2w, mean2, rstd2, dx1, P_n2w.buf, P_n2b.buf, dx_residual=dx2)
         # ---- attention branch ----
         g1b = _empty_bf16(M, D, dev=dev)
-        d_projb, d_g1 = _zeros(D, dev), (_zeros(D, dev) if g1 is not None else None)
         ops.scale_cast_colsum(dx1, M, D, g_bf16=g1b, gamma=g1, row_scale=dp_scale, rows_per_scale=N,
-                              y_bf16=y1 if g1 is not None else None, dbias=d_projb, dgamma=d_g1)
+                              y_bf16=y1 if g1 is not None else None, dbias=P_projb.buf, dgamma=P_g1.buf)
         dattn = _empty_bf16(M, D, dev=dev)
         ops.gemm(g1b, sh["proj"].get_nograd(), M, D, D, b_mn=True, out_bf16=dattn)
         wg_proj = _wgrad(sh["proj"], g1b, attn_o, D, D, M)
@@ -254,22 +290,19 @@ class _BeitBlockFn(torch.autograd.Function):
         ds_out = _empty_bf16(B, H, N, ldb, dev=dev) if table is not None else None
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, ctx.scale, attn_o, lse, dattn, dqkv[:, :D],
                      dqkv[:, D:2 * D], dqkv[:, 2 * D:], ds_out=ds_out, bias=bias_g)
-        d_table = None
         if table is not None:
-            d_table = torch.zeros_like(table)
-            ops.relpos_bias_scatter(ds_out, B, H, N, blk.attn.relative_position_index, d_table)
+            ops.relpos_bias_scatter(ds_out, B, H, N, blk.attn.relative_position_index, P_table.buf)
         d_qkvb = _zeros(3 * D, dev)
         ops.colsum_bf16(dqkv, M, 3 * D, d_qkvb)
         dln1 = _empty_bf16(M, D, dev=dev)
         ops.gemm(dqkv, sh["qkv"].get_nograd(), M, D, 3 * D, b_mn=True, out_bf16=dln1)
         wg_qkv = _wgrad(sh["qkv"], dqkv, ln1, 3 * D, D, M)
         dx = torch.empty(M, D, dtype=torch.float32, device=dev)
-        d_n1w, d_n1b = _zeros(D, dev), _zeros(D, dev)
-        ops.layernorm_bwd(dln1, x2, n1w, mean1, rstd1, dx, d_n1w, d_n1b, dx_residual=dx1)
+        ops.layernorm_bwd(dln1, x2, n1w, mean1, rstd1, dx, P_n1w.buf, P_n1b.buf, dx_residual=dx1)
         # weights were passed in the order qkv, proj, fc1, fc2
         nig = ctx.needs_input_grad
-        return (dx.view(B, N, D), None, None, d_n1w, d_n1b, d_qkvb if nig[5] else None, d_table, d_projb,
-                d_g1 if nig[8] else None, d_n2w, d_n2b, d_fc1b, d_fc2b, d_g2 if nig[13] else None, *wg_qkv, *wg_proj,
+        return (dx.view(B, N, D), None, None, P_n1w.ret(), P_n1b.ret(), d_qkvb if nig[5] else None, P_table.ret(),
+                P_projb.ret(), P_g1.ret(), P_n2w.ret(), P_n2b.ret(), P_fc1b.ret(), P_fc2b.ret(), P_g2.ret(), *wg_qkv, *wg_proj,
                 *wg_fc1, *wg_fc2)
 
 
@@ -280,6 +313,8 @@ def beit_block(x, blk, dp_scale=None):
     qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)) if a.q_bias is not None else None
     sh = blk._x2k
     weights = (*sh["qkv"].params, *sh["proj"].params, *sh["fc1"].params, *sh["fc2"].params)
+    _note_uses(sh["qkv"], sh["proj"], sh["fc1"], sh["fc2"], blk.norm1.weight, blk.norm1.bias, a.relative_position_bias_table,
+               a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias, blk.mlp.fc2.bias, blk.gamma_2)
     return _BeitBlockFn.apply(x, dp_scale, blk, blk.norm1.weight, blk.norm1.bias, qkv_bias, a.relative_position_bias_table,
                               a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias,
                               blk.mlp.fc2.bias, blk.gamma_2, *weights)
@@ -368,6 +403,8 @@ class _BertLayerFn(torch.autograd.Function):
         sv.update(xb2=xb2, qkv=qkv, ctx1=ctx1, lse1=lse1, s1=s1, m1=m1, r1=r1, x1b=x1b, xab=xab, hpre=hpre, act=act, s3=s3,
                   m3=m3, r3=r3, d_a1=d_a1, d_h1=d_h1, d_h3=d_h3, ln1w=ln1w, lncw=lncw, ln2w=ln2w)
         ctx.sv, ctx.layer, ctx.cfg, ctx.has_cross = sv, layer, cfg, has_cross
+        ctx.P = (b_o, ln1w, ln1b, b_qc, b_oc, lncw, lncb, b_i, b_out, ln2w, ln2b)
+        ctx.packed_bias = (b_qkv, b_kvc)
         ctx.dims = (Bt, L, D, H, Di, scale)
         ctx.enc_needs_grad = has_cross and enc.requires_grad
         ctx.mark_non_differentiable(yb)
@@ -381,35 +418,40 @@ class _BertLayerFn(torch.autograd.Function):
         M = Bt * L
         dev = dy.device
         dy2 = dy.contiguous().view(M, D)
+        P_bo, P_ln1w, P_ln1b, P_bqc, P_boc, P_lncw, P_lncb, P_bi, P_bout, P_ln2w, P_ln2b = (
+            _G(q if (ctx.has_cross or i not in (3, 4, 5, 6)) else None, dev) for i, q in enumerate(ctx.P))
+
+        def packed_slot(key, tensor, n):
+            """Packed bias (q|k|v or k|v): the arena's adjacent gradient views, else a zero buffer for autograd."""
+            shd = sh.get(key)
+            if tensor is not None and shd is not None and shd.arena is not None and not tensor.requires_grad:
+                return shd.grad_sink().view(-1), shd
+            return (_zeros(n, dev) if tensor is not None else None), None
+
         # ---- feed-forward ----
         ds3 = torch.empty(M, D, dtype=torch.float32, device=dev)
-        d_ln2w, d_ln2b = _zeros(D, dev), _zeros(D, dev)
-        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, d_ln2w, d_ln2b)
+        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, P_ln2w.buf, P_ln2b.buf)
         g3 = _empty_bf16(M, D, dev=dev)
-        d_bout = _zeros(D, dev)
         p, seed, off = sv["d_h3"]
-        ops.scale_cast_colsum(ds3, M, D, g_bf16=g3, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_bout)
+        ops.scale_cast_colsum(ds3, M, D, g_bf16=g3, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_bout.buf)
         dh = _empty_bf16(M, Di, dev=dev)
         ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_GELU_BWD, aux=sv["hpre"], out_bf16=dh)
         wg_out = _wgrad(sh["out"], g3, sv["act"], D, Di, M)
-        d_bi = _zeros(Di, dev)
-        ops.colsum_bf16(dh, M, Di, d_bi)
+        ops.colsum_bf16(dh, M, Di, P_bi.buf)
         dxab = _empty_bf16(M, D, dev=dev)
         ops.gemm(dh, sh["i"].get_nograd(), M, D, Di, b_mn=True, out_bf16=dxab)
         wg_i = _wgrad(sh["i"], dh, sv["xab"], Di, D, M)
         del dh, g3
-        d_bqc = d_bkvc = d_boc = d_lncw = d_lncb = d_enc = None
+        d_bkvc = d_enc = None
         wg_qc, wg_kvc, wg_oc = [None] * len(sh["qc"].params) if "qc" in sh else [], \
             [None] * len(sh["kvc"].params) if "kvc" in sh else [], [None] * len(sh["oc"].params) if "oc" in sh else []
         if ctx.has_cross:
             n_kv, Nk, Dv = sv["dims_c"]
             ds2 = torch.empty(M, D, dtype=torch.float32, device=dev)
-            d_lncw, d_lncb = _zeros(D, dev), _zeros(D, dev)
-            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, d_lncw, d_lncb)
+            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, P_lncw.buf, P_lncb.buf)
             g2 = _empty_bf16(M, D, dev=dev)
-            d_boc = _zeros(D, dev)
             p, seed, off = sv["d_h2"]
-            ops.scale_cast_colsum(ds2, M, D, g_bf16=g2, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_boc)
+            ops.scale_cast_colsum(ds2, M, D, g_bf16=g2, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_boc.buf)
             dctx2 = _empty_bf16(M, D, dev=dev)
             ops.gemm(g2, sh["oc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx2)
             wg_oc = _wgrad(sh["oc"], g2, sv["ctx2"], D, D, M)
@@ -425,15 +467,17 @@ class _BertLayerFn(torch.autograd.Function):
                 ops.segment_sum_bf16(dkv_seq.view(Bt, Nk * 2 * D), cfg["kv_index"], n_kv, dkv.view(n_kv, Nk * 2 * D))
             else:
                 dkv = dkv_seq
-            d_bkvc = _zeros(2 * D, dev)
+            d_bkvc, kv_shd = packed_slot("bkvc", ctx.packed_bias[1], 2 * D)
             ops.colsum_bf16(dkv, n_kv * Nk, 2 * D, d_bkvc)
+            if kv_shd is not None:
+                kv_shd.grads_done()
+                d_bkvc = None
             if ctx.enc_needs_grad:
                 d_enc = torch.empty(n_kv * Nk, Dv, dtype=torch.float32, device=dev)
                 ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=d_enc)
                 d_enc = d_enc.view(n_kv, Nk, Dv)
             wg_kvc = _wgrad(sh["kvc"], dkv, sv["enc2"], 2 * D, Dv, n_kv * Nk)
-            d_bqc = _zeros(D, dev)
-            ops.colsum_bf16(dqc, M, D, d_bqc)
+            ops.colsum_bf16(dqc, M, D, P_bqc.buf)
             dx1b = _empty_bf16(M, D, dev=dev)
             ops.gemm(dqc, sh["qc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dx1b)
             wg_qc = _wgrad(sh["qc"], dqc, sv["x1b"], D, D, M)
@@ -442,12 +486,10 @@ class _BertLayerFn(torch.autograd.Function):
             res_f32, res_bf16 = ds3, dxab
         # ---- self-attention ----
         ds1 = torch.empty(M, D, dtype=torch.float32, device=dev)
-        d_ln1w, d_ln1b = _zeros(D, dev), _zeros(D, dev)
-        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, d_ln1w, d_ln1b)
+        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, P_ln1w.buf, P_ln1b.buf)
         g1 = _empty_bf16(M, D, dev=dev)
-        d_bo = _zeros(D, dev)
         p, seed, off = sv["d_h1"]
-        ops.scale_cast_colsum(ds1, M, D, g_bf16=g1, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=d_bo)
+        ops.scale_cast_colsum(ds1, M, D, g_bf16=g1, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_bo.buf)
         dctx1 = _empty_bf16(M, D, dev=dev)
         ops.gemm(g1, sh["o"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx1)
         wg_o = _wgrad(sh["o"], g1, sv["ctx1"], D, D, M)
@@ -457,27 +499,42 @@ class _BertLayerFn(torch.autograd.Function):
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, L, L, scale, sv["ctx1"], sv["lse1"], dctx1,
                      dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], mask=cfg["self_mask"],
                      mask_per_query=cfg["self_mask_3d"], dropout_p=p, dropout_seed=seed, dropout_offset=off)
-        d_bqkv = _zeros(3 * D, dev)
+        d_bqkv, qkv_shd = packed_slot("bqkv", ctx.packed_bias[0], 3 * D)
         ops.colsum_bf16(dqkv, M, 3 * D, d_bqkv)
+        if qkv_shd is not None:
+            qkv_shd.grads_done()
+            d_bqkv = None
         dx = torch.empty(M, D, dtype=torch.float32, device=dev)
         ops.gemm(dqkv, sh["qkv"].get_nograd(), M, D, 3 * D, b_mn=True, residual=ds1, out_f32=dx)
         wg_qkv = _wgrad(sh["qkv"], dqkv, sv["xb2"], 3 * D, D, M)
         ctx.sv = None
         # weight order: qkv(3), o, [qc, kvc(2), oc], i, out
-        return (dx.view(Bt, L, D), None, d_enc, None, None, None, d_bqkv, d_bo, d_ln1w, d_ln1b, d_bqc, d_bkvc, d_boc, d_lncw,
-                d_lncb, d_bi, d_bout, d_ln2w, d_ln2b, *wg_qkv, *wg_o, *wg_qc, *wg_kvc, *wg_oc, *wg_i, *wg_out)
+        return (dx.view(Bt, L, D), None, d_enc, None, None, None, d_bqkv, P_bo.ret(), P_ln1w.ret(), P_ln1b.ret(), P_bqc.ret(),
+                d_bkvc, P_boc.ret(), P_lncw.ret(), P_lncb.ret(), P_bi.ret(), P_bout.ret(), P_ln2w.ret(), P_ln2b.ret(),
+                *wg_qkv, *wg_o, *wg_qc, *wg_kvc, *wg_oc, *wg_i, *wg_out)
 
 
 def bert_layer(x, xb, layer, cfg, enc=None, encb=None):
     """One BertLayer.  Returns (y fp32 [Bt,L,D], y bf16 copy)."""
     sh = layer._x2k
     at, so = layer.attention.self, layer.attention.output
-    b_qkv = torch.cat((at.query.bias, at.key.bias, at.value.bias))
+
+    def packed(key, *biases):
+        """fp32 packed bias: a plain view of the arena (members are adjacent) or a differentiable torch.cat."""
+        shd = sh[key]
+        if shd.arena is not None:
+            return shd.get_f32()
+        return torch.cat(biases)
+
+    b_qkv = packed("bqkv", at.query.bias, at.key.bias, at.value.bias)
     use_cross = enc is not None and layer.has_cross_attention
+    uses = [sh["qkv"], sh["o"], sh["i"], sh["out"], sh["bqkv"], so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+            layer.intermediate.dense.bias, layer.output.dense.bias, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias]
     if use_cross:
         ca, co = layer.crossattention.self, layer.crossattention.output
-        b_qc, b_kvc, b_oc = ca.query.bias, torch.cat((ca.key.bias, ca.value.bias)), co.dense.bias
+        b_qc, b_kvc, b_oc = ca.query.bias, packed("bkvc", ca.key.bias, ca.value.bias), co.dense.bias
         lncw, lncb = co.LayerNorm.weight, co.LayerNorm.bias
+        uses += [sh["qc"], sh["kvc"], sh["oc"], sh["bkvc"], b_qc, b_oc, lncw, lncb]
     else:
         b_qc = b_kvc = b_oc = lncw = lncb = None
         enc = encb = None
@@ -485,6 +542,7 @@ def bert_layer(x, xb, layer, cfg, enc=None, encb=None):
     if "qc" in sh:
         weights += [*sh["qc"].params, *sh["kvc"].params, *sh["oc"].params]
     weights += [*sh["i"].params, *sh["out"].params]
+    _note_uses(*uses)
     return _BertLayerFn.apply(x, xb, enc, encb, layer, cfg, b_qkv, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
                               b_qc, b_kvc, b_oc, lncw, lncb, layer.intermediate.dense.bias, layer.output.dense.bias,
                               layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, *weights)

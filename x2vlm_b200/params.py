@@ -44,8 +44,6 @@ class Shadow:
         if self.arena is not None:
             if tuple(p._version for p in self.params) != self._versions:
                 self.arena.sync_bf16()  # some parameter was modified in place since the last sync
-            if count_use and torch.is_grad_enabled():
-                self.arena.note_use(self)
             return self.arena.bf16[self.offset:self.offset + self.total_rows * self.K].view(self.total_rows, self.K)
         p0 = self.params[0]
         if self._buf is None or self._buf.device != p0.device:
@@ -66,9 +64,15 @@ class Shadow:
             return None
         return self.arena.grad[self.offset:self.offset + self.total_rows * self.K].view(self.total_rows, self.K)
 
+    def get_f32(self):
+        """fp32 [total_rows * K] view of the packed parameters inside the arena (None without an arena)."""
+        if self.arena is None:
+            return None
+        return self.arena.flat[self.offset:self.offset + self.total_rows * self.K]
+
     def grads_done(self):
         if self.arena is not None:
-            self.arena.note_grad_written(self)
+            self.arena.note_grad_written(self, self.params)
 
     def split_grad(self, g):
         """Split a packed [total_rows, K] gradient into per-parameter pieces (non-arena path)."""
@@ -137,6 +141,7 @@ class ParamArena:
                 self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + p.numel()].view(p.shape)
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                p._x2k_grad, p._x2k_arena = p.grad, self  # fused backwards accumulate small gradients in place
         for s in shadows:
             o = self.offsets[id(s.params[0])]
             for a, b in zip(s.params[:-1], s.params[1:]):
@@ -173,14 +178,16 @@ class ParamArena:
         self.grad.zero_()
         self._pending.clear()
 
-    def note_use(self, shadow):
-        self._pending[id(shadow)] = self._pending.get(id(shadow), 0) + 1
+    def note_use(self, obj):
+        """One forward use of a shadow / parameter whose gradient a fused backward will write in place."""
+        self._pending[id(obj)] = self._pending.get(id(obj), 0) + 1
 
-    def note_grad_written(self, shadow):
-        n = self._pending.get(id(shadow), 1) - 1
-        self._pending[id(shadow)] = n
+    def note_grad_written(self, obj, params):
+        """One backward contribution has been accumulated; after the last one of this step the parameters are final."""
+        n = self._pending.get(id(obj), 1) - 1
+        self._pending[id(obj)] = n
         if n <= 0 and self.on_grad_ready is not None:
-            self.on_grad_ready(shadow.params)
+            self.on_grad_ready(params)
 
     def _autograd_hook(self, p):
         if self.on_grad_ready is not None:

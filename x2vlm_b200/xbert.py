@@ -145,12 +145,14 @@ class BertLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config, drop_path_rate=drop_path_rate)
         at = self.attention
+        D = config.hidden_size
         sh = {"qkv": Shadow(at.self.query.weight, at.self.key.weight, at.self.value.weight),
+              "bqkv": Shadow(at.self.query.bias, at.self.key.bias, at.self.value.bias, K=D),
               "o": Shadow(at.output.dense.weight)}
         if self.has_cross_attention:
             ca = self.crossattention
             sh.update(qc=Shadow(ca.self.query.weight), kvc=Shadow(ca.self.key.weight, ca.self.value.weight),
-                      oc=Shadow(ca.output.dense.weight))
+                      bkvc=Shadow(ca.self.key.bias, ca.self.value.bias, K=D), oc=Shadow(ca.output.dense.weight))
         sh.update(i=Shadow(self.intermediate.dense.weight), out=Shadow(self.output.dense.weight))
         self._x2k = sh
         self._x2k_shadows = list(sh.values())

@@ -53,8 +53,9 @@ int64_t x2k_launch_count(void);
  *   if preact_out:  preact_out[m,n] = bf16(v)            (saved for GELU backward)
  *   if act == X2K_ACT_GELU:       v = gelu_erf(v)
  *   if act == X2K_ACT_GELU_BWD:   v = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation)
- *   if dropout_p > 0:  v = keep(m,n) ? v/(1-p) : 0        (Philox4x32-10 keyed by seed,
- *                                                          counter = offset + (m*N+n)/4)
+ *   if dropout_p > 0:  v = keep(e) ? v*s : 0,  e = m*N+n     (16 random bits per element from
+ *                      Philox4x32-7(key = seed, counter = offset + e/8): word (e%8)/2, low half for
+ *                      even e; keep iff bits >= thr = round(p*65536); s = 65536/(65536-thr))
  *   if gamma:     v *= gamma[n]                           (BEiT LayerScale)
  *   if row_scale: v *= row_scale[m / rows_per_scale]      (per-sample DropPath keep/(1-p))
  *   if residual:  v += residual[m,n]                      (fp32)
@@ -155,13 +156,14 @@ int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream)
  * the packed QKV projection output in place ([B·L, 3D] for BEiT/BERT self-attention, separate
  * Q and KV buffers for cross-attention) and several query sequences may share one K/V sequence
  * (the image K/V cache across the ITM/MLM passes, models/xvlm.py:859-899).
- * Let Lk_pad = Lk rounded up to 16 (Lk <= 256).
+ * Let Lk_pad = Lk rounded up to 16 (Lk <= 256) and Lk_32 = Lk rounded up to 32.
  * bias: fp32, element (h,i,j) at bias[h*bias_h_stride + i*bias_q_stride + j] (BEiT relative
- *   position bias already gathered), or NULL.  Strides are multiples of 4, q stride >= Lk_pad.
+ *   position bias already gathered), or NULL.  Strides are multiples of 4, q stride >= Lk_32
+ *   (the kernels stage it in coalesced 32-row x 32-column blocks).
  * mask: fp32 additive, element (b,i,j) at mask[b*mask_b_stride + i*mask_q_stride + j]
  *   (mask_q_stride = 0 for a key mask [B,Lk]), or NULL.  Same stride rules.
- * dropout on probabilities (BERT attention_probs_dropout) via Philox4x32-10, counter =
- *   offset + (((b*H+h)*Lq + i)*Lk_pad + j)/4.
+ * dropout on probabilities (BERT attention_probs_dropout): element e = ((b*H+h)*Lq + i)*Lk_pad + j
+ *   of the Philox stream described at x2k_gemm.
  * Outputs: O bf16 at o + (b*Lq+i)*ld_o + h*64, lse fp32 [B,H,Lq] (log2 domain: log2 sum exp2).
  * Replaces models/beit2.py:135-159 and models/xbert.py:364-410.
  *

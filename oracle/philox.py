@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE — numpy restatement of the Philox4x32-10 stream the x2k kernels use for dropout
-(x2vlm_b200/csrc/common.cuh: philox4x32 / dropout_keep), to build the exact keep-mask on the CPU.
+"""TEST INFRASTRUCTURE — numpy restatement of the Philox4x32 stream the x2k kernels use for dropout
+(x2vlm_b200/csrc/common.cuh: philox4x32<7> / drop8), to build the exact keep-mask on the CPU.
 
 Published algorithm: Salmon et al., "Parallel Random Numbers: As Easy as 1, 2, 3" (SC'11), Philox-4x32 with
 10 rounds, multipliers 0xD2511F53 / 0xCD9E8D57, Weyl keys 0x9E3779B9 / 0xBB67AE85.  The kernels' counter is
@@ -30,10 +30,16 @@ def philox4x32(seed, ctr):
                           int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
 
 
-def keep_scale(seed, offset, n_elems, p):
-    """float32 [n_elems]: 1/(1-p) where the element is kept else 0; element i uses word i%4 of counter offset + i//4."""
-    n4 = (n_elems + 3) // 4
-    words = philox4x32(seed, np.uint64(offset) + np.arange(n4, dtype=np.uint64))
-    r = np.stack(words, axis=1).reshape(-1)[:n_elems]
-    u = (r >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-    return np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32)
+def keep_scale(seed, offset, n_elems, p, rounds=7):
+    """float32 [n_elems] keep-scales of the kernels' dropout stream (common.cuh: drop8): element e draws 16 bits from
+    Philox4x32-7(seed, counter = offset + (e >> 3)), word (e & 7) >> 1, low half for even e / high half for odd e; it is
+    kept iff r16 >= thr = round(p * 65536) and then scaled by 65536 / (65536 - thr)."""
+    n8 = (n_elems + 7) // 8
+    ctr = np.uint64(offset) + np.arange(n8, dtype=np.uint64)
+    words = philox4x32_raw(ctr & MASK, ctr >> np.uint64(32), np.full_like(ctr, 0x2B992DDF), np.zeros_like(ctr),
+                           int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF, rounds=rounds)
+    w = np.stack(words, axis=1)  # [n8, 4]
+    r16 = np.stack([w & np.uint64(0xFFFF), w >> np.uint64(16)], axis=2).reshape(-1)[:n_elems]
+    thr = int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)) if p > 0 else 0
+    scale = np.float32(65536.0) / (np.float32(65536.0) - np.float32(thr))
+    return np.where(r16 >= np.uint64(thr), scale, np.float32(0.0)).astype(np.float32)

@@ -168,7 +168,8 @@ def test_attention_fwd_bwd(dev, case):
     if case == "text_dropout":
         p_drop = 0.1
     D = H * 64
-    ld = ops.pad16(Lk)
+    ld = ops.pad32(Lk)      # row stride of bias / mask / dS buffers
+    lkp = ops.pad16(Lk)     # the kernels' padded key count (dropout element index)
     scale = 0.125
     qkv = _bf(torch.randn(B * Lq, 3 * D, device=dev, generator=g))
     if Lq == Lk and kv_index is None:
@@ -202,7 +203,7 @@ def test_attention_fwd_bwd(dev, case):
         mask_r = mask[:, None, :, :Lk] if per_query else mask[:, None, None, :Lk]
     keep = None
     if p_drop > 0:
-        keep = torch.from_numpy(philox.keep_scale(42, 1000, B * H * Lq * ld, p_drop)).view(B, H, Lq, ld)[..., :Lk].to(dev)
+        keep = torch.from_numpy(philox.keep_scale(42, 1000, B * H * Lq * lkp, p_drop)).view(B, H, Lq, lkp)[..., :Lk].to(dev)
     oref, pref = _attn_ref(qf, kf, vf, scale, bias_r, mask_r, keep)
     o_cmp = _heads(o.float(), B, Lq, H)
     tol = 2e-2  # P is rounded to bf16 before P·V: relative error ~2^-8 per term, outputs are O(1)
@@ -235,11 +236,11 @@ def test_relpos_gather_scatter(dev):
     g = torch.Generator(device=dev).manual_seed(2)
     table = torch.randn(R, H, device=dev, generator=g)
     index = restate.relative_position_index((14, 14)).to(dev)
-    out = torch.empty(H, N, 208, device=dev)
+    out = torch.empty(H, N, 224, device=dev)
     ops.relpos_bias_gather(table, index, N, H, out)
     ref = table[index.view(-1)].view(N, N, H).permute(2, 0, 1)
     assert torch.equal(out[:, :, :N], ref) and out[:, :, N:].abs().max() == 0
-    ds = _bf(torch.randn(4, H, N, 208, device=dev, generator=g))
+    ds = _bf(torch.randn(4, H, N, 224, device=dev, generator=g))
     dt = torch.zeros(R, H, device=dev)
     ops.relpos_bias_scatter(ds, 4, H, N, index, dt)
     want = torch.zeros(R, H, device=dev).index_add_(0, index.view(-1), ds.float().sum(0)[:, :, :N].permute(1, 2, 0).reshape(N * N, H))

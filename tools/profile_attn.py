@@ -6,7 +6,7 @@ from x2vlm_b200 import ops
 dev = torch.device("cuda:0"); torch.manual_seed(0)
 H, D = 12, 768
 def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps=3):
-    ld = ops.pad16(Lk)
+    ld = ops.pad32(Lk)
     q = torch.randn(B * Lq, 3 * D, device=dev).bfloat16()
     kv = torch.randn(n_kv * Lk, 2 * D, device=dev).bfloat16()
     if Lq == Lk and not shared:

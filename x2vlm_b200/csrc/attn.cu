@@ -76,13 +76,94 @@ __device__ __forceinline__ void load_additive(const AttnParams& p, const float* 
   for (int j = 0; j < 16; ++j) add[j] *= kLog2e;
 }
 
+// TMEM row (this thread's lane) -> NCH x 16 fp32 columns -> scaled bf16 -> global (16-byte stores)
+template <int NCH>
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, uint32_t tcol_addr, float mul, bool valid) {
+  uint32_t o[16];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    tmem_ld_32x16(tcol_addr + c * 16, o);
+    tmem_wait_ld();
+    if (valid) {
+      uint4 v0, v1;
+      v0.x = pack_bf16x2(__uint_as_float(o[0]) * mul, __uint_as_float(o[1]) * mul);
+      v0.y = pack_bf16x2(__uint_as_float(o[2]) * mul, __uint_as_float(o[3]) * mul);
+      v0.z = pack_bf16x2(__uint_as_float(o[4]) * mul, __uint_as_float(o[5]) * mul);
+      v0.w = pack_bf16x2(__uint_as_float(o[6]) * mul, __uint_as_float(o[7]) * mul);
+      v1.x = pack_bf16x2(__uint_as_float(o[8]) * mul, __uint_as_float(o[9]) * mul);
+      v1.y = pack_bf16x2(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
+      v1.z = pack_bf16x2(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
+      v1.w = pack_bf16x2(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
+      *reinterpret_cast<uint4*>(dst + c * 16) = v0;
+      *reinterpret_cast<uint4*>(dst + c * 16 + 8) = v1;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// forward: grid (q tiles, H, B), 128 threads, 2 CTAs / SM (TMEM 256 columns each)
+// Thread mapping shared by both kernels: 256 threads = 8 warps.  Warp w owns TMEM lane quadrant (w & 3) — the
+// hardware restriction for tcgen05.ld/st — i.e. rows quad*32 .. +31 of the 128-row tile, thread == row, and
+// column half (w >> 2): the two warps of a quadrant split the key columns of every tile between them, so two
+// threads work on each row (twice the warps to hide instruction / memory latency).
+// ---------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 256;
+
+// Coalesced load of a [32 rows x 32 cols] fp32 bias block for one warp: each LDG.128 instruction covers 4 rows x 128
+// contiguous bytes (4 wavefronts instead of 32 for a thread-per-row access), staged through a 4 KB XOR-swizzled smem
+// tile, then every thread picks up the 32 values of ITS row.  `rows_left` clamps rows past the end of the tensor.
+__device__ __forceinline__ void load_bias_block(const float* __restrict__ base, int64_t row_stride, int rows_left,
+                                                uint32_t stage_addr, int lane, float (&out)[32]) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const int rc = r < rows_left ? r : (rows_left - 1);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + rc * row_stride) + ch);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr + r * 128 + ((ch ^ (r & 7)) << 4)), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(stage_addr + lane * 128 + ((c ^ (lane & 7)) << 4))
+                 : "memory");
+    out[4 * c] = v.x; out[4 * c + 1] = v.y; out[4 * c + 2] = v.z; out[4 * c + 3] = v.w;
+  }
+  __syncwarp();
+}
+
+// additive term (bias + mask) * log2e for the 32 columns [k0, k0+32) of query row q (k0 % 32 == 0)
+__device__ __forceinline__ void additive32(const AttnParams& p, const float* bias_blk, int bias_rows_left,
+                                           const float* mask_row, int k0, uint32_t stage_addr, int lane, float (&add)[32]) {
+  if (bias_blk) {
+    load_bias_block(bias_blk + k0, p.bias_q_stride, bias_rows_left, stage_addr, lane, add);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) add[j] = 0.f;
+  }
+  if (mask_row) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + k0 + j));
+      add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) add[j] *= kLog2e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: grid (q tiles, H, B), 256 threads, 2 CTAs / SM (TMEM 256 columns, ~101 KB smem each)
 // ---------------------------------------------------------------------------------------------
 constexpr int FWD_REGION0 = 65536;  // Q (16 KB) + K (<= 32 KB) during S; P (4 x 16 KB) afterwards
-constexpr int FWD_SMEM = FWD_REGION0 + 32768 + 1024 + 128;
+constexpr int FWD_REGIONV = 32768;  // bias staging (8 warps x 4 KB) during pass 1, then the V tile
+constexpr int FWD_SMEM = FWD_REGION0 + FWD_REGIONV + 2048 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,12 +172,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sK = smem + 16384;
   uint8_t* sP = smem;  // aliases Q/K once S has been computed
   uint8_t* sV = smem + FWD_REGION0;
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + FWD_REGION0 + 32768);
+  float* s_red = reinterpret_cast<float*>(smem + FWD_REGION0 + FWD_REGIONV);  // [2 halves][128 rows] max, then sum
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + FWD_REGION0 + FWD_REGIONV + 1024);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_mma = bar_qk + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_qk + 3);
 
-  const int warp = threadIdx.x >> 5, row = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int Lk_pad = p.Lk_pad;
@@ -120,9 +204,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_arrive_expect_tx(bar_qk, 16384 + Lk_pad * 128);
     tma_load_2d(sQ, &tmap_q, bar_qk, h * 64, b * p.Lq + qt * 128);
     tma_load_2d(sK, &tmap_k, bar_qk, h * 64, kvb * p.Lk);
-    mbar_arrive_expect_tx(bar_v, Lk_pad * 128);
-    tma_load_2d(sV, &tmap_v, bar_v, h * 64, kvb * p.Lk);
-    // S = Q · Kᵀ
     mbar_wait(bar_qk, 0);
     tc_fence_after();
     const uint32_t idesc = make_idesc_bf16(128, Lk_pad, 0, 0);
@@ -136,70 +217,83 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  // ---- softmax over the row owned by this thread ----
-  // Pass 1 forms t = scale·qk + bias + mask (log2 domain) 64 columns at a time — all bias/mask loads of a
-  // super-chunk are issued together so their latency overlaps — tracks the row max and writes t back to TMEM;
-  // pass 2 re-reads t only (no second trip to global memory), exponentiates and emits P.
+  // ---- softmax: pass 1 forms t = scale·qk + bias + mask (log2 domain), row max, writes t back to TMEM ----
   const int q = qt * 128 + row;
   const bool qvalid = q < p.Lq;
-  const bool warp_live = (qt * 128 + warp * 32) < p.Lq;  // warp-uniform: dead warps own no valid query row
-  const float* bias_row = (p.bias && qvalid) ? p.bias + h * p.bias_h_stride + q * p.bias_q_stride : nullptr;
+  const bool warp_live = (qt * 128 + quad * 32) < p.Lq;  // warp-uniform
+  const int q_warp0 = qt * 128 + quad * 32;              // first row of this warp
+  const float* bias_blk = (p.bias && warp_live) ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(q_warp0) * p.bias_q_stride : nullptr;
   const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const int nchunk = Lk_pad >> 4;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+  const uint32_t stage_addr = smem_u32(sV) + warp * 4096;
+  const int nchunk = Lk_pad >> 4;           // 16-column chunks
+  const int nunit = (nchunk + 1) >> 1;      // 32-column units
+  const int u_begin = half == 0 ? 0 : (nunit + 1) >> 1;
+  const int u_end = half == 0 ? (nunit + 1) >> 1 : nunit;
   const uint32_t sP_addr = smem_u32(sP);
   float mx = -INFINITY, sum = 0.f;
   if (warp_live) {
-    for (int c0 = 0; c0 < nchunk; c0 += 4) {
-      uint32_t s[4][16];
-      float add[4][16];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < nchunk) tmem_ld_32x16(trow + (c0 + u) * 16, s[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < nchunk) load_additive(p, bias_row, mask_row, (c0 + u) * 16, add[u]);
+    for (int u = u_begin; u < u_end; ++u) {
+      const bool two = (2 * u + 1) < nchunk;  // the last unit may hold a single chunk
+      uint32_t s0[16], s1[16];
+      tmem_ld_32x16(trow + u * 32, s0);
+      if (two) tmem_ld_32x16(trow + u * 32 + 16, s1);
+      float add[32];
+      additive32(p, bias_blk, p.Lq - q_warp0, mask_row, u * 32, stage_addr, lane, add);
       tmem_wait_ld();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c0 + u < nchunk) {
+      for (int j = 0; j < 16; ++j) {
+        const float t = (u * 32 + j < p.Lk) ? fmaf(__uint_as_float(s0[j]), p.scale_log2, add[j]) : -INFINITY;
+        mx = fmaxf(mx, t);
+        s0[j] = __float_as_uint(t);
+      }
+      tmem_st_32x16(trow + u * 32, s0);
+      if (two) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float t = ((c0 + u) * 16 + j < p.Lk) ? fmaf(__uint_as_float(s[u][j]), p.scale_log2, add[u][j]) : -INFINITY;
-            mx = fmaxf(mx, t);
-            s[u][j] = __float_as_uint(t);
-          }
-          tmem_st_32x16(trow + (c0 + u) * 16, s[u]);
+        for (int j = 0; j < 16; ++j) {
+          const float t = (u * 32 + 16 + j < p.Lk) ? fmaf(__uint_as_float(s1[j]), p.scale_log2, add[16 + j]) : -INFINITY;
+          mx = fmaxf(mx, t);
+          s1[j] = __float_as_uint(t);
         }
+        tmem_st_32x16(trow + u * 32 + 16, s1);
       }
     }
     tmem_wait_st();
+    s_red[half * 128 + row] = mx;
+  }
+  __syncthreads();  // max exchange; the bias staging area is free from here on
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_v, Lk_pad * 128);
+    tma_load_2d(sV, &tmap_v, bar_v, h * 64, kvb * p.Lk);  // lands while pass 2 runs
+  }
+  if (warp_live) {
+    mx = fmaxf(mx, s_red[(half ^ 1) * 128 + row]);
     if (mx == -INFINITY) mx = 0.f;
-    const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+    const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * Lk_pad;
-    for (int c0 = 0; c0 < nchunk; c0 += 2) {
+    const int c_begin = 2 * u_begin, c_end = min(nchunk, 2 * u_end);
+    for (int c0 = c_begin; c0 < c_end; c0 += 2) {
       uint32_t s[2][16];
       tmem_ld_32x16(trow + c0 * 16, s[0]);
-      if (c0 + 1 < nchunk) tmem_ld_32x16(trow + (c0 + 1) * 16, s[1]);
+      if (c0 + 1 < c_end) tmem_ld_32x16(trow + (c0 + 1) * 16, s[1]);
       tmem_wait_ld();
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (c0 + u < nchunk) {
-          const int c = c0 + u;
+      for (int v = 0; v < 2; ++v) {
+        if (c0 + v < c_end) {
+          const int c = c0 + v;
           float pr[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            pr[j] = exp2f(__uint_as_float(s[u][j]) - mx);
+            pr[j] = fast_exp2(__uint_as_float(s[v][j]) - mx);
             sum += pr[j];
           }
           if (p.dropout_p > 0.f) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + c * 16 + j) >> 2));
-              pr[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
-              pr[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
-              pr[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
-              pr[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+            for (int j = 0; j < 16; j += 8) {
+              float k[8];
+              drop8(p.seed, p.offset, (drop_base + c * 16 + j) >> 3, dc, k);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pr[j + i] *= k[i];
             }
           }
           st_shared_v4(sP_addr + swz_off(row, c * 16), pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
@@ -210,6 +304,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   }
+  __syncthreads();  // every thread has read the partner's max before the slots are reused for the sums
+  if (warp_live) s_red[half * 128 + row] = sum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -231,29 +327,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
-  {
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    uint32_t o[16];
-    __nv_bfloat16* dst = p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      tmem_ld_32x16(trow + c * 16, o);
-      tmem_wait_ld();
-      if (qvalid) {
-        uint4 v0, v1;
-        v0.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        v0.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        v0.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        v0.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        v1.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-        v1.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-        v1.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-        v1.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-        *reinterpret_cast<uint4*>(dst + c * 16) = v0;
-        *reinterpret_cast<uint4*>(dst + c * 16 + 8) = v1;
-      }
-    }
-    if (qvalid) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = mx + log2f(sum);
+  if (warp_live) {  // each half writes 32 of the 64 output dims of its rows
+    const float tot = sum + s_red[(half ^ 1) * 128 + row];
+    const float inv = tot > 0.f ? 1.0f / tot : 0.f;
+    __nv_bfloat16* dst = p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64 + half * 32;
+    store_row_bf16<2>(dst, trow + half * 32, inv, qvalid);
+    if (qvalid && half == 0) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = mx + log2f(tot);
   }
   tc_fence_before();
   __syncthreads();
@@ -264,36 +343,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: grid (H, B), 128 threads, 1 CTA / SM (TMEM 512 columns)
+// backward: grid (H, B), 256 threads, 1 CTA / SM (TMEM 512 columns)
 // ---------------------------------------------------------------------------------------------
 constexpr int BWD_SQ = 0, BWD_SDO = 32768, BWD_SK = 65536, BWD_SV = 81920, BWD_SP = 98304, BWD_SDS = 131072;
-constexpr int BWD_BARS = 163840;
+constexpr int BWD_STAGE = 163840;              // bias staging, 8 warps x 4 KB
+constexpr int BWD_BARS = BWD_STAGE + 32768;
 constexpr int BWD_SMEM = BWD_BARS + 1024 + 128;
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
-__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t tcol_addr, float mul, bool valid) {
-  uint32_t o[16];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    tmem_ld_32x16(tcol_addr + c * 16, o);
-    tmem_wait_ld();
-    if (valid) {
-      uint4 v0, v1;
-      v0.x = pack_bf16x2(__uint_as_float(o[0]) * mul, __uint_as_float(o[1]) * mul);
-      v0.y = pack_bf16x2(__uint_as_float(o[2]) * mul, __uint_as_float(o[3]) * mul);
-      v0.z = pack_bf16x2(__uint_as_float(o[4]) * mul, __uint_as_float(o[5]) * mul);
-      v0.w = pack_bf16x2(__uint_as_float(o[6]) * mul, __uint_as_float(o[7]) * mul);
-      v1.x = pack_bf16x2(__uint_as_float(o[8]) * mul, __uint_as_float(o[9]) * mul);
-      v1.y = pack_bf16x2(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
-      v1.z = pack_bf16x2(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
-      v1.w = pack_bf16x2(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
-      *reinterpret_cast<uint4*>(dst + c * 16) = v0;
-      *reinterpret_cast<uint4*>(dst + c * 16 + 8) = v1;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const AttnParams p) {
@@ -304,7 +362,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_mma = bar_q + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 3);
 
-  const int warp = threadIdx.x >> 5, row = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
   const int h = blockIdx.x, b = blockIdx.y;
   const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int nqb = (p.Lq + 127) >> 7, nkb = (p.Lk + 127) >> 7;
@@ -323,8 +383,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const uint32_t sbase = smem_u32(smem);
+  const uint32_t stage_addr = sbase + BWD_STAGE + warp * 4096;
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_q, nqb * 2 * 16384);
@@ -334,7 +395,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   }
 
-  // per-row statistics: lse (log2 domain) and delta = rowsum(dO ∘ O), for each query block
+  // per-row statistics (both halves of a row compute them): lse (log2 domain) and delta = rowsum(dO ∘ O)
   float lse2[2] = {0.f, 0.f}, delta[2] = {0.f, 0.f};
   for (int qb = 0; qb < nqb; ++qb) {
     const int q = qb * 128 + row;
@@ -354,7 +415,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   }
 
-  const float inv_keep = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  const DropCfg dc = make_drop(p.dropout_p);
   uint32_t mma_phase = 0;
   const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
@@ -362,6 +423,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   for (int kb = 0; kb < nkb; ++kb) {
     // valid keys of this block in 16-column chunks: S/dP are only formed (N = nkc*16) and consumed up to there
     const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
+    const int nunit = (nkc + 1) >> 1;  // 32-column units, split between the two halves
+    const int u_begin = half == 0 ? 0 : (nunit + 1) >> 1;
+    const int u_end = half == 0 ? (nunit + 1) >> 1 : nunit;
     const uint32_t idesc_skb = make_idesc_bf16(128, nkc * 16, 0, 0);
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(bar_kv, 2 * 16384);
@@ -390,62 +454,57 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mma_phase ^= 1;
       tc_fence_after();
 
-      // ---- P and dS for this (q block, key block) tile; thread == query row ----
+      // ---- P and dS for this (q block, key block) tile; thread == query row, half == column range ----
       const int q = qb * 128 + row;
       const bool qvalid = q < p.Lq;
-      const float* bias_row = (p.bias && qvalid) ? p.bias + h * p.bias_h_stride + q * p.bias_q_stride : nullptr;
+      const int q_warp0 = qb * 128 + quad * 32;
+      // a warp whose rows all lie beyond Lq has nothing to produce (its P/dS rows only feed dQ rows never stored)
+      const bool warp_live = q_warp0 < p.Lq;
+      const float* bias_blk = (p.bias && warp_live) ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(q_warp0) * p.bias_q_stride : nullptr;
       const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
       const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad;
       __nv_bfloat16* ds_row =
           (p.ds_out && qvalid) ? p.ds_out + b * p.ds_b_stride + h * p.ds_h_stride + q * p.ds_q_stride : nullptr;
       const float my_lse = lse2[qb], my_delta = delta[qb];
-      // rows of this q block that any MMA will read as a contraction index, in 16-row groups; a warp whose rows all
-      // lie beyond them has nothing to produce (its P/dS rows only feed dQ rows that are never stored)
-      const bool warp_live = (qb * 128 + warp * 32) < p.Lq;
-      // two 16-column chunks per iteration: their TMEM reads and bias/mask loads are all issued before the wait
       if (warp_live) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < nkc; c0 += 2) {
+        for (int u = u_begin; u < u_end; ++u) {
+          const bool two = (2 * u + 1) < nkc;
           uint32_t s[2][16], dp[2][16];
-          float add[2][16];
-          bool live[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (c0 + u < nkc) {
-              tmem_ld_32x16(trow + TM_S + (c0 + u) * 16, s[u]);
-              tmem_ld_32x16(trow + TM_DP + (c0 + u) * 16, dp[u]);
-            }
+          tmem_ld_32x16(trow + TM_S + u * 32, s[0]);
+          tmem_ld_32x16(trow + TM_DP + u * 32, dp[0]);
+          if (two) {
+            tmem_ld_32x16(trow + TM_S + u * 32 + 16, s[1]);
+            tmem_ld_32x16(trow + TM_DP + u * 32 + 16, dp[1]);
           }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            live[u] = qvalid && (c0 + u < nkc);
-            if (live[u]) load_additive(p, bias_row, mask_row, kb * 128 + (c0 + u) * 16, add[u]);
-          }
+          float add[32];
+          additive32(p, bias_blk, p.Lq - q_warp0, mask_row, kb * 128 + u * 32, stage_addr, lane, add);
           tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (c0 + u >= nkc) continue;  // warp-uniform
-            const int c = c0 + u;
+          for (int v = 0; v < 2; ++v) {
+            if (v == 1 && !two) continue;  // warp-uniform
+            const int c = 2 * u + v;
             const int k0 = kb * 128 + c * 16;
             float pr[16], ds[16];
-            if (live[u]) {
+            if (qvalid) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float t = fmaf(__uint_as_float(s[u][j]), p.scale_log2, add[u][j]);
-                pr[j] = (k0 + j < p.Lk) ? exp2f(t - my_lse) : 0.f;
-                ds[j] = __uint_as_float(dp[u][j]);
+                const float t = fmaf(__uint_as_float(s[v][j]), p.scale_log2, add[16 * v + j]);
+                pr[j] = (k0 + j < p.Lk) ? fast_exp2(t - my_lse) : 0.f;
+                ds[j] = __uint_as_float(dp[v][j]);
               }
               if (p.dropout_p > 0.f) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const uint4 r = philox4x32(p.seed, p.offset + ((drop_base + k0 + j) >> 2));
-                  const float k0_ = dropout_keep(r.x, p.dropout_p, inv_keep), k1_ = dropout_keep(r.y, p.dropout_p, inv_keep);
-                  const float k2_ = dropout_keep(r.z, p.dropout_p, inv_keep), k3_ = dropout_keep(r.w, p.dropout_p, inv_keep);
-                  // dS uses the un-dropped P; the P that feeds dV is the dropped one
-                  const float p0 = pr[j], p1 = pr[j + 1], p2 = pr[j + 2], p3 = pr[j + 3];
-                  ds[j] = p0 * (ds[j] * k0_ - my_delta); ds[j + 1] = p1 * (ds[j + 1] * k1_ - my_delta);
-                  ds[j + 2] = p2 * (ds[j + 2] * k2_ - my_delta); ds[j + 3] = p3 * (ds[j + 3] * k3_ - my_delta);
-                  pr[j] = p0 * k0_; pr[j + 1] = p1 * k1_; pr[j + 2] = p2 * k2_; pr[j + 3] = p3 * k3_;
+                for (int j = 0; j < 16; j += 8) {
+                  float k[8];
+                  drop8(p.seed, p.offset, (drop_base + k0 + j) >> 3, dc, k);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    // dS uses the un-dropped P; the P that feeds dV is the dropped one
+                    const float pu = pr[j + i];
+                    ds[j + i] = pu * (ds[j + i] * k[i] - my_delta);
+                    pr[j + i] = pu * k[i];
+                  }
                 }
               } else {
 #pragma unroll
@@ -482,8 +541,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t aq = sbase + BWD_SQ + qb * 16384, ado = sbase + BWD_SDO + qb * 16384;
         const uint32_t ak = sbase + BWD_SK;
         const uint32_t ap = sbase + BWD_SP, ads = sbase + BWD_SDS;
-        // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
         const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
+        // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
         for (int ks = 0; ks < nkc; ++ks)
           umma_bf16(tmem + TM_DQ + qb * 64, make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                     make_smem_desc(ak + ks * 2048, 8192, 1024), idesc_dq, (kb | ks) != 0);
@@ -499,7 +558,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       __syncwarp();
     }
-    // ---- drain dK / dV of this key block; thread == key row ----
+    // ---- drain dK / dV of this key block; thread == key row, each half stores 32 of the 64 dims ----
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
@@ -507,8 +566,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int key = kb * 128 + row;
       const bool kvalid = key < p.Lk;
       const int64_t r = static_cast<int64_t>(b) * p.Lk + key;
-      store_row64_bf16(p.dk + r * p.ld_dk + h * 64, trow + TM_DK, p.scale, kvalid);
-      store_row64_bf16(p.dv + r * p.ld_dv + h * 64, trow + TM_DV, 1.0f, kvalid);
+      store_row_bf16<2>(p.dk + r * p.ld_dk + h * 64 + half * 32, trow + TM_DK + half * 32, p.scale, kvalid);
+      store_row_bf16<2>(p.dv + r * p.ld_dv + h * 64 + half * 32, trow + TM_DV + half * 32, 1.0f, kvalid);
     }
     tc_fence_before();
     __syncthreads();
@@ -517,8 +576,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // ---- drain dQ (all MMAs retired: the last commit covered them) ----
   for (int qb = 0; qb < nqb; ++qb) {
     const int q = qb * 128 + row;
-    store_row64_bf16(p.dq + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_dq + h * 64, trow + TM_DQ + qb * 64, p.scale,
-                     q < p.Lq);
+    store_row_bf16<2>(p.dq + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_dq + h * 64 + half * 32,
+                      trow + TM_DQ + qb * 64 + half * 32, p.scale, q < p.Lq);
   }
   tc_fence_before();
   __syncthreads();
@@ -558,11 +617,11 @@ int check_common(const X2kAttnArgs& a, const char* who) {
   X2K_REQUIRE(a.Lk <= 256, "%s: Lk=%d > 256 is not supported by this kernel", who, a.Lk);
   X2K_REQUIRE(a.ld_q % 8 == 0 && a.ld_k % 8 == 0 && a.ld_v % 8 == 0 && a.ld_o % 8 == 0, "%s: ld must be multiples of 8", who);
   const int Lk_pad = (a.Lk + 15) & ~15;
-  X2K_REQUIRE(!a.bias || (a.bias_q_stride % 4 == 0 && a.bias_h_stride % 4 == 0 && a.bias_q_stride >= Lk_pad),
-              "%s: bias strides must be multiples of 4 and >= Lk_pad=%d", who, Lk_pad);
+  X2K_REQUIRE(!a.bias || (a.bias_q_stride % 4 == 0 && a.bias_h_stride % 4 == 0 && a.bias_q_stride >= ((a.Lk + 31) & ~31)),
+              "%s: bias strides must be multiples of 4 and the row stride >= Lk rounded up to 32 (%d)", who, (a.Lk + 31) & ~31);
   X2K_REQUIRE(!a.mask || (a.mask_b_stride % 4 == 0 && a.mask_q_stride % 4 == 0 &&
-                          (a.mask_q_stride == 0 ? a.mask_b_stride >= Lk_pad : a.mask_q_stride >= Lk_pad)),
-              "%s: mask strides must be multiples of 4 and cover Lk_pad=%d", who, Lk_pad);
+                          (a.mask_q_stride == 0 ? a.mask_b_stride >= ((a.Lk + 31) & ~31) : a.mask_q_stride >= ((a.Lk + 31) & ~31))),
+              "%s: mask strides must be multiples of 4 and cover Lk rounded up to 32 (%d)", who, (a.Lk + 31) & ~31);
   X2K_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "%s: dropout_p", who);
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   X2K_REQUIRE(al16(a.q) && al16(a.k) && al16(a.v) && al16(a.o) && al16(a.bias) && al16(a.mask), "%s: 16-byte alignment", who);
@@ -608,7 +667,7 @@ extern "C" int x2k_attn_fwd(const X2kAttnArgs* args, void* stream_) {
     attr_set = true;
   }
   dim3 grid((a.Lq + 127) / 128, a.H, a.B);
-  attn_fwd_kernel<<<grid, 128, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;
@@ -640,7 +699,7 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
     attr_set = true;
   }
   dim3 grid(a.H, a.B);
-  attn_bwd_kernel<<<grid, 128, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;

@@ -234,12 +234,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-// Philox4x32-10.  One call yields 4 x 32 random bits for counter (ctr) under key (seed).
+// Philox4x32 counter-based RNG (Salmon et al., SC'11).  ROUNDS = 10 is the standard generator; the dropout
+// stream uses the 7-round variant (the cheapest Philox4x32 that passes BigCrush).
+template <int ROUNDS>
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x2B992DDFu, c3 = 0u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < ROUNDS; ++i) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
@@ -251,12 +253,35 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-scale of element `idx` (idx = linear element index): 1/(1-p) if kept else 0.
-// Elements 4q..4q+3 share one Philox call; `r` is that call's output.
-__device__ __forceinline__ float dropout_keep(uint32_t rbits, float p, float inv_keep) {
-  // uniform in [0,1): top 24 bits
-  const float u = static_cast<float>(rbits >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+
+// Dropout: element e of a tensor draws 16 random bits: Philox4x32-7(seed, offset + (e >> 3)) yields 8 x 16 bits,
+// element e uses word (e & 7) >> 1, low half if e is even else high half.  It is kept iff r16 >= thr with
+// thr = round(p * 65536); kept values are scaled by 65536 / (65536 - thr) (unbiased for the realised keep rate).
+struct DropCfg {
+  uint32_t thr;
+  float scale;
+};
+__host__ __device__ __forceinline__ DropCfg make_drop(float p) {
+  DropCfg d;
+  d.thr = p > 0.f ? static_cast<uint32_t>(p * 65536.0f + 0.5f) : 0u;
+  d.scale = 65536.0f / (65536.0f - static_cast<float>(d.thr));
+  return d;
+}
+// keep-scales of the 8 consecutive elements of group `grp` (element index >> 3)
+__device__ __forceinline__ void drop8(uint64_t seed, uint64_t offset, uint64_t grp, const DropCfg& d, float (&k)[8]) {
+  const uint4 r = philox4x32<7>(seed, offset + grp);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    k[2 * i] = (w[i] & 0xFFFFu) >= d.thr ? d.scale : 0.0f;
+    k[2 * i + 1] = (w[i] >> 16) >= d.thr ? d.scale : 0.0f;
+  }
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 #endif  // __CUDACC__

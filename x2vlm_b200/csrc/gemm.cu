@@ -35,7 +35,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
@@ -119,16 +120,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
     }
   }
   if (p.dropout_p > 0.0f) {
-    const float inv_keep = 1.0f / (1.0f - p.dropout_p);
+    const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
-    // N is a multiple of 4 whenever dropout is used (checked on the host), so base % 4 == 0.
+    // N is a multiple of 8 whenever dropout is used (checked on the host), so base % 8 == 0.
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const uint4 r = philox4x32(p.dropout_seed, p.dropout_offset + ((base + j) >> 2));
-      v[j] *= dropout_keep(r.x, p.dropout_p, inv_keep);
-      v[j + 1] *= dropout_keep(r.y, p.dropout_p, inv_keep);
-      v[j + 2] *= dropout_keep(r.z, p.dropout_p, inv_keep);
-      v[j + 3] *= dropout_keep(r.w, p.dropout_p, inv_keep);
+    for (int j = 0; j < 32; j += 8) {
+      float k[8];
+      drop8(p.dropout_seed, p.dropout_offset, (base + j) >> 3, dc, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
     }
   }
   if (p.gamma) {
@@ -206,6 +206,155 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coalesced epilogue.  tcgen05.ld hands every thread one ROW of the accumulator, but a warp-wide access in which
+// each lane touches a different row costs 32 L1 wavefronts / 32 half-filled sectors per instruction.  Every
+// per-element tensor of the epilogue (pre-activation, aux, residual, outputs) therefore goes through a per-warp
+// [32][33] fp32 transpose tile in shared memory (the +1 padding makes both access patterns conflict-free): global
+// loads/stores are issued with lanes sweeping contiguous 128-byte row segments (4 or 8 rows per instruction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_put(float* st, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+  __syncwarp();
+}
+__device__ __forceinline__ void st_get(const float* st, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = st[lane * 33 + j];
+  __syncwarp();
+}
+// tile [rows x 32] bf16 at `dst` (row stride ld) <- staging
+__device__ __forceinline__ void st_store_bf16(const float* st, int lane, __nv_bfloat16* dst, int64_t ld, int rows) {
+  const int c = (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    const float* s = st + r * 33 + c;
+    uint4 q;
+    q.x = pack_bf16x2(s[0], s[1]); q.y = pack_bf16x2(s[2], s[3]); q.z = pack_bf16x2(s[4], s[5]); q.w = pack_bf16x2(s[6], s[7]);
+    if (r < rows) *reinterpret_cast<uint4*>(dst + r * ld + c) = q;
+  }
+  __syncwarp();
+}
+// tile [rows x 32] fp32 <- staging; mode 0 = store, 1 = atomic accumulate (split-K)
+__device__ __forceinline__ void st_store_f32(const float* st, int lane, float* dst, int64_t ld, int rows, bool atomic) {
+  const int c = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const float* s = st + r * 33 + c;
+    const float4 o = make_float4(s[0], s[1], s[2], s[3]);
+    if (r < rows) {
+      if (atomic) atomicAdd(reinterpret_cast<float4*>(dst + r * ld + c), o);
+      else *reinterpret_cast<float4*>(dst + r * ld + c) = o;
+    }
+  }
+  __syncwarp();
+}
+// staging <- tile [rows x 32] fp32 / bf16 (rows past `rows` are filled with 0)
+__device__ __forceinline__ void st_load_f32(float* st, int lane, const float* src, int64_t ld, int rows) {
+  const int c = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) v = *reinterpret_cast<const float4*>(src + r * ld + c);
+    float* s = st + r * 33 + c;
+    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void st_load_bf16(float* st, int lane, const __nv_bfloat16* src, int64_t ld, int rows) {
+  const int c = (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) q = __ldg(reinterpret_cast<const uint4*>(src + r * ld + c));
+    float* s = st + r * 33 + c;
+    s[0] = bf16_lo(q.x); s[1] = bf16_hi(q.x); s[2] = bf16_lo(q.y); s[3] = bf16_hi(q.y);
+    s[4] = bf16_lo(q.z); s[5] = bf16_hi(q.z); s[6] = bf16_lo(q.w); s[7] = bf16_hi(q.w);
+  }
+  __syncwarp();
+}
+
+// Fused epilogue of a full 32-column chunk for the 32 rows [mw, mw+32) owned by this warp (thread == row mw+lane);
+// `rows` = number of those rows inside the matrix.  Same arithmetic, in the same order, as epilogue_chunk.
+__device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, float* st, int lane, int mw, int rows, int n0,
+                                                         uint32_t (&acc)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  const int m = mw + lane;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (p.preact_out) {
+    st_put(st, lane, v);
+    st_store_bf16(st, lane, p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0, p.ld_preact, rows);
+  }
+  if (p.act == X2K_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == X2K_ACT_GELU_BWD) {
+    float a[32];
+    st_load_bf16(st, lane, p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0, p.ld_aux, rows);
+    st_get(st, lane, a);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
+  }
+  if (p.dropout_p > 0.0f) {
+    const DropCfg dc = make_drop(p.dropout_p);
+    const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float k[8];
+      drop8(p.dropout_seed, p.dropout_offset, (base + j) >> 3, dc, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
+    }
+  }
+  if (p.gamma) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
+      v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+    }
+  }
+  if (p.row_scale) {
+    const float sc = __ldg(p.row_scale + min(m, p.M - 1) / p.rows_per_scale);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= sc;
+  }
+  if (p.residual) {
+    float a[32];
+    st_load_f32(st, lane, p.residual + static_cast<int64_t>(mw) * p.ld_res + n0, p.ld_res, rows);
+    st_get(st, lane, a);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += a[j];
+  }
+  if (p.out_f32) {
+    float* dst = p.out_f32 + static_cast<int64_t>(mw) * p.ld_out_f32 + n0;
+    if (p.accumulate && p.split_k <= 1) {
+      float a[32];
+      st_load_f32(st, lane, dst, p.ld_out_f32, rows);
+      st_get(st, lane, a);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += a[j];
+    }
+    st_put(st, lane, v);
+    st_store_f32(st, lane, dst, p.ld_out_f32, rows, p.split_k > 1);
+  }
+  if (p.out_bf16) {
+    st_put(st, lane, v);
+    st_store_bf16(st, lane, p.out_bf16 + static_cast<int64_t>(mw) * p.ld_out_bf16 + n0, p.ld_out_bf16, rows);
+  }
+}
+
 template <int BLOCK_N, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -215,7 +364,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -350,7 +500,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_32x32(taddr + c, acc);
         tmem_wait_ld();
         const int n = n0 + half * COLS_PER_WARP + c;
-        if (m < p.M && n < p.N) epilogue_chunk(p, m, n, acc);
+        const int mw = m0 + quad * 32;  // first row of this warp
+        if (mw < p.M && n < p.N) {
+          if (n + 32 <= p.N) epilogue_chunk_coalesced(p, epi_stage + ew * (32 * 33), lane, mw, min(32, p.M - mw), n, acc);
+          else if (m < p.M) epilogue_chunk(p, m, n, acc);  // ragged last chunk: thread-per-row path
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -426,7 +580,7 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   X2K_REQUIRE(a.out_bf16 || a.out_f32 || a.preact_out, "x2k_gemm: no output");
   X2K_REQUIRE(!a.accumulate || a.out_f32, "x2k_gemm: accumulate needs out_f32");
   X2K_REQUIRE(a.act != X2K_ACT_GELU_BWD || a.aux, "x2k_gemm: GELU_BWD needs aux");
-  X2K_REQUIRE(!(a.dropout_p > 0.f) || (a.N % 4 == 0 && a.dropout_p < 1.f), "x2k_gemm: dropout needs N%%4==0, p<1");
+  X2K_REQUIRE(!(a.dropout_p > 0.f) || (a.N % 8 == 0 && a.dropout_p < 1.f), "x2k_gemm: dropout needs N%%8==0, p<1");
   X2K_REQUIRE(!a.row_scale || a.rows_per_scale > 0, "x2k_gemm: rows_per_scale must be > 0");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   X2K_REQUIRE(al16(a.bias) && al16(a.gamma) && al16(a.residual) && al16(a.out_f32) && al16(a.out_bf16) &&

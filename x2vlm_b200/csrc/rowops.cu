@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
   const int r1 = min(M, r0 + rows_per_block);
   float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
   if (gamma) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
-  const float inv_keep = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  const DropCfg dc = make_drop(dropout_p);
   float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int m = r0; m < r1; ++m) {
@@ -175,11 +175,10 @@ __global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
     d.x *= gm.x; d.y *= gm.y; d.z *= gm.z; d.w *= gm.w;
     if (dropout_p > 0.f) {
       const uint64_t idx = static_cast<uint64_t>(m) * static_cast<uint64_t>(N) + static_cast<uint64_t>(n);
-      const uint4 r = philox4x32(seed, offset + (idx >> 2));
-      d.x *= dropout_keep(r.x, dropout_p, inv_keep);
-      d.y *= dropout_keep(r.y, dropout_p, inv_keep);
-      d.z *= dropout_keep(r.z, dropout_p, inv_keep);
-      d.w *= dropout_keep(r.w, dropout_p, inv_keep);
+      float k[8];
+      drop8(seed, offset, idx >> 3, dc, k);
+      const int o = static_cast<int>(idx & 4);  // this thread's 4 columns are the low or the high half of the group
+      d.x *= k[o]; d.y *= k[o + 1]; d.z *= k[o + 2]; d.w *= k[o + 3];
     }
     sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
     if (g) {
@@ -197,7 +196,11 @@ __global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
   }
 }
 
-// thread owns 8 bf16 columns (16 B)
+// thread owns 8 bf16 columns (16 B); four independent row loads are issued per iteration (memory-level parallelism)
+__device__ __forceinline__ void acc8(float (&s)[8], const uint4& q) {
+  s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+  s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+}
 __global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
                                                           float* __restrict__ dcol, int rows_per_block) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -205,12 +208,16 @@ __global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* _
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-  for (int m = r0; m < r1; ++m) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(m) * ld + n));
-    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
-    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+  const __nv_bfloat16* px = x + static_cast<int64_t>(r0) * ld + n;
+  int m = r0;
+  for (; m + 4 <= r1; m += 4, px += 4 * ld) {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(px));
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(px + ld));
+    const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(px + 2 * ld));
+    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(px + 3 * ld));
+    acc8(s, q0); acc8(s, q1); acc8(s, q2); acc8(s, q3);
   }
+  for (; m < r1; ++m, px += ld) acc8(s, __ldg(reinterpret_cast<const uint4*>(px)));
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(dcol + n + j, s[j]);
 }

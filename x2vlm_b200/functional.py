@@ -223,7 +223,7 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.layernorm_fwd(x2, n1w, n1b, 1e-6, y_bf16=ln1, mean=mean1, rstd=rstd1)
         qkv = _empty_bf16(M, 3 * D, dev=dev)
         ops.gemm(ln1, sh["qkv"].get(), M, 3 * D, D, bias=qkv_bias, out_bf16=qkv)
-        ldb = ops.pad16(N)
+        ldb = ops.pad32(N)
         bias_g = None
         if table is not None:
             bias_g = torch.empty(H, N, ldb, dtype=torch.float32, device=dev)

@@ -202,3 +202,8 @@ def adamw_flat(p, g, m, v, p_bf16, n, seg_end, seg_lr, seg_wd, beta1, beta2, eps
 
 def pad16(n):
     return (n + 15) // 16 * 16
+
+
+def pad32(n):
+    """Row stride (in elements) of attention bias / mask buffers: the kernels read them in 32-column units."""
+    return (n + 31) // 32 * 32

@@ -174,7 +174,7 @@ class BertLayer(nn.Module):
 
 
 def _pad_mask(ext_mask, B, Lq, Lk, device):
-    """Extended additive mask [B,1,1,Lk] / [B,1,Lq,Lk] (or None) -> (fp32 [B,(Lq,)pad16(Lk)] contiguous, is_3d)."""
+    """Extended additive mask [B,1,1,Lk] / [B,1,Lq,Lk] (or None) -> (fp32 [B,(Lq,)pad32(Lk)] contiguous, is_3d)."""
     if ext_mask is None:
         return None, False
     m = ext_mask.to(device=device, dtype=torch.float32)
@@ -185,7 +185,7 @@ def _pad_mask(ext_mask, B, Lq, Lk, device):
     if m.shape[0] != B:
         m = m.expand(B, -1, -1)
     per_query = m.shape[1] != 1
-    ld = ops.pad16(Lk)
+    ld = ops.pad32(Lk)
     out = torch.zeros(B, m.shape[1], ld, dtype=torch.float32, device=device)
     out[:, :, :Lk] = m
     return (out if per_query else out[:, 0].contiguous()), per_query

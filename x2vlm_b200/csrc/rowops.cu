@@ -275,21 +275,42 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
   const float stepf = static_cast<float>(step_dev ? *step_dev : step);
   const float bc1 = 1.0f - powf(beta1, stepf);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, stepf));
+  // 4 consecutive parameters per thread (16-byte accesses).  Arena offsets are multiples of 8 and every parameter
+  // that follows another one inside a packed group has a size that is a multiple of 4, so a float4 never straddles
+  // two segments: one segment lookup per float4.
+  const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (int64_t i4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const int64_t i = i4 << 2;
     int lo = 0, hi = n_seg - 1;  // first segment with seg_end > i
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (__ldg(seg_end + mid) > i) hi = mid; else lo = mid + 1;
     }
     const float lr = __ldg(seg_lr + lo), wd = __ldg(seg_wd + lo);
-    const float gi = g[i] * gs;
-    float pi = p[i] * (1.0f - lr * wd);
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+    const float decay = 1.0f - lr * wd, step_size = lr / bc1;
+    float4 pv = reinterpret_cast<float4*>(p)[i4];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i4];
+    float4 mv = reinterpret_cast<float4*>(m)[i4];
+    float4 vv = reinterpret_cast<float4*>(v)[i4];
+#define X2K_ADAM1(c)                                                         \
+    {                                                                        \
+      const float gi = gv.c * gs;                                            \
+      mv.c = beta1 * mv.c + (1.0f - beta1) * gi;                             \
+      vv.c = beta2 * vv.c + (1.0f - beta2) * gi * gi;                        \
+      pv.c = pv.c * decay - step_size * mv.c / (sqrtf(vv.c) / bc2_sqrt + eps); \
+    }
+    X2K_ADAM1(x) X2K_ADAM1(y) X2K_ADAM1(z) X2K_ADAM1(w)
+#undef X2K_ADAM1
+    reinterpret_cast<float4*>(p)[i4] = pv;
+    reinterpret_cast<float4*>(m)[i4] = mv;
+    reinterpret_cast<float4*>(v)[i4] = vv;
+    if (p_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(pv.x, pv.y);
+      pk.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(p_bf16)[i4] = pk;
+    }
   }
 }
 
@@ -452,7 +473,10 @@ extern "C" int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   X2K_REQUIRE(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && n_seg > 0 && (step > 0 || step_dev),
               "x2k_adamw_flat: bad arguments");
-  int64_t blocks = (n + 255) / 256;
+  X2K_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
+              "x2k_adamw_flat: buffers must be 16-byte aligned and n a multiple of 4");
+  int64_t blocks = (n / 4 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n,

@@ -214,7 +214,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
-  mbar_wait(bar_mma, 0);
+  mbar_wait_warp(bar_mma, 0);
   tc_fence_after();
 
   // ---- softmax: pass 1 forms t = scale·qk + bias + mask (log2 domain), row max, writes t back to TMEM ----
@@ -325,7 +325,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
-  mbar_wait(bar_mma, 1);
+  mbar_wait_warp(bar_mma, 1);
   tc_fence_after();
   if (warp_live) {  // each half writes 32 of the 64 output dims of its rows
     const float tot = sum + s_red[(half ^ 1) * 128 + row];
@@ -450,7 +450,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_commit(bar_mma);
       }
       __syncwarp();
-      mbar_wait(bar_mma, mma_phase);
+      mbar_wait_warp(bar_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
 
@@ -559,7 +559,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
     }
     // ---- drain dK / dV of this key block; thread == key row, each half stores 32 of the 64 dims ----
-    mbar_wait(bar_mma, mma_phase);
+    mbar_wait_warp(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
     {

@@ -86,29 +86,38 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin on the given phase parity.  A watchdog traps (instead of hanging the GPU box) if the
-// barrier never flips — a broken pipeline must fail loudly.
+// Wait for the given phase parity.  try_wait suspends the thread in hardware (up to the hinted time) instead of
+// burning issue slots; a watchdog traps (instead of hanging the GPU box) if the barrier never flips — a broken
+// pipeline must fail loudly.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(addr), "r"(parity), "r"(20000u)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
   const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: a healthy pipeline never waits that long
-      printf("x2k: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr,
-             parity);
+  uint32_t spins = 0;
+  while (!mbar_try_wait(addr, parity)) {
+    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {  // ~2 s: a healthy pipeline never waits that long
+      printf("x2k: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
       __trap();
     }
   }
+}
+// One lane polls, the rest of the warp sleeps at the warp barrier (keeps 31 lanes out of the issue slots).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---- TMA ----

@@ -35,7 +35,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 33 * 4;  // per-warp [32][33] fp32 transpose tile
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 80;  // per-warp transpose tile (EPI_TILE_BYTES)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -207,82 +207,79 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
 }
 
 // ---------------------------------------------------------------------------------------------
-// Coalesced epilogue.  tcgen05.ld hands every thread one ROW of the accumulator, but a warp-wide access in which
-// each lane touches a different row costs 32 L1 wavefronts / 32 half-filled sectors per instruction.  Every
+// Coalesced epilogue.  tcgen05.ld hands every thread one ROW of the accumulator, but a warp-wide global access in
+// which each lane touches a different row costs 32 L1 wavefronts / 32 half-filled sectors per instruction.  Every
 // per-element tensor of the epilogue (pre-activation, aux, residual, outputs) therefore goes through a per-warp
-// [32][33] fp32 transpose tile in shared memory (the +1 padding makes both access patterns conflict-free): global
-// loads/stores are issued with lanes sweeping contiguous 128-byte row segments (4 or 8 rows per instruction).
+// transpose tile in shared memory: 32 rows x 64 payload bytes (32 bf16 or 16 fp32 columns) with an 80-byte row
+// pitch, which keeps 16-byte accesses conflict-free on the thread-per-row side (8 lanes x 80 B hit disjoint bank
+// quads).  On the global side lane l handles 16 bytes of row 8*it + l/4: every instruction moves 8 rows x 64
+// contiguous bytes.  fp32 tensors are processed as two 16-column halves.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_put(float* st, int lane, const float (&v)[32]) {
+constexpr int EPI_ROW_PITCH = 80;
+constexpr int EPI_TILE_BYTES = 32 * EPI_ROW_PITCH;  // 2560 B per epilogue warp
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// thread-per-row side: this thread's 16 words <-> row `lane` of the tile
+__device__ __forceinline__ void tile_put(uint32_t sa, int lane, const uint32_t (&w)[16]) {
+  const uint32_t r = sa + lane * EPI_ROW_PITCH;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+  for (int j = 0; j < 4; ++j) sts128(r + 16 * j, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
   __syncwarp();
 }
-__device__ __forceinline__ void st_get(const float* st, int lane, float (&v)[32]) {
+__device__ __forceinline__ void tile_get(uint32_t sa, int lane, uint32_t (&w)[16]) {
+  const uint32_t r = sa + lane * EPI_ROW_PITCH;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = st[lane * 33 + j];
-  __syncwarp();
-}
-// tile [rows x 32] bf16 at `dst` (row stride ld) <- staging
-__device__ __forceinline__ void st_store_bf16(const float* st, int lane, __nv_bfloat16* dst, int64_t ld, int rows) {
-  const int c = (lane & 3) * 8;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2);
-    const float* s = st + r * 33 + c;
-    uint4 q;
-    q.x = pack_bf16x2(s[0], s[1]); q.y = pack_bf16x2(s[2], s[3]); q.z = pack_bf16x2(s[4], s[5]); q.w = pack_bf16x2(s[6], s[7]);
-    if (r < rows) *reinterpret_cast<uint4*>(dst + r * ld + c) = q;
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = lds128(r + 16 * j);
+    w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
   }
   __syncwarp();
 }
-// tile [rows x 32] fp32 <- staging; mode 0 = store, 1 = atomic accumulate (split-K)
-__device__ __forceinline__ void st_store_f32(const float* st, int lane, float* dst, int64_t ld, int rows, bool atomic) {
-  const int c = (lane & 7) * 4;
+// global side: tile <-> 32 rows x 64 bytes at `g` (row pitch ld_bytes); rows >= `rows` are skipped / zero-filled
+__device__ __forceinline__ void tile_store(uint32_t sa, int lane, uint8_t* g, int64_t ld_bytes, int rows, bool atomic_f32) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const float* s = st + r * 33 + c;
-    const float4 o = make_float4(s[0], s[1], s[2], s[3]);
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), ch = (lane & 3) * 16;
+    const uint4 q = lds128(sa + r * EPI_ROW_PITCH + ch);
     if (r < rows) {
-      if (atomic) atomicAdd(reinterpret_cast<float4*>(dst + r * ld + c), o);
-      else *reinterpret_cast<float4*>(dst + r * ld + c) = o;
+      uint8_t* dst = g + r * ld_bytes + ch;
+      if (atomic_f32)
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
+                                                               __uint_as_float(q.w)));
+      else
+        *reinterpret_cast<uint4*>(dst) = q;
     }
   }
   __syncwarp();
 }
-// staging <- tile [rows x 32] fp32 / bf16 (rows past `rows` are filled with 0)
-__device__ __forceinline__ void st_load_f32(float* st, int lane, const float* src, int64_t ld, int rows) {
-  const int c = (lane & 7) * 4;
+__device__ __forceinline__ void tile_load(uint32_t sa, int lane, const uint8_t* g, int64_t ld_bytes, int rows) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) v = *reinterpret_cast<const float4*>(src + r * ld + c);
-    float* s = st + r * 33 + c;
-    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), ch = (lane & 3) * 16;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) q = *reinterpret_cast<const uint4*>(g + r * ld_bytes + ch);
+    sts128(sa + r * EPI_ROW_PITCH + ch, q.x, q.y, q.z, q.w);
   }
   __syncwarp();
 }
-__device__ __forceinline__ void st_load_bf16(float* st, int lane, const __nv_bfloat16* src, int64_t ld, int rows) {
-  const int c = (lane & 3) * 8;
+__device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&w)[16]) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2);
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) q = __ldg(reinterpret_cast<const uint4*>(src + r * ld + c));
-    float* s = st + r * 33 + c;
-    s[0] = bf16_lo(q.x); s[1] = bf16_hi(q.x); s[2] = bf16_lo(q.y); s[3] = bf16_hi(q.y);
-    s[4] = bf16_lo(q.z); s[5] = bf16_hi(q.z); s[6] = bf16_lo(q.w); s[7] = bf16_hi(q.w);
-  }
-  __syncwarp();
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 
 // Fused epilogue of a full 32-column chunk for the 32 rows [mw, mw+32) owned by this warp (thread == row mw+lane);
 // `rows` = number of those rows inside the matrix.  Same arithmetic, in the same order, as epilogue_chunk.
-__device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, float* st, int lane, int mw, int rows, int n0,
+__device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uint32_t sa, int lane, int mw, int rows, int n0,
                                                          uint32_t (&acc)[32]) {
   float v[32];
+  uint32_t w[16];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   const int m = mw + lane;
@@ -294,18 +291,22 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, flo
     }
   }
   if (p.preact_out) {
-    st_put(st, lane, v);
-    st_store_bf16(st, lane, p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0, p.ld_preact, rows);
+    pack32(v, w);
+    tile_put(sa, lane, w);
+    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
+               rows, false);
   }
   if (p.act == X2K_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   } else if (p.act == X2K_ACT_GELU_BWD) {
-    float a[32];
-    st_load_bf16(st, lane, p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0, p.ld_aux, rows);
-    st_get(st, lane, a);
+    tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
+    tile_get(sa, lane, w);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] *= gelu_erf_grad(bf16_lo(w[j]));
+      v[2 * j + 1] *= gelu_erf_grad(bf16_hi(w[j]));
+    }
   }
   if (p.dropout_p > 0.0f) {
     const DropCfg dc = make_drop(p.dropout_p);
@@ -331,27 +332,37 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, flo
     for (int j = 0; j < 32; ++j) v[j] *= sc;
   }
   if (p.residual) {
-    float a[32];
-    st_load_f32(st, lane, p.residual + static_cast<int64_t>(mw) * p.ld_res + n0, p.ld_res, rows);
-    st_get(st, lane, a);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += a[j];
+    for (int hf = 0; hf < 2; ++hf) {
+      tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.residual + static_cast<int64_t>(mw) * p.ld_res + n0 + 16 * hf),
+                p.ld_res * 4, rows);
+      tile_get(sa, lane, w);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[16 * hf + j] += __uint_as_float(w[j]);
+    }
   }
   if (p.out_f32) {
-    float* dst = p.out_f32 + static_cast<int64_t>(mw) * p.ld_out_f32 + n0;
-    if (p.accumulate && p.split_k <= 1) {
-      float a[32];
-      st_load_f32(st, lane, dst, p.ld_out_f32, rows);
-      st_get(st, lane, a);
+    const bool atomic = p.split_k > 1;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
+    for (int hf = 0; hf < 2; ++hf) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p.out_f32 + static_cast<int64_t>(mw) * p.ld_out_f32 + n0 + 16 * hf);
+      if (p.accumulate && !atomic) {
+        tile_load(sa, lane, dst, p.ld_out_f32 * 4, rows);
+        tile_get(sa, lane, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * hf + j] += __uint_as_float(w[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[16 * hf + j]);
+      tile_put(sa, lane, w);
+      tile_store(sa, lane, dst, p.ld_out_f32 * 4, rows, atomic);
     }
-    st_put(st, lane, v);
-    st_store_f32(st, lane, dst, p.ld_out_f32, rows, p.split_k > 1);
   }
   if (p.out_bf16) {
-    st_put(st, lane, v);
-    st_store_bf16(st, lane, p.out_bf16 + static_cast<int64_t>(mw) * p.ld_out_bf16 + n0, p.ld_out_bf16, rows);
+    pack32(v, w);
+    tile_put(sa, lane, w);
+    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.out_bf16 + static_cast<int64_t>(mw) * p.ld_out_bf16 + n0), p.ld_out_bf16 * 2,
+               rows, false);
   }
 }
 
@@ -364,7 +375,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  const uint32_t epi_stage = smem_u32(smem + STAGES * C::STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -441,42 +452,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc_stage = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc_stage * BLOCK_N;
-      const int ks = tile % split_k;
-      const int kb_begin = ks * kb_per, kb_end = min(k_blocks_total, (ks + 1) * kb_per);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (one thread; the other 31 lanes wait at the final barrier) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc_stage * BLOCK_N;
+        const int ks = tile % split_k;
+        const int kb_begin = ks * kb_per, kb_end = min(k_blocks_total, (ks + 1) * kb_per);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t mn_lbo = p.dbg_lbo ? p.dbg_lbo : BLOCK_K * 128;
-            const uint32_t mn_sbo = p.dbg_sbo ? p.dbg_sbo : 1024;
-            const uint32_t mn_kadv = p.dbg_kadv ? p.dbg_kadv : UMMA_K * 128;
             const uint64_t da = A_MN == 0 ? make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024)
-                                          : make_smem_desc(sa + k * mn_kadv, mn_lbo, mn_sbo);
+                                          : make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
             const uint64_t db = B_MN == 0 ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
-                                          : make_smem_desc(sb + k * mn_kadv, mn_lbo, mn_sbo);
+                                          : make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (kb == kb_end - 1) umma_commit(&tmem_full_bar[acc_stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
-      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue =====================
@@ -490,7 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int t = tile / split_k;
       const int m0 = (t / n_tiles) * BLOCK_M;
       const int n0 = (t % n_tiles) * BLOCK_N;
-      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const int m = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
@@ -502,7 +509,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n = n0 + half * COLS_PER_WARP + c;
         const int mw = m0 + quad * 32;  // first row of this warp
         if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N) epilogue_chunk_coalesced(p, epi_stage + ew * (32 * 33), lane, mw, min(32, p.M - mw), n, acc);
+          if (n + 32 <= p.N) epilogue_chunk_coalesced(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc);
           else if (m < p.M) epilogue_chunk(p, m, n, acc);  // ragged last chunk: thread-per-row path
         }
       }

@@ -145,81 +145,123 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 }
 
 // ---------------------------------------------------------------------------------------------
-// scale / cast / column sums: thread owns 4 columns, loops over a chunk of rows.
+// Column reductions.  Block = 8 warps; a warp covers a contiguous run of columns (lane = 4 fp32 or 8 bf16 columns,
+// 512 contiguous bytes per row) and the 8 warps interleave over the block's rows with 4 independent row loads in
+// flight per thread; partial sums are combined across the warps in shared memory, so each block issues ONE atomic per
+// column (same-address atomics were the bottleneck of the thread-per-column-group version).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) scale_cast_colsum_kernel(
+__global__ void __launch_bounds__(256) scale_cast_colsum_kernel(
     const float* __restrict__ dx, int64_t ld_dx, int M, int N, const float* __restrict__ gamma,
     const float* __restrict__ row_scale, int rows_per_scale, float dropout_p, uint64_t seed, uint64_t offset,
     const __nv_bfloat16* __restrict__ y, int64_t ld_y, __nv_bfloat16* __restrict__ g, int64_t ld_g,
     float* __restrict__ dbias, float* __restrict__ dgamma, int rows_per_block) {
-  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;  // column group
-  const int n = c4 * 4;
-  if (n >= N) return;
+  __shared__ float4 red[2][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + lane) * 4;
+  const bool col_ok = n < N;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (gamma) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
+  if (gamma && col_ok) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
   const DropCfg dc = make_drop(dropout_p);
   float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int m = r0; m < r1; ++m) {
-    float4 d = __ldg(reinterpret_cast<const float4*>(dx + static_cast<int64_t>(m) * ld_dx + n));
-    if (row_scale) {
-      const float s = __ldg(row_scale + m / rows_per_scale);
-      d.x *= s; d.y *= s; d.z *= s; d.w *= s;
-    }
-    if (dgamma) {
-      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(y + static_cast<int64_t>(m) * ld_y + n));
-      sg.x += d.x * bf16_lo(pk.x); sg.y += d.y * bf16_hi(pk.x); sg.z += d.z * bf16_lo(pk.y); sg.w += d.w * bf16_hi(pk.y);
-    }
-    d.x *= gm.x; d.y *= gm.y; d.z *= gm.z; d.w *= gm.w;
-    if (dropout_p > 0.f) {
-      const uint64_t idx = static_cast<uint64_t>(m) * static_cast<uint64_t>(N) + static_cast<uint64_t>(n);
-      float k[8];
-      drop8(seed, offset, idx >> 3, dc, k);
-      const int o = static_cast<int>(idx & 4);  // this thread's 4 columns are the low or the high half of the group
-      d.x *= k[o]; d.y *= k[o + 1]; d.z *= k[o + 2]; d.w *= k[o + 3];
-    }
-    sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
-    if (g) {
-      uint2 pk;
-      pk.x = pack_bf16x2(d.x, d.y);
-      pk.y = pack_bf16x2(d.z, d.w);
-      *reinterpret_cast<uint2*>(g + static_cast<int64_t>(m) * ld_g + n) = pk;
+  if (col_ok) {
+    for (int m0 = r0 + w; m0 < r1; m0 += 32) {  // rows m0, m0+8, m0+16, m0+24: four loads in flight
+      float4 d[4];
+      uint2 yk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = m0 + 8 * u;
+        if (m < r1) {
+          d[u] = __ldg(reinterpret_cast<const float4*>(dx + static_cast<int64_t>(m) * ld_dx + n));
+          if (dgamma) yk[u] = __ldg(reinterpret_cast<const uint2*>(y + static_cast<int64_t>(m) * ld_y + n));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = m0 + 8 * u;
+        if (m >= r1) continue;
+        float4 v = d[u];
+        if (row_scale) {
+          const float sc = __ldg(row_scale + m / rows_per_scale);
+          v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        }
+        if (dgamma) {
+          sg.x += v.x * bf16_lo(yk[u].x); sg.y += v.y * bf16_hi(yk[u].x);
+          sg.z += v.z * bf16_lo(yk[u].y); sg.w += v.w * bf16_hi(yk[u].y);
+        }
+        v.x *= gm.x; v.y *= gm.y; v.z *= gm.z; v.w *= gm.w;
+        if (dropout_p > 0.f) {
+          const uint64_t idx = static_cast<uint64_t>(m) * static_cast<uint64_t>(N) + static_cast<uint64_t>(n);
+          float k[8];
+          drop8(seed, offset, idx >> 3, dc, k);
+          const int o = static_cast<int>(idx & 4);  // this thread's 4 columns are the low or the high half of the group
+          v.x *= k[o]; v.y *= k[o + 1]; v.z *= k[o + 2]; v.w *= k[o + 3];
+        }
+        sb.x += v.x; sb.y += v.y; sb.z += v.z; sb.w += v.w;
+        if (g) {
+          uint2 pk;
+          pk.x = pack_bf16x2(v.x, v.y);
+          pk.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(g + static_cast<int64_t>(m) * ld_g + n) = pk;
+        }
+      }
     }
   }
-  if (dbias) {
-    atomicAdd(dbias + n, sb.x); atomicAdd(dbias + n + 1, sb.y); atomicAdd(dbias + n + 2, sb.z); atomicAdd(dbias + n + 3, sb.w);
-  }
-  if (dgamma) {
-    atomicAdd(dgamma + n, sg.x); atomicAdd(dgamma + n + 1, sg.y); atomicAdd(dgamma + n + 2, sg.z); atomicAdd(dgamma + n + 3, sg.w);
+  red[0][w][lane] = sb;
+  red[1][w][lane] = sg;
+  __syncthreads();
+  if (w < 2 && col_ok) {  // warp 0 finishes dbias, warp 1 dgamma
+    float* out = w == 0 ? dbias : dgamma;
+    if (out) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = red[w][i][lane];
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+      }
+      atomicAdd(out + n, t.x); atomicAdd(out + n + 1, t.y); atomicAdd(out + n + 2, t.z); atomicAdd(out + n + 3, t.w);
+    }
   }
 }
 
-// thread owns 8 bf16 columns (16 B); four independent row loads are issued per iteration (memory-level parallelism)
 __device__ __forceinline__ void acc8(float (&s)[8], const uint4& q) {
   s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
   s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
 }
-__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
                                                           float* __restrict__ dcol, int rows_per_block) {
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (n >= N) return;
+  __shared__ float red[8][32][9];  // +1 padding: conflict-free column reads
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + lane) * 8;
+  const bool col_ok = n < N;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const __nv_bfloat16* px = x + static_cast<int64_t>(r0) * ld + n;
-  int m = r0;
-  for (; m + 4 <= r1; m += 4, px += 4 * ld) {
-    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(px));
-    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(px + ld));
-    const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(px + 2 * ld));
-    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(px + 3 * ld));
-    acc8(s, q0); acc8(s, q1); acc8(s, q2); acc8(s, q3);
-  }
-  for (; m < r1; ++m, px += ld) acc8(s, __ldg(reinterpret_cast<const uint4*>(px)));
+  if (col_ok) {
+    const __nv_bfloat16* px = x + n;
+    for (int m0 = r0 + w; m0 < r1; m0 += 32) {
+      uint4 q[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(dcol + n + j, s[j]);
+      for (int u = 0; u < 4; ++u)
+        if (m0 + 8 * u < r1) q[u] = __ldg(reinterpret_cast<const uint4*>(px + static_cast<int64_t>(m0 + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m0 + 8 * u < r1) acc8(s, q[u]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[w][lane][j] = s[j];
+  __syncthreads();
+  // 256 threads finish the 32 x 8 columns of the block: thread t -> column (t >> 3, t & 7)
+  const int cl = threadIdx.x >> 3, cj = threadIdx.x & 7;
+  const int nn = (blockIdx.x * 32 + cl) * 8 + cj;
+  if (nn < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cl][cj];
+    atomicAdd(dcol + nn, t);
+  }
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
@@ -409,12 +451,12 @@ extern "C" int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, 
   X2K_REQUIRE(!g_bf16 || ld_g % 4 == 0, "x2k_scale_cast_colsum: ld_g must be a multiple of 4");
   X2K_REQUIRE(!row_scale || rows_per_scale > 0, "x2k_scale_cast_colsum: rows_per_scale");
   X2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "x2k_scale_cast_colsum: dropout_p");
-  const int col_blocks = (N / 4 + 127) / 128;
-  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  const int col_blocks = (N / 4 + 31) / 32;  // 128 columns per block
+  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
   int rows_per_block = (M + row_blocks - 1) / row_blocks;
-  if (rows_per_block < 8) rows_per_block = 8;
+  if (rows_per_block < 64) rows_per_block = 64;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
-  scale_cast_colsum_kernel<<<dim3(col_blocks, row_blocks), 128, 0, stream>>>(
+  scale_cast_colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(
       dx, ld_dx, M, N, gamma, row_scale, rows_per_scale, dropout_p, dropout_seed, dropout_offset,
       static_cast<const __nv_bfloat16*>(y_bf16), ld_y, static_cast<__nv_bfloat16*>(g_bf16), ld_g, dbias, dgamma,
       rows_per_block);
@@ -426,12 +468,12 @@ extern "C" int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, 
 extern "C" int x2k_colsum_bf16(const void* x_bf16, int64_t ld, int32_t M, int32_t N, float* dcol, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   X2K_REQUIRE(x_bf16 && dcol && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "x2k_colsum_bf16: bad arguments");
-  const int col_blocks = (N / 8 + 127) / 128;
-  int row_blocks = (sm_count() * 8 + col_blocks - 1) / col_blocks;
+  const int col_blocks = (N / 8 + 31) / 32;  // 256 columns per block
+  int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
   int rows_per_block = (M + row_blocks - 1) / row_blocks;
-  if (rows_per_block < 8) rows_per_block = 8;
+  if (rows_per_block < 64) rows_per_block = 64;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
-  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), ld, M,
+  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), ld, M,
                                                                        N, dcol, rows_per_block);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -56,6 +56,7 @@ struct EpiParams {
   int64_t ld_res;
   int accumulate;
   int split_k;  // >1: work unit = (tile, k-slice), fp32 output accumulated with atomics
+  int raster_m;  // 1: consecutive tiles walk down M (CTAs running together share the B tile), 0: walk along N (share A)
   __nv_bfloat16* out_bf16;
   int64_t ld_out_bf16;
   float* out_f32;
@@ -274,8 +275,22 @@ __device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&w)[16]) 
   for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 }
 
+// Compile-time epilogue feature mask.  The kernel is instantiated for the handful of combinations the hot path
+// uses (the epilogue warps are latency-bound: every branch and address computation of an unused feature costs issue
+// slots on the critical path of a K = 768 tile) plus a generic variant that tests the runtime pointers.
+enum : int {
+  EF_BIAS = 1, EF_PREACT = 2, EF_GELU = 4, EF_GELU_BWD = 8, EF_DROPOUT = 16, EF_SCALE = 32 /*gamma and/or row_scale*/,
+  EF_RESIDUAL = 64, EF_OUT_F32 = 128, EF_OUT_BF16 = 256, EF_GENERIC = 1 << 20
+};
+template <int EPI, int F>
+__device__ __forceinline__ bool has(bool runtime) {
+  if constexpr (EPI == EF_GENERIC) return runtime;
+  else return (EPI & F) != 0;
+}
+
 // Fused epilogue of a full 32-column chunk for the 32 rows [mw, mw+32) owned by this warp (thread == row mw+lane);
 // `rows` = number of those rows inside the matrix.  Same arithmetic, in the same order, as epilogue_chunk.
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uint32_t sa, int lane, int mw, int rows, int n0,
                                                          uint32_t (&acc)[32]) {
   float v[32];
@@ -283,23 +298,23 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   const int m = mw + lane;
-  if (p.bias) {
+  if (has<EPI, EF_BIAS>(p.bias != nullptr)) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (p.preact_out) {
+  if (has<EPI, EF_PREACT>(p.preact_out != nullptr)) {
     pack32(v, w);
     tile_put(sa, lane, w);
     tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
                rows, false);
   }
-  if (p.act == X2K_ACT_GELU) {
+  if (has<EPI, EF_GELU>(p.act == X2K_ACT_GELU)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == X2K_ACT_GELU_BWD) {
+  } else if (has<EPI, EF_GELU_BWD>(p.act == X2K_ACT_GELU_BWD)) {
     tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
     tile_get(sa, lane, w);
 #pragma unroll
@@ -308,7 +323,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
       v[2 * j + 1] *= gelu_erf_grad(bf16_hi(w[j]));
     }
   }
-  if (p.dropout_p > 0.0f) {
+  if (has<EPI, EF_DROPOUT>(true) && p.dropout_p > 0.0f) {
     const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
 #pragma unroll
@@ -319,19 +334,19 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
       for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
     }
   }
-  if (p.gamma) {
+  if (has<EPI, EF_SCALE>(true) && p.gamma) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
       v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
     }
   }
-  if (p.row_scale) {
+  if (has<EPI, EF_SCALE>(true) && p.row_scale) {
     const float sc = __ldg(p.row_scale + min(m, p.M - 1) / p.rows_per_scale);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= sc;
   }
-  if (p.residual) {
+  if (has<EPI, EF_RESIDUAL>(p.residual != nullptr)) {
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.residual + static_cast<int64_t>(mw) * p.ld_res + n0 + 16 * hf),
@@ -341,7 +356,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
       for (int j = 0; j < 16; ++j) v[16 * hf + j] += __uint_as_float(w[j]);
     }
   }
-  if (p.out_f32) {
+  if (has<EPI, EF_OUT_F32>(p.out_f32 != nullptr)) {
     const bool atomic = p.split_k > 1;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -358,7 +373,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
       tile_store(sa, lane, dst, p.ld_out_f32 * 4, rows, atomic);
     }
   }
-  if (p.out_bf16) {
+  if (has<EPI, EF_OUT_BF16>(p.out_bf16 != nullptr)) {
     pack32(v, w);
     tile_put(sa, lane, w);
     tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.out_bf16 + static_cast<int64_t>(mw) * p.ld_out_bf16 + n0), p.ld_out_bf16 * 2,
@@ -366,7 +381,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
   }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const EpiParams p) {
@@ -424,8 +439,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int t = tile / split_k, ks = tile % split_k;
-        const int m0 = (t / n_tiles) * BLOCK_M;
-        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int m0 = (p.raster_m ? t % m_tiles : t / n_tiles) * BLOCK_M;
+        const int n0 = (p.raster_m ? t / m_tiles : t % n_tiles) * BLOCK_N;
         const int kb_end = min(k_blocks_total, (ks + 1) * kb_per);
         for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -495,22 +510,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int t = tile / split_k;
-      const int m0 = (t / n_tiles) * BLOCK_M;
-      const int n0 = (t % n_tiles) * BLOCK_N;
+      const int m0 = (p.raster_m ? t % m_tiles : t / n_tiles) * BLOCK_M;
+      const int n0 = (p.raster_m ? t / m_tiles : t % n_tiles) * BLOCK_N;
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const int m = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c, acc);
+      // software-pipelined over the warp's 32-column chunks: the TMEM load of chunk c+1 is in flight while chunk c
+      // goes through the epilogue
+      constexpr int NCH = COLS_PER_WARP / 32;
+      uint32_t acc[2][32];
+      tmem_ld_32x32(taddr, acc[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
         tmem_wait_ld();
-        const int n = n0 + half * COLS_PER_WARP + c;
+        if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
+        const int n = n0 + half * COLS_PER_WARP + ci * 32;
         const int mw = m0 + quad * 32;  // first row of this warp
         if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N) epilogue_chunk_coalesced(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc);
-          else if (m < p.M) epilogue_chunk(p, m, n, acc);  // ragged last chunk: thread-per-row path
+          if (n + 32 <= p.N) epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
+          else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);  // ragged last chunk: thread-per-row path
         }
       }
       tc_fence_before();
@@ -528,7 +547,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, int EPI>
 int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -544,7 +563,7 @@ int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
     rc = make_tmap_bf16_2d(&tb, a.B, a.K, a.N, a.ldb, BLOCK_K, 64);
   if (rc) return rc;
 
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static bool attr_set = false;  // idempotent; racing writers set the same value
   if (!attr_set) {
     X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -562,12 +581,48 @@ int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
   return X2K_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 int dispatch_major(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
-  if (!a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 0, 0>(a, ep, stream);
-  if (!a.a_mn_major && a.b_mn_major) return launch<BLOCK_N, 0, 1>(a, ep, stream);
-  if (a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 1, 0>(a, ep, stream);
-  return launch<BLOCK_N, 1, 1>(a, ep, stream);
+  if (!a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 0, 0, EPI>(a, ep, stream);
+  if (!a.a_mn_major && a.b_mn_major) return launch<BLOCK_N, 0, 1, EPI>(a, ep, stream);
+  if (a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 1, 0, EPI>(a, ep, stream);
+  return launch<BLOCK_N, 1, 1, EPI>(a, ep, stream);
+}
+
+// feature mask of a call (what the runtime pointers ask for)
+int epi_mask(const X2kGemmArgs& a) {
+  int m = 0;
+  if (a.bias) m |= EF_BIAS;
+  if (a.preact_out) m |= EF_PREACT;
+  if (a.act == X2K_ACT_GELU) m |= EF_GELU;
+  if (a.act == X2K_ACT_GELU_BWD) m |= EF_GELU_BWD;
+  if (a.dropout_p > 0.f) m |= EF_DROPOUT;
+  if (a.gamma || a.row_scale) m |= EF_SCALE;
+  if (a.residual) m |= EF_RESIDUAL;
+  if (a.out_f32) m |= EF_OUT_F32;
+  if (a.out_bf16) m |= EF_OUT_BF16;
+  return m;
+}
+
+template <int BLOCK_N>
+int dispatch_epi(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  const int m = epi_mask(a);
+  // the specialised variants may contain MORE features than requested only where the extra feature is itself guarded
+  // by a runtime test (dropout_p, gamma/row_scale pointers), never fewer
+#define X2K_EPI_CASE(MASK) \
+  if (m == (MASK)) return dispatch_major<BLOCK_N, (MASK)>(a, ep, stream);
+  X2K_EPI_CASE(EF_OUT_BF16)                                              // plain dgrad
+  X2K_EPI_CASE(EF_BIAS | EF_OUT_BF16)                                    // qkv / q / kv projections
+  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_GELU | EF_OUT_BF16)              // fc1 / intermediate
+  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_SCALE | EF_RESIDUAL | EF_OUT_F32)  // BEiT proj / fc2 (LayerScale, DropPath)
+  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_RESIDUAL | EF_OUT_F32)           // same without LayerScale / DropPath
+  X2K_EPI_CASE(EF_BIAS | EF_DROPOUT | EF_RESIDUAL | EF_OUT_F32)          // BERT dense + dropout + residual (train)
+  X2K_EPI_CASE(EF_BIAS | EF_RESIDUAL | EF_OUT_F32)                       // BERT dense + residual (eval)
+  X2K_EPI_CASE(EF_GELU_BWD | EF_OUT_BF16)                                // dgrad through GELU
+  X2K_EPI_CASE(EF_OUT_F32)                                               // wgrad (accumulate / split-K atomics)
+  X2K_EPI_CASE(EF_RESIDUAL | EF_OUT_F32)                                 // dgrad + residual-stream gradient
+#undef X2K_EPI_CASE
+  return dispatch_major<BLOCK_N, EF_GENERIC>(a, ep, stream);
 }
 
 }  // namespace
@@ -609,7 +664,8 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); ep.ld_out_bf16 = a.ld_out_bf16;
   ep.out_f32 = a.out_f32; ep.ld_out_f32 = a.ld_out_f32;
   ep.dbg_lbo = ep.dbg_sbo = ep.dbg_kadv = 0;
-  if (const char* dbg = getenv("X2K_DBG_MN")) sscanf(dbg, "%u,%u,%u", &ep.dbg_lbo, &ep.dbg_sbo, &ep.dbg_kadv);
+  ep.raster_m = 0;
+  if (const char* r = getenv("X2K_GEMM_RASTER")) ep.raster_m = atoi(r);
 
   // split-K: a wgrad-shaped GEMM (small output, very long K) has fewer tiles than SMs; slice K across CTAs and
   // accumulate the fp32 output with vector atomics.  Only for the pure (accumulating) fp32 epilogue.
@@ -648,5 +704,5 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
     tile_n = (a.N <= 128 || cost128 < cost256) ? 128 : 256;
   }
   X2K_REQUIRE(tile_n == 128 || tile_n == 256, "x2k_gemm: tile_n must be 0, 128 or 256");
-  return tile_n == 256 ? dispatch_major<256>(a, ep, stream) : dispatch_major<128>(a, ep, stream);
+  return tile_n == 256 ? dispatch_epi<256>(a, ep, stream) : dispatch_epi<128>(a, ep, stream);
 }

@@ -56,6 +56,7 @@ struct EpiParams {
   int64_t ld_res;
   int accumulate;
   int split_k;  // >1: work unit = (tile, k-slice), fp32 output accumulated with atomics
+  int use_pair;  // host-side: launch the CTA-pair (cta_group::2) kernel
   int raster_m;  // 1: consecutive tiles walk down M (CTAs running together share the B tile), 0: walk along N (share A)
   __nv_bfloat16* out_bf16;
   int64_t ld_out_bf16;
@@ -547,6 +548,226 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  A cluster of two CTAs on one TPC computes a 256 x 256 tile: CTA r holds rows
+// [128r, 128r+128) of A and of the accumulator, and HALF of the B tile (128 of the 256 output columns); one
+// tcgen05.mma.cta_group::2 issued by CTA 0 drives both tensor cores, each reading the B halves of both CTAs.  Per SM
+// and per k-block that is 32 KB of TMA writes and 8 KB of operand reads per MMA instead of 48 KB / 12 KB — the 1-CTA
+// kernel is bound by shared-memory bandwidth (TMA fill + operand fetch > 128 B/clk), this one is not.
+// Barriers: full[] lives in CTA 0 and collects the TMA bytes of both CTAs; empty[] / tmem_full[] are per CTA and are
+// signalled by multicast tcgen05.commit; tmem_empty[] lives in CTA 0 and is arrived on by the epilogue warps of both.
+// ---------------------------------------------------------------------------------------------
+template <int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const EpiParams p) {
+  constexpr int BLOCK_N = 256;
+  constexpr int HALF_N = 128;
+  constexpr int STAGE_BYTES = A_TILE_BYTES + HALF_N * BLOCK_K * 2;  // 32 KB
+  constexpr int STAGES = 6;
+  constexpr int TMEM_COLS = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t epi_stage = smem_u32(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());  // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int split_k = p.split_k > 1 ? p.split_k : 1;
+  const int kb_per = (k_blocks_total + split_k - 1) / split_k;
+  const int num_tiles = m_tiles * n_tiles * split_k;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 2);   // CTA 0: own arrive.expect_tx + the peer's arrive
+        mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA thread
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 2 * NUM_EPI_WARPS);  // CTA 0: epilogue warps of both CTAs
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int t = tile / split_k, ks = tile % split_k;
+        const int m0 = (t / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
+        const int n0 = (t % n_tiles) * BLOCK_N + rank * HALF_N;
+        const int kb_end = min(k_blocks_total, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (A_MN == 0) {
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d_pair(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < HALF_N / 64; ++c)
+              tma_load_2d_pair(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          else mbar_arrive_cta0(&full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_stage * BLOCK_N;
+        const int ks = tile % split_k;
+        const int kb_begin = ks * kb_per, kb_end = min(k_blocks_total, (ks + 1) * kb_per);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN == 0 ? make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                          : make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
+            const uint64_t db = B_MN == 0 ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
+                                          : make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
+            umma_bf16_pair(d_tmem, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);  // frees this smem slot in both CTAs
+          if (kb == kb_end - 1) umma_commit_pair(&tmem_full_bar[acc_stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, each on its own 128 rows) =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int t = tile / split_k;
+      const int m0 = (t / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
+      tc_fence_after();
+      const int m = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+      constexpr int NCH = COLS_PER_WARP / 32;
+      uint32_t acc[2][32];
+      tmem_ld_32x32(taddr, acc[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        tmem_wait_ld();
+        if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
+        const int n = n0 + half * COLS_PER_WARP + ci * 32;
+        const int mw = m0 + quad * 32;
+        if (mw < p.M && n < p.N) {
+          if (n + 32 <= p.N) epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
+          else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta0(&tmem_empty_bar[acc_stage]);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its partner can still signal or read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+constexpr int PAIR_SMEM_BYTES = 6 * (A_TILE_BYTES + 128 * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 + 256;
+
+template <int A_MN, int B_MN, int EPI>
+int launch_pair(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (A_MN == 0) rc = make_tmap_bf16_2d(&ta, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K);
+  else rc = make_tmap_bf16_2d(&ta, a.A, a.K, a.M, a.lda, BLOCK_K, 64);
+  if (rc) return rc;
+  if (B_MN == 0) rc = make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, 128, BLOCK_K);
+  else rc = make_tmap_bf16_2d(&tb, a.B, a.K, a.N, a.ldb, BLOCK_K, 64);
+  if (rc) return rc;
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (a.N + 255) / 256;
+  const int units = m_tiles * n_tiles * (ep.split_k > 1 ? ep.split_k : 1);
+  int pairs = sm_count() / 2;
+  if (a.max_ctas > 0 && a.max_ctas / 2 < pairs) pairs = a.max_ctas / 2 > 0 ? a.max_ctas / 2 : 1;
+  if (units < pairs) pairs = units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  X2K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep));
+  count_launch();
+  return X2K_OK;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN, int EPI>
 int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
@@ -583,6 +804,12 @@ int launch(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
 
 template <int BLOCK_N, int EPI>
 int dispatch_major(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  if (BLOCK_N == 256 && ep.use_pair) {
+    if (!a.a_mn_major && !a.b_mn_major) return launch_pair<0, 0, EPI>(a, ep, stream);
+    if (!a.a_mn_major && a.b_mn_major) return launch_pair<0, 1, EPI>(a, ep, stream);
+    if (a.a_mn_major && !a.b_mn_major) return launch_pair<1, 0, EPI>(a, ep, stream);
+    return launch_pair<1, 1, EPI>(a, ep, stream);
+  }
   if (!a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 0, 0, EPI>(a, ep, stream);
   if (!a.a_mn_major && a.b_mn_major) return launch<BLOCK_N, 0, 1, EPI>(a, ep, stream);
   if (a.a_mn_major && !a.b_mn_major) return launch<BLOCK_N, 1, 0, EPI>(a, ep, stream);
@@ -704,5 +931,13 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
     tile_n = (a.N <= 128 || cost128 < cost256) ? 128 : 256;
   }
   X2K_REQUIRE(tile_n == 128 || tile_n == 256, "x2k_gemm: tile_n must be 0, 128 or 256");
+  // CTA-pair kernel: 256x256 tiles, for problems with enough rows/columns to fill them
+  ep.use_pair = 0;
+  {
+    int mode = 2;  // 0 = never, 1 = always when the tile is 256 wide, 2 = auto
+    if (const char* e = getenv("X2K_GEMM_PAIR")) mode = atoi(e);
+    if (a.tile_n == 0 && mode == 2 && a.M >= 1024 && a.N >= 256 && ep.split_k <= 1) { ep.use_pair = 1; tile_n = 256; }
+    if (mode == 1 && (a.tile_n == 0 || a.tile_n == 256) && a.N >= 256) { ep.use_pair = 1; tile_n = 256; }
+  }
   return tile_n == 256 ? dispatch_epi<256>(a, ep, stream) : dispatch_epi<128>(a, ep, stream);
 }

@@ -46,13 +46,35 @@ def _digest(path):
     return h.hexdigest()
 
 
-def _compile_one(nvcc, src, verbose):
-    obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+def _parts(src):
+    """Number of -DX2K_<NAME>_PART=i compilations a source asks for (marker: `// X2K_BUILD_PARTS: n`), else 0."""
+    with open(src) as fh:
+        for line in fh:
+            if "X2K_BUILD_PARTS:" in line:
+                return int(line.split("X2K_BUILD_PARTS:")[1].split()[0])
+    return 0
+
+
+def _jobs():
+    jobs = []
+    for src in _sources():
+        n = _parts(src)
+        base = os.path.basename(src)[:-3]
+        if n:
+            jobs += [(src, "%s_p%d" % (base, i), ["-DX2K_%s_PART=%d" % (base.upper(), i)]) for i in range(n)]
+        else:
+            jobs.append((src, base, []))
+    return jobs
+
+
+def _compile_one(nvcc, job, verbose):
+    src, name, defs = job
+    obj = os.path.join(OBJDIR, name + ".o")
     stamp = obj + ".sha1"
     dig = _digest(src)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, ""
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
@@ -69,9 +91,9 @@ def build_lib(verbose=False, force=False):
     if force:
         for f in os.listdir(OBJDIR):
             os.remove(os.path.join(OBJDIR, f))
-    srcs = _sources()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
+    jobs = _jobs()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(jobs))) as ex:
+        results = list(ex.map(lambda j: _compile_one(nvcc, j, verbose), jobs))
     objs = [r[0] for r in results]
     if verbose:
         for _, log in results:

@@ -15,29 +15,14 @@
 // read the tensors where they lie, no transposes are materialised.
 //
 // Replaces the F.linear(+bias+act+residual) sequences cited in include/x2k.h.
+//
+// X2K_BUILD_PARTS: 4   (compiled 4x with -DX2K_GEMM_PART=0..3; each part instantiates a quarter of the epilogue
+//                       variants so the ~130 kernel instantiations build in parallel)
 #include <cstdlib>
 
 #include "common.cuh"
 
 namespace x2k {
-namespace {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-
-template <int BLOCK_N>
-struct Cfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 80;  // per-warp transpose tile (EPI_TILE_BYTES)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
 
 struct EpiParams {
   int M, N, K;
@@ -65,6 +50,26 @@ struct EpiParams {
   // debug overrides for the MN-major smem descriptors (0 = defaults); env X2K_DBG_MN="lbo,sbo,kadv"
   uint32_t dbg_lbo, dbg_sbo, dbg_kadv;
 };
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 80;  // per-warp transpose tile (EPI_TILE_BYTES)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
 
 // Apply the fused epilogue to 32 consecutive columns [n0, n0+32) of row m.
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0, uint32_t (&acc)[32]) {
@@ -831,30 +836,69 @@ int epi_mask(const X2kGemmArgs& a) {
   return m;
 }
 
-template <int BLOCK_N>
-int dispatch_epi(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
-  const int m = epi_mask(a);
-  // the specialised variants may contain MORE features than requested only where the extra feature is itself guarded
-  // by a runtime test (dropout_p, gamma/row_scale pointers), never fewer
-#define X2K_EPI_CASE(MASK) \
-  if (m == (MASK)) return dispatch_major<BLOCK_N, (MASK)>(a, ep, stream);
-  X2K_EPI_CASE(EF_OUT_BF16)                                              // plain dgrad
-  X2K_EPI_CASE(EF_BIAS | EF_OUT_BF16)                                    // qkv / q / kv projections
-  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_GELU | EF_OUT_BF16)              // fc1 / intermediate
-  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_SCALE | EF_RESIDUAL | EF_OUT_F32)  // BEiT proj / fc2 (LayerScale, DropPath)
-  X2K_EPI_CASE(EF_BIAS | EF_PREACT | EF_RESIDUAL | EF_OUT_F32)           // same without LayerScale / DropPath
-  X2K_EPI_CASE(EF_BIAS | EF_DROPOUT | EF_RESIDUAL | EF_OUT_F32)          // BERT dense + dropout + residual (train)
-  X2K_EPI_CASE(EF_BIAS | EF_RESIDUAL | EF_OUT_F32)                       // BERT dense + residual (eval)
-  X2K_EPI_CASE(EF_GELU_BWD | EF_OUT_BF16)                                // dgrad through GELU
-  X2K_EPI_CASE(EF_OUT_F32)                                               // wgrad (accumulate / split-K atomics)
-  X2K_EPI_CASE(EF_RESIDUAL | EF_OUT_F32)                                 // dgrad + residual-stream gradient
+// epilogue variants: index -> compile-time feature mask.  A specialised variant may contain MORE features than requested
+// only where the extra feature is itself guarded by a runtime test (dropout_p, gamma/row_scale pointers), never fewer.
+#define X2K_EPI_LIST(X)                                                                   \
+  X(0, EF_OUT_BF16)                                               /* plain dgrad */                        \
+  X(1, EF_BIAS | EF_OUT_BF16)                                     /* qkv / q / kv projections */           \
+  X(2, EF_BIAS | EF_PREACT | EF_GELU | EF_OUT_BF16)               /* fc1 / intermediate */                 \
+  X(3, EF_BIAS | EF_PREACT | EF_SCALE | EF_RESIDUAL | EF_OUT_F32) /* BEiT proj / fc2 (LayerScale, DropPath) */ \
+  X(4, EF_BIAS | EF_PREACT | EF_RESIDUAL | EF_OUT_F32)            /* same without LayerScale / DropPath */ \
+  X(5, EF_BIAS | EF_DROPOUT | EF_RESIDUAL | EF_OUT_F32)           /* BERT dense + dropout + residual */    \
+  X(6, EF_BIAS | EF_RESIDUAL | EF_OUT_F32)                        /* BERT dense + residual (eval) */       \
+  X(7, EF_GELU_BWD | EF_OUT_BF16)                                 /* dgrad through GELU */                 \
+  X(8, EF_OUT_F32)                                                /* wgrad (accumulate / split-K atomics) */ \
+  X(9, EF_RESIDUAL | EF_OUT_F32)                                  /* dgrad + residual-stream gradient */   \
+  X(10, EF_GENERIC)                                               /* anything else: runtime tests */
+
+}  // namespace
+#ifndef X2K_GEMM_PART
+#error "gemm.cu is compiled in parts: pass -DX2K_GEMM_PART=0..3 (x2vlm_b200/build.py does)"
+#endif
+#define X2K_PART_FN_(n) gemm_epi_part##n
+#define X2K_PART_FN(n) X2K_PART_FN_(n)
+int gemm_epi_part0(int, int, const X2kGemmArgs&, const EpiParams&, cudaStream_t);
+int gemm_epi_part1(int, int, const X2kGemmArgs&, const EpiParams&, cudaStream_t);
+int gemm_epi_part2(int, int, const X2kGemmArgs&, const EpiParams&, cudaStream_t);
+int gemm_epi_part3(int, int, const X2kGemmArgs&, const EpiParams&, cudaStream_t);
+
+// this translation unit's share of the variants
+int X2K_PART_FN(X2K_GEMM_PART)(int idx, int tile_n, const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  switch (idx) {
+#define X2K_EPI_CASE(I, MASK)                                                                                  \
+  case I:                                                                                                      \
+    if constexpr ((I) % 4 == X2K_GEMM_PART)                                                                    \
+      return tile_n == 256 ? dispatch_major<256, (MASK)>(a, ep, stream) : dispatch_major<128, (MASK)>(a, ep, stream); \
+    break;
+    X2K_EPI_LIST(X2K_EPI_CASE)
 #undef X2K_EPI_CASE
-  return dispatch_major<BLOCK_N, EF_GENERIC>(a, ep, stream);
+  }
+  set_error("x2k_gemm: epilogue variant %d is not in part %d", idx, X2K_GEMM_PART);
+  return X2K_ERR_UNSUPPORTED;
 }
+namespace {
+
+#if X2K_GEMM_PART == 0
+int dispatch_epi(int tile_n, const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
+  const int m = epi_mask(a);
+  int idx = 10;
+#define X2K_EPI_CASE(I, MASK) \
+  if ((MASK) != EF_GENERIC && m == (MASK)) idx = I;
+  X2K_EPI_LIST(X2K_EPI_CASE)
+#undef X2K_EPI_CASE
+  switch (idx % 4) {
+    case 0: return gemm_epi_part0(idx, tile_n, a, ep, stream);
+    case 1: return gemm_epi_part1(idx, tile_n, a, ep, stream);
+    case 2: return gemm_epi_part2(idx, tile_n, a, ep, stream);
+    default: return gemm_epi_part3(idx, tile_n, a, ep, stream);
+  }
+}
+#endif
 
 }  // namespace
 }  // namespace x2k
 
+#if X2K_GEMM_PART == 0
 extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   using namespace x2k;
   X2K_REQUIRE(args != nullptr, "x2k_gemm: args is NULL");
@@ -894,18 +938,31 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   ep.raster_m = 0;
   if (const char* r = getenv("X2K_GEMM_RASTER")) ep.raster_m = atoi(r);
 
-  // split-K: a wgrad-shaped GEMM (small output, very long K) has fewer tiles than SMs; slice K across CTAs and
-  // accumulate the fp32 output with vector atomics.  Only for the pure (accumulating) fp32 epilogue.
+  // ---- tiling: CTA-pair kernel (256 x 256 cluster tiles) whenever the output has >= 256 rows and columns, else the
+  //      1-CTA kernel with the tile width that minimises (waves x tile cost) ----
+  int tile_n = a.tile_n;
+  ep.use_pair = 0;
+  {
+    int mode = 2;  // 0 = never, 1 = whenever the tile is 256 wide, 2 = auto
+    if (const char* e = getenv("X2K_GEMM_PAIR")) mode = atoi(e);
+    const bool can = (a.tile_n == 0 || a.tile_n == 256) && a.N >= 256;
+    if (can && (mode == 1 || (mode == 2 && a.tile_n == 0 && a.M >= 256))) { ep.use_pair = 1; tile_n = 256; }
+  }
+  // ---- split-K: a wgrad-shaped GEMM (small output, very long K) has fewer work units than SMs; slice K across CTAs
+  //      and accumulate the fp32 output with vector atomics.  Only for the pure (accumulating) fp32 epilogue. ----
   ep.split_k = 1;
   const bool plain_f32 = a.out_f32 && !a.out_bf16 && !a.preact_out && !a.bias && a.act == X2K_ACT_NONE &&
                          !(a.dropout_p > 0.f) && !a.gamma && !a.row_scale && !a.residual;
   if (plain_f32 && a.split_k != 1) {
     const int sms = sm_count();
-    const long tiles = static_cast<long>((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + 127) / 128);  // at tile_n = 128
+    // work units and the number of them that run concurrently with the chosen tiling
+    const long units = ep.use_pair ? static_cast<long>((a.M + 255) / 256) * ((a.N + 255) / 256)
+                                   : static_cast<long>((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + 127) / 128);
+    const long slots = ep.use_pair ? sms / 2 : sms;
     const int kbt = (a.K + BLOCK_K - 1) / BLOCK_K;
     int s = a.split_k > 1 ? a.split_k : 1;
-    if (a.split_k == 0 && tiles < sms && kbt >= 32) {
-      s = static_cast<int>((2L * sms + tiles - 1) / tiles);
+    if (a.split_k == 0 && units < slots && kbt >= 32) {
+      s = static_cast<int>((2L * slots + units - 1) / units);
       if (s > kbt / 8) s = kbt / 8;  // keep >= 8 k-blocks per slice
       if (s < 1) s = 1;
     }
@@ -920,24 +977,17 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
                                          a.M, stream));
     }
   }
-  int tile_n = a.tile_n;
-  if (ep.split_k > 1 && tile_n == 0) tile_n = 128;
-  if (tile_n == 0) {
-    // Pick the tile width that minimises (waves x tile cost) over the SMs.
-    const int sms = sm_count();
-    const long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-    const long t256 = m_tiles * ((a.N + 255) / 256), t128 = m_tiles * ((a.N + 127) / 128);
-    const long cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = ((t128 + sms - 1) / sms) * 1;
-    tile_n = (a.N <= 128 || cost128 < cost256) ? 128 : 256;
+  if (!ep.use_pair) {
+    if (ep.split_k > 1 && tile_n == 0) tile_n = 128;
+    if (tile_n == 0) {
+      const int sms = sm_count();
+      const long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+      const long t256 = m_tiles * ((a.N + 255) / 256), t128 = m_tiles * ((a.N + 127) / 128);
+      const long cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = ((t128 + sms - 1) / sms) * 1;
+      tile_n = (a.N <= 128 || cost128 < cost256) ? 128 : 256;
+    }
   }
   X2K_REQUIRE(tile_n == 128 || tile_n == 256, "x2k_gemm: tile_n must be 0, 128 or 256");
-  // CTA-pair kernel: 256x256 tiles, for problems with enough rows/columns to fill them
-  ep.use_pair = 0;
-  {
-    int mode = 2;  // 0 = never, 1 = always when the tile is 256 wide, 2 = auto
-    if (const char* e = getenv("X2K_GEMM_PAIR")) mode = atoi(e);
-    if (a.tile_n == 0 && mode == 2 && a.M >= 1024 && a.N >= 256 && ep.split_k <= 1) { ep.use_pair = 1; tile_n = 256; }
-    if (mode == 1 && (a.tile_n == 0 || a.tile_n == 256) && a.N >= 256) { ep.use_pair = 1; tile_n = 256; }
-  }
-  return tile_n == 256 ? dispatch_epi<256>(a, ep, stream) : dispatch_epi<128>(a, ep, stream);
+  return dispatch_epi(tile_n, a, ep, stream);
 }
+#endif  // X2K_GEMM_PART == 0

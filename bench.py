@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic FLOPs (fwd+bwd, 2 FLOP / MAC) of the reference algorithm, SURVEY.md §8d
+# average DRAM bytes per GEMM launch of the step (dram__bytes_read.sum + dram__bytes_write.sum over the 422 tcgen05 GEMM
+# launches of profiles/r01_launches_step.md), from the committed ncu capture — not re-measured at bench time
+ROOFLINE_TRAFFIC = 120.93e6
 FLOP_IMAGE_PAIR = 231.4e9            # image iteration, per pair
 FLOP_REGION_SAMPLE = 3 * 48.92e9     # region iteration, per region-text sample (text x2, fusion x5, head)
 FLOP_VISION_IMAGE = 3 * 35.13e9      # + vision once per unique region image
@@ -176,9 +179,9 @@ def run_ours(args):
     burst, sustained, hbm, src = peaks()
     step_tflops = flop_step_gpu * args.steps / (ms / 1e3) / 1e12  # per GPU (ms is the max over ranks)
 
+    roof = dominant_kernel_roofline(lambda: step(ib_d, rb_d, False), sustained, src)  # every rank steps (collectives)
     out = None
     if rank == 0:
-        roof = dominant_kernel_roofline(dev, B + (n_img if rb_h is not None else 0), burst, src)
         sys.stderr.write("[bench] timed: %.2f ms/step resident, %.2f ms/step e2e\n" % (ms / args.steps, ms_e2e / args.steps))
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         out = {
@@ -209,31 +212,25 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def dominant_kernel_roofline(dev, n_images, peak_burst, src):
-    """The dominant kernel is the tcgen05 GEMM; time its largest instance of the step (vision fc1:
-    [n_images*197, 768] x [768 -> 3072], bias + GELU + pre-activation epilogue) live with CUDA events."""
+def dominant_kernel_roofline(step_fn, peak_sustained, src):
+    """The dominant kernel is the tcgen05 GEMM (x2k gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel: ~47% of the
+    step's GPU time in profiles/).  One extra, instrumented step after the timed region brackets EVERY GEMM and
+    attention launch with CUDA events on the launching stream; achieved = sum of algorithmic flops (2MNK per
+    launch) / sum of launch durations = flops per launch / average launch duration.  The kernels run inside a long
+    step, so the denominator is the sustained measured bf16 peak."""
     from x2vlm_b200 import ops
-    from x2vlm_b200._capi import ACT_GELU
-    M, N, K = n_images * 197, 3072, 768
-    a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16()
-    bias = torch.randn(N, device=dev)
-    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(o)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    times = []
-    for i in range(13):
-        flush.zero_()  # > L2: cold operands each launch
-        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        st.record()
-        ops.gemm(a, w, M, N, K, bias=bias, act=ACT_GELU, preact_out=pre, out_bf16=o)
-        en.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            times.append(st.elapsed_time(en))
-    ms = statistics.median(times)
-    tf = 2.0 * M * N * K / (ms / 1e3) / 1e12
-    return {"kernel": "x2k gemm_tcgen05_kernel<256,K,K> vision fc1 %dx%dx%d bias+GELU" % (M, N, K), "bound": "tensor",
-            "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst, "peak_source": src + " (burst)",
-            "launch_ms": ms, "traffic": None}
+    with ops.kernel_timing() as kt:
+        step_fn()
+    tot = kt.totals()
+    n, flops, ms = tot["gemm"]
+    tf = flops / (ms / 1e3) / 1e12
+    other = {k: {"launches": v[0], "ms_per_step": v[2], "tflops": v[1] / (v[2] / 1e3) / 1e12,
+                 "frac": v[1] / (v[2] / 1e3) / 1e12 / peak_sustained} for k, v in tot.items() if k != "gemm"}
+    return {"kernel": "x2k gemm_tcgen05_pair_kernel (+1-CTA gemm_tcgen05_kernel for M or N < 256), all %d launches of one step" % n,
+            "bound": "tensor", "achieved": tf, "peak": peak_sustained, "unit": "TFLOP/s", "frac": tf / peak_sustained,
+            "peak_source": src + " (sustained: kernels timed inside a long step)", "launches_per_step": n,
+            "avg_launch_ms": ms / n, "ms_per_step": ms, "algorithmic_gflop_per_launch": flops / n / 1e9,
+            "traffic": ROOFLINE_TRAFFIC, "other_kernels": other}
 
 
 def host_threads():

@@ -37,6 +37,43 @@ def launch_count():
     return int(C.lib().x2k_launch_count())
 
 
+# -- optional per-launch device timing (bench.py's roofline leg) -------------------------------------------------
+_timing = None  # list of (family, algorithmic flops, start event, end event) while kernel_timing() is active
+
+
+class kernel_timing:
+    """Context manager: bracket every GEMM / attention launch with CUDA events on the launching stream.
+    `totals()` afterwards gives {family: (launches, flops, ms)}.  Off (and free) by default."""
+
+    def __enter__(self):
+        global _timing
+        _timing = self.records = []
+        return self
+
+    def __exit__(self, *exc):
+        global _timing
+        _timing = None
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, flops, st, en in self.records:
+            n, f, ms = out.get(fam, (0, 0.0, 0.0))
+            out[fam] = (n + 1, f + flops, ms + st.elapsed_time(en))
+        return out
+
+
+def _timed(family, flops, call):
+    if _timing is None:
+        return call()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    r = call()
+    en.record()
+    _timing.append((family, flops, st, en))
+    return r
+
+
 def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=None, preact_out=None,
          dropout_p=0.0, dropout_seed=0, dropout_offset=0, gamma=None, row_scale=None, rows_per_scale=0,
          residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0, split_k=0):
@@ -74,7 +111,7 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
         g.out_f32, g.ld_out_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.tile_n = tile_n
     g.split_k = split_k
-    C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm")
+    _timed("gemm", 2.0 * M * N * K, lambda: C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm"))
 
 
 def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
@@ -162,7 +199,8 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, kv_index=None, n_kv=0, bias
 def attn_fwd(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw):
     """q/k/v/o: 2-D bf16 views [rows, >= H*64] (rows = B*Lq or n_kv*Lk) with row stride = ld."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw)
-    C.check(C.lib().x2k_attn_fwd(ctypes.byref(a), _stream()), "x2k_attn_fwd")
+    _timed("attn_fwd", 4.0 * B * H * Lq * Lk * 64,
+           lambda: C.check(C.lib().x2k_attn_fwd(ctypes.byref(a), _stream()), "x2k_attn_fwd"))
 
 
 def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None, **kw):
@@ -175,7 +213,8 @@ def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None,
     if ds_out is not None:  # [B, H, Lq, ld]
         a.ds_out = ds_out.data_ptr()
         a.ds_b_stride, a.ds_h_stride, a.ds_q_stride = ds_out.stride(0), ds_out.stride(1), ds_out.stride(2)
-    C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd")
+    _timed("attn_bwd", 10.0 * B * H * Lq * Lk * 64,
+           lambda: C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd"))
 
 
 def relpos_bias_gather(table, index, N, H, out):

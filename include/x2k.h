@@ -195,10 +195,28 @@ typedef struct X2kAttnArgs {
   int64_t ld_dq, ld_dk, ld_dv;
   void* ds_out;            /* bf16 or NULL */
   int64_t ds_b_stride, ds_h_stride, ds_q_stride;
+  /* grouped cross-attention (optional): work-item table built by x2k_attn_group_build from kv_index.
+   * When set, x2k_attn_bwd writes dK/dV PER K/V SOURCE: n_kv*Lk rows addressed like k/v, already
+   * summed over the query sequences that share the source (zeros for a source nobody reads). */
+  const int32_t* kv_groups;
 } X2kAttnArgs;
 
 int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);
 int x2k_attn_bwd(const X2kAttnArgs* args, void* stream);
+
+/* Short query sequences (Lq rounded up to 8 <= 64, no bias): several sequences share one 128-row MMA
+ * tile.  Self-attention (kv_index == NULL, Lq == Lk-sized segments) is packed automatically inside
+ * x2k_attn_fwd/bwd.  Cross-attention over shared K/V needs the sequences grouped by K/V source:
+ *   x2k_attn_group_slots(Lq)            -> sequences per tile G (0 = Lq not eligible)
+ *   x2k_attn_group_table_ints(B,n_kv,Lq)-> int32 elements the caller allocates for the table
+ *   x2k_attn_group_build(...)           -> fills the table on the device (one launch, no host sync):
+ *       {n_items, G, n_kv, B} | first[n_kv+1] | pad to 4 | items[(B + n_kv*(G-1))/G][12] = {src, n, b[0..7], 0, 0}
+ *       sequences of a source keep their batch order (deterministic).
+ * Replaces the per-(text, image) repeated K/V handling of models/xvlm.py:859-899 + models/xbert.py:343-349. */
+int32_t x2k_attn_group_slots(int32_t Lq);
+int64_t x2k_attn_group_table_ints(int32_t B, int32_t n_kv, int32_t Lq);
+int x2k_attn_group_build(const int32_t* kv_index, int32_t B, int32_t n_kv, int32_t Lq, int32_t* table,
+                         void* stream);
 
 /* BEiT relative position bias (models/beit2.py:138-143): out[h, i, j] = table[index[i*N+j], h]
  * written with row stride ld_out (>= N, multiple of 4), h stride N*ld_out; and its backward:

@@ -229,6 +229,114 @@ def test_attention_fwd_bwd(dev, case):
         assert (dbias - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
 
 
+def _group_table_ref(kv, n_kv, G):
+    """Python restatement of x2k_attn_group_build: sequences grouped by source in batch order, G per item."""
+    by_src = [[] for _ in range(n_kv)]
+    for b, s_ in enumerate(kv):
+        by_src[s_].append(b)
+    first, items = [0], []
+    for s_ in range(n_kv):
+        seqs = by_src[s_]
+        for i in range(0, len(seqs), G):
+            chunk = seqs[i:i + G]
+            items.append([s_, len(chunk)] + chunk + [-1] * (8 - len(chunk)) + [0, 0])
+        first.append(len(items))
+    return first, items
+
+
+@pytest.mark.parametrize("case", ["cross_grouped", "cross_grouped_l30", "cross_identity", "self_l30", "self_l16_3d", "self_l64"])
+def test_attention_packed(dev, case):
+    """Packed short-sequence kernels (attn_pack.cu): several sequences per MMA tile; grouped cross-attention returns
+    dK/dV per K/V source (summed over the sequences sharing it)."""
+    from x2vlm_b200 import ops
+    from x2vlm_b200 import _capi as C
+    from oracle import philox
+    g = torch.Generator(device=dev).manual_seed(23)
+    H, scale = 4, 0.125
+    D = H * 64
+    kv_list = None
+    p_drop, use_mask, per_query = 0.0, False, False
+    if case == "cross_grouped":      # source 1 unused, source 2 needs two work items (5 sequences, G = 3)
+        B, Lq, Lk, n_kv = 11, 40, 197, 4
+        kv_list = [0, 2, 3, 2, 0, 2, 2, 3, 2, 0, 3]
+        p_drop, use_mask = 0.1, True
+    elif case == "cross_grouped_l30":
+        B, Lq, Lk, n_kv = 9, 30, 50, 3
+        kv_list = [2, 2, 0, 1, 2, 2, 2, 0, 1]
+    elif case == "cross_identity":
+        B, Lq, Lk, n_kv = 5, 40, 197, 5
+        kv_list = list(range(5))
+        use_mask = True
+    elif case == "self_l30":
+        B, Lq, Lk, n_kv = 9, 30, 30, 9
+        p_drop, use_mask = 0.1, True
+    elif case == "self_l16_3d":
+        B, Lq, Lk, n_kv = 19, 16, 16, 19
+        use_mask = per_query = True
+    else:
+        B, Lq, Lk, n_kv = 5, 64, 64, 5
+        use_mask = True
+    cross = kv_list is not None
+    ld, lkp = ops.pad32(Lk), ops.pad16(Lk)
+    qkv = _bf(torch.randn(B * Lq, 3 * D, device=dev, generator=g))
+    if cross:
+        kvbuf = _bf(torch.randn(n_kv * Lk, 2 * D, device=dev, generator=g))
+        qv, kv_, vv = qkv[:, :D], kvbuf[:, :D], kvbuf[:, D:]
+        kv_index = torch.tensor(kv_list, device=dev, dtype=torch.int32)
+        table = ops.attn_group_table(kv_index, n_kv, Lq, Lk)
+        assert table is not None
+        G = C.lib().x2k_attn_group_slots(Lq)
+        first, items = _group_table_ref(kv_list, n_kv, G)
+        t = table.cpu().tolist()
+        assert t[:4] == [len(items), G, n_kv, B]
+        assert t[4:4 + n_kv + 1] == first
+        off = 4 + ((n_kv + 1 + 3) // 4) * 4
+        for i, it in enumerate(items):
+            assert t[off + 12 * i: off + 12 * i + 10] == it[:10], (i, t[off + 12 * i: off + 12 * i + 12], it)
+    else:
+        qv, kv_, vv = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        kv_index = table = None
+    mask = None
+    if use_mask and not per_query:
+        m01 = (torch.rand(B, Lk, device=dev, generator=g) > 0.3).float(); m01[:, 0] = 1
+        mask = torch.zeros(B, ld, device=dev); mask[:, :Lk] = (1 - m01) * -10000.0
+    if per_query:
+        m01 = torch.tril(torch.ones(Lq, Lk, device=dev)).expand(B, -1, -1)
+        mask = torch.zeros(B, Lq, ld, device=dev); mask[:, :, :Lk] = (1 - m01) * -10000.0
+    o = torch.full((B * Lq, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    lse = torch.full((B, H, Lq), float("nan"), device=dev)
+    kw = dict(kv_index=kv_index, n_kv=n_kv, kv_groups=table, mask=mask, mask_per_query=per_query, dropout_p=p_drop,
+              dropout_seed=77, dropout_offset=4096)
+    ops.attn_fwd(qv, kv_, vv, B, H, Lq, Lk, scale, o, lse, **kw)
+    sel = kv_index.long() if cross else torch.arange(B, device=dev)
+    qf = _heads(qv.float(), B, Lq, H).requires_grad_(True)
+    k_src = _heads(kv_.float(), n_kv, Lk, H).detach().requires_grad_(True)   # [n_kv, H, Lk, 64]
+    v_src = _heads(vv.float(), n_kv, Lk, H).detach().requires_grad_(True)
+    kf, vf = k_src[sel], v_src[sel]
+    mask_r = None
+    if mask is not None:
+        mask_r = mask[:, None, :, :Lk] if per_query else mask[:, None, None, :Lk]
+    keep = None
+    if p_drop > 0:
+        keep = torch.from_numpy(philox.keep_scale(77, 4096, B * H * Lq * lkp, p_drop)).view(B, H, Lq, lkp)[..., :Lk].to(dev)
+    oref, _ = _attn_ref(qf, kf, vf, scale, None, mask_r, keep)
+    o_cmp = _heads(o.float(), B, Lq, H)
+    assert not torch.isnan(o_cmp).any() and not torch.isnan(lse).any()
+    assert (o_cmp - oref).abs().max().item() < 2e-2 * max(1.0, oref.abs().max().item())
+    sref = (qf @ kf.transpose(-1, -2)) * scale + (mask_r if mask_r is not None else 0)
+    assert (lse - torch.logsumexp(sref, -1) / math.log(2.0)).abs().max().item() < 2e-3
+    do = _bf(torch.randn(B * Lq, D, device=dev, generator=g))
+    dq = torch.full((B * Lq, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    dkv = torch.full((n_kv * Lk, 2 * D), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.attn_bwd(qv, kv_, vv, B, H, Lq, Lk, scale, o, lse, do, dq, dkv[:, :D], dkv[:, D:], **kw)
+    oref.backward(_heads(do.float(), B, Lq, H))
+    for name, got, want in (("dq", _heads(dq.float(), B, Lq, H), qf.grad), ("dk", _heads(dkv[:, :D].float(), n_kv, Lk, H), k_src.grad),
+                            ("dv", _heads(dkv[:, D:].float(), n_kv, Lk, H), v_src.grad)):
+        assert not torch.isnan(got).any(), name
+        err = (got - want).abs().max().item()
+        assert err < 3e-2 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
+
+
 def test_relpos_gather_scatter(dev):
     from x2vlm_b200 import ops
     from oracle import restate

@@ -59,6 +59,7 @@ class X2kAttnArgs(ctypes.Structure):
         ("ld_dq", c_int64), ("ld_dk", c_int64), ("ld_dv", c_int64),
         ("ds_out", c_void_p),
         ("ds_b_stride", c_int64), ("ds_h_stride", c_int64), ("ds_q_stride", c_int64),
+        ("kv_groups", c_void_p),
     ]
 
 
@@ -83,6 +84,9 @@ SYMBOLS = {
     "x2k_cast_f32_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "x2k_attn_fwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
     "x2k_attn_bwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
+    "x2k_attn_group_slots": (c_int32, [c_int32]),
+    "x2k_attn_group_table_ints": (c_int64, [c_int32, c_int32, c_int32]),
+    "x2k_attn_group_build": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "x2k_relpos_bias_gather": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "x2k_relpos_bias_scatter": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64,
                                                c_void_p, c_void_p, c_void_p]),

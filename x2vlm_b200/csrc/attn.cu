@@ -615,6 +615,7 @@ int check_common(const X2kAttnArgs& a, const char* who) {
   X2K_REQUIRE(a.q && a.k && a.v && a.o && a.lse, "%s: NULL q/k/v/o/lse", who);
   X2K_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "%s: bad shape", who);
   X2K_REQUIRE(a.Lk <= 256, "%s: Lk=%d > 256 is not supported by this kernel", who, a.Lk);
+  X2K_REQUIRE(!a.kv_index || !a.kv_groups || a.n_kv > 0, "%s: kv_index / kv_groups need n_kv", who);
   X2K_REQUIRE(a.ld_q % 8 == 0 && a.ld_k % 8 == 0 && a.ld_v % 8 == 0 && a.ld_o % 8 == 0, "%s: ld must be multiples of 8", who);
   const int Lk_pad = (a.Lk + 15) & ~15;
   X2K_REQUIRE(!a.bias || (a.bias_q_stride % 4 == 0 && a.bias_h_stride % 4 == 0 && a.bias_q_stride >= ((a.Lk + 31) & ~31)),
@@ -653,6 +654,11 @@ extern "C" int x2k_attn_fwd(const X2kAttnArgs* args, void* stream_) {
   const X2kAttnArgs& a = *args;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_common(a, "x2k_attn_fwd")) return rc;
+  {
+    const int rc = attn_pack_fwd(a, stream);  // short query sequences: several sequences per MMA tile
+    if (rc <= 0) return rc;
+  }
+  X2K_REQUIRE(a.kv_groups == nullptr, "x2k_attn_fwd: kv_groups given but the shape is not eligible for the grouped kernel");
   AttnParams p;
   fill_params(a, p);
   const int n_kv = a.n_kv > 0 ? a.n_kv : a.B;
@@ -679,8 +685,13 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_common(a, "x2k_attn_bwd")) return rc;
   X2K_REQUIRE(a.d_o && a.dq && a.dk && a.dv, "x2k_attn_bwd: NULL d_o/dq/dk/dv");
-  X2K_REQUIRE(a.Lq <= 256, "x2k_attn_bwd: Lq=%d > 256 is not supported by this kernel", a.Lq);
   X2K_REQUIRE(a.ld_do % 8 == 0 && a.ld_dq % 8 == 0 && a.ld_dk % 8 == 0 && a.ld_dv % 8 == 0, "x2k_attn_bwd: ld alignment");
+  {
+    const int rc = attn_pack_bwd(a, stream);
+    if (rc <= 0) return rc;
+  }
+  X2K_REQUIRE(a.kv_groups == nullptr, "x2k_attn_bwd: kv_groups given but the shape is not eligible for the grouped kernel");
+  X2K_REQUIRE(a.Lq <= 256, "x2k_attn_bwd: Lq=%d > 256 is not supported by this kernel", a.Lq);
   X2K_REQUIRE(!a.ds_out || (a.ds_q_stride % 8 == 0 && a.ds_h_stride % 8 == 0 && a.ds_b_stride % 8 == 0 &&
                             a.ds_q_stride >= ((a.Lk + 15) & ~15)),
               "x2k_attn_bwd: ds_out strides must be multiples of 8 and cover Lk_pad");

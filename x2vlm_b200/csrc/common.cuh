@@ -31,6 +31,10 @@ EncodeTiledFn encode_tiled_fn();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// attn_pack.cu: packed short-sequence attention.  0 = launched, 1 = shape not eligible (use attn.cu), < 0 = error.
+int attn_pack_fwd(const X2kAttnArgs& a, cudaStream_t stream);
+int attn_pack_bwd(const X2kAttnArgs& a, cudaStream_t stream);
+
 #define X2K_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

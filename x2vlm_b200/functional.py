@@ -374,7 +374,7 @@ class _BertLayerFn(torch.autograd.Function):
             lse2 = torch.empty(Bt, H, L, dtype=torch.float32, device=dev)
             d_a2 = _drop(p_a, train, Bt * H * L * ops.pad16(Nk))
             ops.attn_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, ctx2, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
-                         mask=cfg["cross_mask"], dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
+                         kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"], dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
             s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
             d_h2 = _drop(p_h, train, M * D)
             ops.gemm(ctx2, sh["oc"].get(), M, D, D, bias=b_oc, dropout_p=d_h2[0], dropout_seed=d_h2[1],
@@ -456,13 +456,14 @@ class _BertLayerFn(torch.autograd.Function):
             ops.gemm(g2, sh["oc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx2)
             wg_oc = _wgrad(sh["oc"], g2, sv["ctx2"], D, D, M)
             dqc = _empty_bf16(M, D, dev=dev)
-            dkv_seq = _empty_bf16(Bt * Nk, 2 * D, dev=dev)
+            grouped = cfg.get("kv_groups") is not None  # grouped kernels return dK/dV per K/V source, already summed
+            dkv_seq = _empty_bf16((n_kv if grouped else Bt) * Nk, 2 * D, dev=dev)
             p, seed, off = sv["d_a2"]
             kvc = sv["kvc"]
             ops.attn_bwd(sv["qc"], kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, sv["ctx2"], sv["lse2"], dctx2, dqc,
-                         dkv_seq[:, :D], dkv_seq[:, D:], kv_index=cfg["kv_index"], n_kv=n_kv, mask=cfg["cross_mask"],
-                         dropout_p=p, dropout_seed=seed, dropout_offset=off)
-            if cfg["kv_index"] is not None:
+                         dkv_seq[:, :D], dkv_seq[:, D:], kv_index=cfg["kv_index"], n_kv=n_kv, kv_groups=cfg.get("kv_groups"),
+                         mask=cfg["cross_mask"], dropout_p=p, dropout_seed=seed, dropout_offset=off)
+            if cfg["kv_index"] is not None and not grouped:
                 dkv = _empty_bf16(n_kv * Nk, 2 * D, dev=dev)
                 ops.segment_sum_bf16(dkv_seq.view(Bt, Nk * 2 * D), cfg["kv_index"], n_kv, dkv.view(n_kv, Nk * 2 * D))
             else:

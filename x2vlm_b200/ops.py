@@ -170,8 +170,22 @@ def to_bf16(x):
     return out
 
 
+def attn_group_table(kv_index, n_kv, Lq, Lk):
+    """Work-item table of the grouped cross-attention kernels (x2k_attn_group_build): the B query sequences
+    grouped by the K/V source kv_index[b] they attend to.  Returns None when (Lq, Lk) is not eligible for the
+    grouped path (the one-sequence-per-tile kernels are used then)."""
+    _req(kv_index, torch.int32, "kv_index")
+    B = kv_index.numel()
+    if C.lib().x2k_attn_group_slots(Lq) < 1 or pad16(Lk) > 256 or n_kv > 4096:
+        return None
+    n = C.lib().x2k_attn_group_table_ints(B, n_kv, Lq)
+    table = torch.empty(n, dtype=torch.int32, device=kv_index.device)
+    C.check(C.lib().x2k_attn_group_build(_p(kv_index), B, n_kv, Lq, _p(table), _stream()), "x2k_attn_group_build")
+    return table
+
+
 def _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, kv_index=None, n_kv=0, bias=None, mask=None, mask_per_query=False,
-               dropout_p=0.0, dropout_seed=0, dropout_offset=0):
+               dropout_p=0.0, dropout_seed=0, dropout_offset=0, kv_groups=None):
     a = C.X2kAttnArgs()
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
         _req(t, torch.bfloat16, n)
@@ -181,6 +195,9 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, kv_index=None, n_kv=0, bias
     if kv_index is not None:
         _req(kv_index, torch.int32, "kv_index")
         a.kv_index = kv_index.data_ptr()
+    if kv_groups is not None:
+        _req(kv_groups, torch.int32, "kv_groups")
+        a.kv_groups = kv_groups.data_ptr()
     a.n_kv = int(n_kv)
     a.scale = float(scale)
     if bias is not None:  # [H, Lq, ld]
@@ -204,6 +221,7 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw):
 
 
 def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None, **kw):
+    """dk/dv: per query sequence [B*Lk rows]; with kv_groups=... per K/V source [n_kv*Lk rows], already summed."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw)
     for t, n in ((d_o, "d_o"), (dq, "dq"), (dk, "dk"), (dv, "dv"), (ds_out, "ds_out")):
         _req(t, torch.bfloat16, n)

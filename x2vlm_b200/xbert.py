@@ -169,6 +169,9 @@ class BertLayer(nn.Module):
         cfg = _layer_cfg(self.config, self.training, attention_mask, encoder_attention_mask, None,
                          hidden_states.shape[0], hidden_states.shape[1],
                          encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0, hidden_states.device)
+        if encoder_hidden_states is not None:
+            cfg["n_kv"] = encoder_hidden_states.shape[0]
+            _group_cross(cfg, hidden_states.shape[0], hidden_states.shape[1], encoder_hidden_states.shape[1], hidden_states.device)
         y, _ = self.fused(hidden_states, None, cfg, encoder_hidden_states)
         return (y, None)
 
@@ -196,9 +199,18 @@ def _layer_cfg(config, training, ext_self_mask, ext_cross_mask, kv_index, B, L, 
     cross_mask, cross_3d = _pad_mask(ext_cross_mask, B, L, Nk, device) if Nk else (None, False)
     if cross_3d:
         raise NotImplementedError("per-query cross-attention masks")
-    return dict(self_mask=self_mask, self_mask_3d=self_3d, cross_mask=cross_mask, kv_index=kv_index, n_kv=0,
+    return dict(self_mask=self_mask, self_mask_3d=self_3d, cross_mask=cross_mask, kv_index=kv_index, n_kv=0, kv_groups=None,
                 train=bool(training), p_hidden=float(config.hidden_dropout_prob),
                 p_attn=float(config.attention_probs_dropout_prob), eps=float(config.layer_norm_eps))
+
+
+def _group_cross(cfg, B, L, Nk, device):
+    """Short captions: group the query sequences by the K/V source they attend to (one table per encoder call,
+    shared by every fusion layer) so the grouped cross-attention kernels can stack them in one MMA tile."""
+    kv = cfg["kv_index"]
+    if kv is None:
+        kv = torch.arange(B, dtype=torch.int32, device=device)
+    cfg["kv_groups"] = ops.attn_group_table(kv, cfg["n_kv"], L, Nk)
 
 
 class BertEncoder(nn.Module):
@@ -244,6 +256,7 @@ class BertEncoder(nn.Module):
             if encoder_kv_index is None and enc.shape[0] != B:
                 raise ValueError("encoder_hidden_states batch %d != %d (pass encoder_kv_index to share K/V)" % (enc.shape[0], B))
             cfg["n_kv"] = enc.shape[0]
+            _group_cross(cfg, B, L, Nk, hidden_states.device)
             if output_layer > self.config.fusion_layer:
                 encb = ops.to_bf16(enc)  # one bf16 copy feeds the K/V projection of every fusion layer
         all_hidden_states = () if output_hidden_states else None

@@ -100,6 +100,8 @@ typedef struct X2kGemmArgs {
   int32_t max_ctas;        /* 0 = all SMs */
   int32_t split_k;         /* 0 = auto (split K over CTAs for wgrad-shaped GEMMs with a plain fp32 output,
                               accumulated with atomics), 1 = never, n = force n slices */
+  const uint64_t* dropout_offset_dev; /* optional device counter ADDED to dropout_offset at run time: a captured
+                              CUDA graph advances it between replays so every step draws fresh masks */
 } X2kGemmArgs;
 
 int x2k_gemm(const X2kGemmArgs* args, void* stream);
@@ -132,7 +134,8 @@ int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, 
  * ------------------------------------------------------------------------------------------ */
 int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, int32_t N, const float* gamma,
                           const float* row_scale, int32_t rows_per_scale, float dropout_p,
-                          uint64_t dropout_seed, uint64_t dropout_offset, const void* y_bf16,
+                          uint64_t dropout_seed, uint64_t dropout_offset,
+                          const uint64_t* dropout_offset_dev, const void* y_bf16,
                           int64_t ld_y, void* g_bf16, int64_t ld_g, float* dbias, float* dgamma,
                           void* stream);
 
@@ -199,6 +202,7 @@ typedef struct X2kAttnArgs {
    * When set, x2k_attn_bwd writes dK/dV PER K/V SOURCE: n_kv*Lk rows addressed like k/v, already
    * summed over the query sequences that share the source (zeros for a source nobody reads). */
   const int32_t* kv_groups;
+  const uint64_t* dropout_offset_dev; /* optional device counter added to dropout_offset (see X2kGemmArgs) */
 } X2kAttnArgs;
 
 int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);

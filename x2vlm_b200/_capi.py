@@ -38,6 +38,7 @@ class X2kGemmArgs(ctypes.Structure):
         ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
         ("out_f32", c_void_p), ("ld_out_f32", c_int64),
         ("tile_n", c_int32), ("max_ctas", c_int32), ("split_k", c_int32),
+        ("dropout_offset_dev", c_void_p),
     ]
 
 
@@ -60,6 +61,7 @@ class X2kAttnArgs(ctypes.Structure):
         ("ds_out", c_void_p),
         ("ds_b_stride", c_int64), ("ds_h_stride", c_int64), ("ds_q_stride", c_int64),
         ("kv_groups", c_void_p),
+        ("dropout_offset_dev", c_void_p),
     ]
 
 
@@ -77,7 +79,7 @@ SYMBOLS = {
                                          c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
     "x2k_scale_cast_colsum": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
-                                             c_int32, c_float, c_uint64, c_uint64, c_void_p, c_int64,
+                                             c_int32, c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
                                              c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "x2k_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "x2k_segment_sum_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),

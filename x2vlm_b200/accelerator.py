@@ -199,6 +199,90 @@ class GradBucketer:
         return order
 
 
+def _flatten(tree, prefix=""):
+    """{path: tensor} over nested dicts / lists / tuples of tensors (None leaves are skipped)."""
+    out = {}
+    if isinstance(tree, torch.Tensor):
+        out[prefix] = tree
+    elif isinstance(tree, dict):
+        for k, v in tree.items():
+            out.update(_flatten(v, prefix + "/" + str(k)))
+    elif isinstance(tree, (list, tuple)):
+        for i, v in enumerate(tree):
+            out.update(_flatten(v, prefix + "/" + str(i)))
+    elif tree is not None:
+        raise TypeError("GraphedStep inputs must be tensors or dicts/lists of tensors, got %r" % type(tree))
+    return out
+
+
+class GraphedStep:
+    """A whole training step — zero_grad, forward, backward (with the bucketed all-reduce), clip, AdamW — captured
+    ONCE into a CUDA graph and replayed: ~8 000 kernel launches per step cost the host one cudaGraphLaunch instead
+    of ~50 ms of Python/ctypes enqueue work (the step is launch-bound otherwise: bench.py reports
+    `host_enqueue_ms_per_step`).
+
+    `fn(inputs)` must be sync-free (no .item(), no pageable H2D copies) and return a tensor or a dict of tensors.
+    Inputs are copied into static device buffers before each replay, outputs are returned as static tensors (valid
+    until the next call).  What changes between replays although kernel arguments are frozen:
+      * the in-kernel dropout masks — every kernel adds the device counter `ops.dropout_base` to its Philox offset and
+        the graph's last node advances it by the offsets one step consumes;
+      * torch's own RNG consumers (hard-negative multinomial, DropPath) — torch.cuda.graph registers the default
+        generator, which is advanced per replay;
+      * the AdamW step count (a device tensor) and the learning rates (seg_lr device tensor, refreshed from
+        `optimizer.param_groups` before each replay).
+    """
+
+    def __init__(self, fn, example_inputs, optimizer=None, warmup=3):
+        from . import functional as XF
+        flat = _flatten(example_inputs)
+        if not flat:
+            raise ValueError("GraphedStep needs at least one input tensor")
+        dev = next(iter(flat.values())).device
+        self.device = dev
+        self.fn, self.optimizer = fn, optimizer
+        self.static_in = self._clone_tree(example_inputs)
+        self._flat_in = _flatten(self.static_in)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):  # lazy inits (cudaFuncSetAttribute, allocator pools, autotuners) happen here
+                fn(self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        base = ops.dropout_base(dev)
+        off0 = XF.dropout_state.offset
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(self.static_in)
+            self.x2k_launches_per_step = ops.launch_count() - l0  # libx2k kernel nodes in the graph
+            self.dropout_offsets_per_step = XF.dropout_state.offset - off0
+            base.add_(self.dropout_offsets_per_step)
+        self.replays = 0
+
+    @staticmethod
+    def _clone_tree(tree):
+        if isinstance(tree, torch.Tensor):
+            return tree.clone()
+        if isinstance(tree, dict):
+            return {k: GraphedStep._clone_tree(v) for k, v in tree.items()}
+        if isinstance(tree, (list, tuple)):
+            return type(tree)(GraphedStep._clone_tree(v) for v in tree)
+        return tree
+
+    def __call__(self, inputs=None):
+        if inputs is not None:
+            for path, t in _flatten(inputs).items():
+                dst = self._flat_in[path]
+                if dst.data_ptr() != t.data_ptr():
+                    dst.copy_(t, non_blocking=True)  # H2D from pinned memory or D2D; stream-ordered before the replay
+        if self.optimizer is not None and hasattr(self.optimizer, "_upload_hparams"):
+            self.optimizer._upload_hparams()
+        self.graph.replay()
+        self.replays += 1
+        return self.static_out
+
+
 class X2kDDPAccelerator:
     def __init__(self, cfg=None, logger=None):
         self.cfg = cfg or {}
@@ -236,6 +320,10 @@ class X2kDDPAccelerator:
         for b in model.buffers():
             dist.broadcast(b, src)
         self.arena.mark_dirty()
+
+    def graph_step(self, fn, example_inputs, optimizer=None, warmup=3):
+        """Capture `fn(inputs)` (a full sync-free training step) into a CUDA graph; see GraphedStep."""
+        return GraphedStep(fn, example_inputs, optimizer=optimizer, warmup=warmup)
 
     def backward_step(self, loss, optimizer=None):
         loss.backward()

@@ -31,6 +31,7 @@ struct AttnParams {
   int64_t mask_b_stride, mask_q_stride;
   float dropout_p;
   uint64_t seed, offset;
+  const uint64_t* offset_dev;
   __nv_bfloat16* o;
   int64_t ld_o;
   float* lse;
@@ -270,6 +271,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mx = fmaxf(mx, s_red[(half ^ 1) * 128 + row]);
     if (mx == -INFINITY) mx = 0.f;
     const DropCfg dc = make_drop(p.dropout_p);
+    const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
     const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * Lk_pad;
     const int c_begin = 2 * u_begin, c_end = min(nchunk, 2 * u_end);
     for (int c0 = c_begin; c0 < c_end; c0 += 2) {
@@ -291,7 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
               float k[8];
-              drop8(p.seed, p.offset, (drop_base + c * 16 + j) >> 3, dc, k);
+              drop8(p.seed, doff, (drop_base + c * 16 + j) >> 3, dc, k);
 #pragma unroll
               for (int i = 0; i < 8; ++i) pr[j + i] *= k[i];
             }
@@ -416,6 +418,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   const DropCfg dc = make_drop(p.dropout_p);
+  const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
   uint32_t mma_phase = 0;
   const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
@@ -497,7 +500,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
                   float k[8];
-                  drop8(p.seed, p.offset, (drop_base + k0 + j) >> 3, dc, k);
+                  drop8(p.seed, doff, (drop_base + k0 + j) >> 3, dc, k);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     // dS uses the un-dropped P; the P that feeds dV is the dropped one
@@ -635,7 +638,7 @@ void fill_params(const X2kAttnArgs& a, AttnParams& p) {
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.bias = a.bias; p.bias_h_stride = a.bias_h_stride; p.bias_q_stride = a.bias_q_stride;
   p.mask = a.mask; p.mask_b_stride = a.mask_b_stride; p.mask_q_stride = a.mask_q_stride;
-  p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset;
+  p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset; p.offset_dev = a.dropout_offset_dev;
   p.o = static_cast<__nv_bfloat16*>(a.o); p.ld_o = a.ld_o; p.lse = a.lse;
   p.d_o = static_cast<const __nv_bfloat16*>(a.d_o); p.ld_do = a.ld_do;
   p.dq = static_cast<__nv_bfloat16*>(a.dq); p.dk = static_cast<__nv_bfloat16*>(a.dk); p.dv = static_cast<__nv_bfloat16*>(a.dv);

@@ -38,6 +38,7 @@ struct PackParams {
   int64_t mask_b_stride, mask_q_stride;
   float dropout_p;
   uint64_t seed, offset;
+  const uint64_t* offset_dev;
   __nv_bfloat16* o;
   int64_t ld_o;
   float* lse;
@@ -267,6 +268,7 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mx = fmaxf(mx, s_red[(half ^ 1) * 128 + row]);
     if (mx == -INFINITY) mx = 0.f;
     const DropCfg dc = make_drop(p.dropout_p);
+    const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
     for (int c = cb; c < ce; ++c) {
       uint32_t s[16];
       tmem_ld_32x16(trow + c * 16, s);
@@ -284,7 +286,7 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const int kk = kk0 + j;
           if (ri.ok && kk >= 0 && kk < p.Lk) {
             float k[8];
-            drop8(p.seed, p.offset, (ri.drop_base + kk) >> 3, dc, k);
+            drop8(p.seed, doff, (ri.drop_base + kk) >> 3, dc, k);
 #pragma unroll
             for (int i = 0; i < 8; ++i) pr[j + i] *= k[i];
           }
@@ -416,6 +418,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t aq = sbase, ado = sbase + p.off_do, ak = sbase + p.off_k, av = sbase + p.off_v;
   const uint32_t ap = sbase + p.off_p, ads = sbase + p.off_ds;
   const DropCfg dc = make_drop(p.dropout_p);
+  const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
   const uint32_t idesc_s = make_idesc_bf16(128, N, 0, 0);
   const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
@@ -505,7 +508,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const int kk = kk0 + j;
             if (ri.ok && kk >= 0 && kk < p.Lk) {
               float k[8];
-              drop8(p.seed, p.offset, (ri.drop_base + kk) >> 3, dc, k);
+              drop8(p.seed, doff, (ri.drop_base + kk) >> 3, dc, k);
 #pragma unroll
               for (int i = 0; i < 8; ++i) { keep[j + i] = k[i]; pd[j + i] *= k[i]; }
             }
@@ -744,7 +747,7 @@ int attn_pack_plan(const X2kAttnArgs& a, bool backward, PackParams& p) {
   p.items_off = PK_HDR_INTS + ((p.n_kv + 1 + 3) & ~3);
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.mask = a.mask; p.mask_b_stride = a.mask_b_stride; p.mask_q_stride = a.mask_q_stride;
-  p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset;
+  p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset; p.offset_dev = a.dropout_offset_dev;
   p.o = static_cast<__nv_bfloat16*>(a.o); p.ld_o = a.ld_o; p.lse = a.lse;
   p.d_o = static_cast<const __nv_bfloat16*>(a.d_o); p.ld_do = a.ld_do;
   p.dq = static_cast<__nv_bfloat16*>(a.dq); p.dk = static_cast<__nv_bfloat16*>(a.dk); p.dv = static_cast<__nv_bfloat16*>(a.dv);

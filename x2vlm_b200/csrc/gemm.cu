@@ -34,6 +34,7 @@ struct EpiParams {
   int64_t ld_preact;
   float dropout_p;
   uint64_t dropout_seed, dropout_offset;
+  const uint64_t* dropout_offset_dev;  // added to dropout_offset when set (advanced on the device between graph replays)
   const float* gamma;
   const float* row_scale;
   int rows_per_scale;
@@ -129,11 +130,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
   if (p.dropout_p > 0.0f) {
     const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
+    const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
     // N is a multiple of 8 whenever dropout is used (checked on the host), so base % 8 == 0.
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float k[8];
-      drop8(p.dropout_seed, p.dropout_offset, (base + j) >> 3, dc, k);
+      drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
     }
@@ -332,10 +334,11 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
   if (has<EPI, EF_DROPOUT>(true) && p.dropout_p > 0.0f) {
     const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
+    const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float k[8];
-      drop8(p.dropout_seed, p.dropout_offset, (base + j) >> 3, dc, k);
+      drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
     }
@@ -930,6 +933,7 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   ep.aux = static_cast<const __nv_bfloat16*>(a.aux); ep.ld_aux = a.ld_aux;
   ep.preact_out = static_cast<__nv_bfloat16*>(a.preact_out); ep.ld_preact = a.ld_preact;
   ep.dropout_p = a.dropout_p; ep.dropout_seed = a.dropout_seed; ep.dropout_offset = a.dropout_offset;
+  ep.dropout_offset_dev = a.dropout_offset_dev;
   ep.gamma = a.gamma; ep.row_scale = a.row_scale; ep.rows_per_scale = a.rows_per_scale;
   ep.residual = a.residual; ep.ld_res = a.ld_res; ep.accumulate = a.accumulate;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); ep.ld_out_bf16 = a.ld_out_bf16;

@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) scale_cast_colsum_kernel(
     const float* __restrict__ dx, int64_t ld_dx, int M, int N, const float* __restrict__ gamma,
-    const float* __restrict__ row_scale, int rows_per_scale, float dropout_p, uint64_t seed, uint64_t offset,
-    const __nv_bfloat16* __restrict__ y, int64_t ld_y, __nv_bfloat16* __restrict__ g, int64_t ld_g,
+    const float* __restrict__ row_scale, int rows_per_scale, float dropout_p, uint64_t seed, uint64_t offset_host,
+    const uint64_t* __restrict__ offset_dev, const __nv_bfloat16* __restrict__ y, int64_t ld_y, __nv_bfloat16* __restrict__ g, int64_t ld_g,
     float* __restrict__ dbias, float* __restrict__ dgamma, int rows_per_block) {
   __shared__ float4 red[2][8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) scale_cast_colsum_kernel(
   float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
   if (gamma && col_ok) gm = __ldg(reinterpret_cast<const float4*>(gamma + n));
   const DropCfg dc = make_drop(dropout_p);
+  const uint64_t offset = offset_host + ((dropout_p > 0.f && offset_dev) ? __ldg(offset_dev) : 0ull);
   float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col_ok) {
     for (int m0 = r0 + w; m0 < r1; m0 += 32) {  // rows m0, m0+8, m0+16, m0+24: four loads in flight
@@ -443,8 +444,9 @@ extern "C" int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
 
 extern "C" int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, int32_t N, const float* gamma,
                                      const float* row_scale, int32_t rows_per_scale, float dropout_p,
-                                     uint64_t dropout_seed, uint64_t dropout_offset, const void* y_bf16, int64_t ld_y,
-                                     void* g_bf16, int64_t ld_g, float* dbias, float* dgamma, void* stream_) {
+                                     uint64_t dropout_seed, uint64_t dropout_offset, const uint64_t* dropout_offset_dev,
+                                     const void* y_bf16, int64_t ld_y, void* g_bf16, int64_t ld_g, float* dbias,
+                                     float* dgamma, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   X2K_REQUIRE(dx && M > 0 && N > 0 && N % 4 == 0 && ld_dx % 4 == 0, "x2k_scale_cast_colsum: bad dx/shape");
   X2K_REQUIRE(!dgamma || (y_bf16 && ld_y % 4 == 0), "x2k_scale_cast_colsum: dgamma needs y");
@@ -457,7 +459,7 @@ extern "C" int x2k_scale_cast_colsum(const float* dx, int64_t ld_dx, int32_t M, 
   if (rows_per_block < 64) rows_per_block = 64;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
   scale_cast_colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, stream>>>(
-      dx, ld_dx, M, N, gamma, row_scale, rows_per_scale, dropout_p, dropout_seed, dropout_offset,
+      dx, ld_dx, M, N, gamma, row_scale, rows_per_scale, dropout_p, dropout_seed, dropout_offset, dropout_offset_dev,
       static_cast<const __nv_bfloat16*>(y_bf16), ld_y, static_cast<__nv_bfloat16*>(g_bf16), ld_g, dbias, dgamma,
       rows_per_block);
   X2K_CHECK_CUDA(cudaGetLastError());

@@ -74,6 +74,21 @@ def _timed(family, flops, call):
     return r
 
 
+_DROP_BASE = {}
+
+
+def dropout_base(device):
+    """Device-side counter added to every kernel's (host-baked) dropout offset.  Zero in eager execution — the host
+    counter of functional.dropout_state advances instead; a captured step graph advances it on the device at the end
+    of every replay (accelerator.GraphedStep), so replays draw fresh Philox ranges although their kernel arguments are
+    frozen."""
+    key = (device.type, device.index)
+    t = _DROP_BASE.get(key)
+    if t is None:
+        t = _DROP_BASE[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return t
+
+
 def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=None, preact_out=None,
          dropout_p=0.0, dropout_seed=0, dropout_offset=0, gamma=None, row_scale=None, rows_per_scale=0,
          residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0, split_k=0):
@@ -98,6 +113,8 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
     if preact_out is not None:
         g.preact_out, g.ld_preact = preact_out.data_ptr(), preact_out.stride(0)
     g.dropout_p, g.dropout_seed, g.dropout_offset = float(dropout_p), int(dropout_seed), int(dropout_offset)
+    if dropout_p > 0.0:
+        g.dropout_offset_dev = dropout_base(a.device).data_ptr()
     if gamma is not None:
         g.gamma = gamma.data_ptr()
     if row_scale is not None:
@@ -138,7 +155,7 @@ def scale_cast_colsum(dx, M, N, g_bf16=None, gamma=None, row_scale=None, rows_pe
     _req(dx, torch.float32, "dx")
     C.check(C.lib().x2k_scale_cast_colsum(
         _p(dx), dx.stride(0), M, N, _p(gamma), _p(row_scale), int(rows_per_scale), float(dropout_p), int(dropout_seed),
-        int(dropout_offset), _p(y_bf16), y_bf16.stride(0) if y_bf16 is not None else 0, _p(g_bf16),
+        int(dropout_offset), _p(dropout_base(dx.device)) if dropout_p > 0.0 else None, _p(y_bf16), y_bf16.stride(0) if y_bf16 is not None else 0, _p(g_bf16),
         g_bf16.stride(0) if g_bf16 is not None else 0, _p(dbias), _p(dgamma), _stream()), "x2k_scale_cast_colsum")
 
 
@@ -208,6 +225,8 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, kv_index=None, n_kv=0, bias
         a.mask, a.mask_b_stride = mask.data_ptr(), mask.stride(0)
         a.mask_q_stride = mask.stride(1) if mask_per_query else 0
     a.dropout_p, a.dropout_seed, a.dropout_offset = float(dropout_p), int(dropout_seed), int(dropout_offset)
+    if dropout_p > 0.0:
+        a.dropout_offset_dev = dropout_base(q.device).data_ptr()
     a.o, a.ld_o = o.data_ptr(), o.stride(0)
     a.lse = lse.data_ptr()
     return a

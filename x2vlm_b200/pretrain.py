@@ -90,6 +90,14 @@ def giou_pairs(b1, b2):
     return inter / union - (area - union) / area
 
 
+def _itm_labels(bs, device):
+    """[1]*bs + [0]*2bs (models/xvlm.py:895-897), built on the device: a pageable host-to-device copy would be a
+    hidden sync and is illegal inside CUDA-graph capture."""
+    labels = torch.zeros(3 * bs, dtype=torch.long, device=device)
+    labels[:bs] = 1
+    return labels
+
+
 class XVLM(nn.Module):
     def __init__(self, config, load_vision_params=False, load_text_params=False, pretraining=True):
         super().__init__()
@@ -190,7 +198,7 @@ class XVLM(nn.Module):
         cross = self.get_cross_embeds(image_embeds, iatt_all, text_embeds=text_all, text_atts=tatt_all,
                                       encoder_kv_index=kv_index)[:, 0, :]
         output = self.itm_head(cross)
-        itm_labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)]).to(output.device)
+        itm_labels = _itm_labels(bs, output.device)
         return F.cross_entropy(output, itm_labels)
 
     def get_mlm_loss(self, text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids):
@@ -296,14 +304,14 @@ class XVLM(nn.Module):
             enc += [emb_r, full[Bi:]]
         cross = self.get_cross_embeds(torch.cat(enc), torch.cat(iatt), text_embeds=torch.cat(txt), text_atts=torch.cat(tatt),
                                       encoder_kv_index=torch.cat(kv).to(torch.int32))
-        labels_i = torch.cat([torch.ones(Bi, dtype=torch.long), torch.zeros(2 * Bi, dtype=torch.long)]).to(dev)
+        labels_i = _itm_labels(Bi, dev)
         itm_logits_i = self.itm_head(cross[:3 * Bi, 0])
         losses["image"]["loss_itm"] = F.cross_entropy(itm_logits_i, labels_i)
         mlm_seq = [cross[3 * Bi:4 * Bi]]
         mpos, mids = [ib["masked_pos"]], [ib["masked_ids"]]
         if has_r:
             o = 4 * Bi
-            labels_r = torch.cat([torch.ones(Br, dtype=torch.long), torch.zeros(2 * Br, dtype=torch.long)]).to(dev)
+            labels_r = _itm_labels(Br, dev)
             losses["region"]["loss_itm"] = F.cross_entropy(self.itm_head(cross[o:o + 3 * Br, 0]), labels_r)
             mlm_seq.append(cross[o + 3 * Br:o + 4 * Br])
             mpos.append(rb["masked_pos"]); mids.append(rb["masked_ids"])

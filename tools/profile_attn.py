@@ -5,7 +5,16 @@ import torch
 from x2vlm_b200 import ops
 dev = torch.device("cuda:0"); torch.manual_seed(0)
 H, D = 12, 768
-def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps=3):
+def step_kv_index():
+    """kv_index of the step's fusion batch (pretrain.XVLM.forward_mixed): 576 sequences over 154 K/V sources."""
+    g = torch.Generator().manual_seed(0)
+    ar = torch.arange(64)
+    img = [ar, torch.randint(0, 64, (64,), generator=g), ar, ar]
+    reg = [64 + ar, 64 + torch.randint(0, 64, (64,), generator=g), 64 + ar, 64 + ar, 128 + torch.randint(0, 26, (64,), generator=g).sort().values]
+    return torch.cat(img + reg).int().to(dev)
+
+
+def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps=3, grouped=False):
     ld = ops.pad32(Lk)
     q = torch.randn(B * Lq, 3 * D, device=dev).bfloat16()
     kv = torch.randn(n_kv * Lk, 2 * D, device=dev).bfloat16()
@@ -15,12 +24,13 @@ def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps
         qv, kk, vv = q[:, :D], kv[:, :D], kv[:, D:]
     b = torch.randn(H, Lq, ld, device=dev) if bias else None
     m = torch.zeros(B, ld, device=dev) if mask else None
-    idx = (torch.arange(B, device=dev) % n_kv).int() if shared else None
+    idx = (step_kv_index() if grouped else (torch.arange(B, device=dev) % n_kv).int()) if shared else None
+    groups = ops.attn_group_table(idx, n_kv, Lq, Lk) if grouped else None
     o = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, Lq, device=dev)
     do = torch.randn(B * Lq, D, device=dev).bfloat16()
-    dq = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); dkv = torch.empty(B * Lk, 2 * D, device=dev, dtype=torch.bfloat16)
+    dq = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); dkv = torch.empty((n_kv if grouped else B) * Lk, 2 * D, device=dev, dtype=torch.bfloat16)
     ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if bias else None
-    kw = dict(kv_index=idx, n_kv=n_kv, bias=b, mask=m, dropout_p=p, dropout_seed=1, dropout_offset=0)
+    kw = dict(kv_index=idx, n_kv=n_kv, kv_groups=groups, bias=b, mask=m, dropout_p=p, dropout_seed=1, dropout_offset=0)
     for _ in range(reps):
         ops.attn_fwd(qv, kk, vv, B, H, Lq, Lk, 0.125, o, lse, **kw)
         ops.attn_bwd(qv, kk, vv, B, H, Lq, Lk, 0.125, o, lse, do, dq, dkv[:, :D], dkv[:, D:], ds_out=ds, **kw)
@@ -32,4 +42,4 @@ def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps
 run("beit", 90, 197, 197, 90, bias=True)
 run("text", 256, 40, 40, 256, mask=True, p=0.1)
 run("fus-self", 576, 40, 40, 576, mask=True, p=0.1)
-run("cross", 576, 40, 197, 154, mask=True, shared=True, p=0.1)
+run("cross", 576, 40, 197, 154, mask=True, shared=True, p=0.1, grouped=True)

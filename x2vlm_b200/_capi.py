@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libx2k.so")
+LIB_PATH = os.environ.get("X2K_LIB") or os.path.join(_HERE, "lib", "libx2k.so")  # X2K_LIB: developer builds (tools/)
 
 c_void_p = ctypes.c_void_p
 c_int32 = ctypes.c_int32

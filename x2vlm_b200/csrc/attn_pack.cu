@@ -15,6 +15,8 @@
 // Slots are 8-row aligned (Lq8 = Lq rounded up to 8) so every slot is a whole number of 128B-swizzle atoms
 // and is fetched by its own TMA box; unused slots are fetched from an out-of-bounds coordinate (zero fill).
 // The dropout stream is indexed exactly like attn.cu's (element ((b*H+h)*Lq + i)*Lk_pad + j).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace x2k {
@@ -25,6 +27,18 @@ constexpr int PK_THREADS = 256;
 constexpr int PK_MAX_G = 8;
 constexpr int PK_ITEM_INTS = 12;  // {src, n, b[0..7], -, -}
 constexpr int PK_HDR_INTS = 4;    // {n_items, G, n_kv, B}
+
+// Optional phase trace (compile with -DX2K_PACK_TRACE): clock64 stamps of one CTA, read back by x2k_debug_pack_trace.
+#ifdef X2K_PACK_TRACE
+__device__ long long g_pack_trace[2][64];
+#define PK_TRACE(i)                                                                           \
+  do {                                                                                        \
+    if (blockIdx.x == 40 && blockIdx.y == 3 && (threadIdx.x == 0 || threadIdx.x == 200))      \
+      g_pack_trace[threadIdx.x ? 1 : 0][(i)] = clock64();                                     \
+  } while (0)
+#else
+#define PK_TRACE(i) do {} while (0)
+#endif
 
 struct PackParams {
   int B, H, Lq, Lk, Lq8, Lk8, G;
@@ -65,8 +79,8 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void zero_smem(uint32_t addr, int bytes, int tid) {
-  for (int i = tid * 16; i < bytes; i += PK_THREADS * 16) st_shared_v4(addr + i, 0u, 0u, 0u, 0u);
+__device__ __forceinline__ void zero_smem(uint32_t addr, int bytes, int tid, int nthreads) {
+  for (int i = tid * 16; i < bytes; i += nthreads * 16) st_shared_v4(addr + i, 0u, 0u, 0u, 0u);
 }
 
 // sequence id sitting in `slot` of work item `item`, or -1
@@ -93,15 +107,17 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const uint32_t 
   v.w = pack_bf16x2(__uint_as_float(s[14]) * mul, __uint_as_float(s[15]) * mul);
   *reinterpret_cast<uint4*>(dst + 8) = v;
 }
-// TMEM lane (this thread's row) -> 2 x 16 fp32 columns -> scaled bf16 -> 64 bytes of global memory
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, uint32_t tcol_addr, float mul, bool valid) {
+// TMEM lane (this thread's row) -> 64 / NPART fp32 columns starting at part * (64 / NPART) -> scaled bf16 -> global
+template <int NPART>
+__device__ __forceinline__ void store_row_part(__nv_bfloat16* dst_row, uint32_t tcol_addr, int part, float mul, bool valid) {
+  constexpr int W = 64 / NPART;  // 32 or 16 columns
   uint32_t a[16], b[16];
-  tmem_ld_32x16(tcol_addr, a);
-  tmem_ld_32x16(tcol_addr + 16, b);
+  tmem_ld_32x16(tcol_addr + part * W, a);
+  if (W == 32) tmem_ld_32x16(tcol_addr + part * W + 16, b);
   tmem_wait_ld();
   if (valid) {
-    store16_bf16(dst, a, mul);
-    store16_bf16(dst + 16, b, mul);
+    store16_bf16(dst_row + part * W, a, mul);
+    if (W == 32) store16_bf16(dst_row + part * W + 16, b, mul);
   }
 }
 
@@ -152,7 +168,8 @@ __device__ __forceinline__ void chunk_span(const PackParams& p, int quad, int& c
 // ---------------------------------------------------------------------------------------------
 // forward: grid (work items, H); 256 threads; TMEM = S (N columns), O aliases its first 64 columns
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PK_THREADS, 2)
+template <int NPART>
+__global__ void __launch_bounds__(NPART * 128, 2)
 attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const PackParams p) {
   const int item = blockIdx.x, h = blockIdx.y;
@@ -164,17 +181,18 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sK = smem + p.off_k;
   uint8_t* sV = smem + p.off_v;
   const uint32_t sP_addr = sbase;  // P overwrites Q/K once S is in TMEM
-  float* s_red = reinterpret_cast<float*>(smem + p.off_red);  // [2 halves][128 rows]
+  float* s_red = reinterpret_cast<float*>(smem + p.off_red);  // [NPART column parts][128 rows]
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_mma = bar_qk + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_qk + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, half = warp >> 2;
+  const int quad = warp & 3, part = warp >> 2;  // TMEM lane quadrant (hardware rule) / column part of the row
   const int row = quad * 32 + lane;
   const int N = p.N, nchunk = N >> 4;
   const int q_rows = p.G * p.Lq8, k_rows = p.cross ? N : p.G * p.Lk8;
+  constexpr int NT = NPART * 128;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_qk, 1);
@@ -209,10 +227,10 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tmem_relinquish();
   }
   // rows no TMA box covers must not hold NaN bit patterns: they are multiplied by P = 0 / are tile padding
-  zero_smem(sbase + q_rows * 128, (128 - q_rows) * 128, threadIdx.x);
+  zero_smem(sbase + q_rows * 128, (128 - q_rows) * 128, threadIdx.x, NT);
   if (!p.cross) {
-    zero_smem(sbase + p.off_k + k_rows * 128, (N - k_rows) * 128, threadIdx.x);
-    zero_smem(sbase + p.off_v + k_rows * 128, (N - k_rows) * 128, threadIdx.x);
+    zero_smem(sbase + p.off_k + k_rows * 128, (N - k_rows) * 128, threadIdx.x, NT);
+    zero_smem(sbase + p.off_v + k_rows * 128, (N - k_rows) * 128, threadIdx.x, NT);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -235,8 +253,7 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   int c_lo, c_hi;
   chunk_span(p, quad, c_lo, c_hi);
   const bool warp_live = __any_sync(0xffffffffu, ri.ok) && c_hi > c_lo;
-  const int c_mid = (c_lo + c_hi + 1) >> 1;
-  const int cb = half == 0 ? c_lo : c_mid, ce = half == 0 ? c_mid : c_hi;  // this half's live chunks
+  const int cb = c_lo + ((c_hi - c_lo) * part) / NPART, ce = c_lo + ((c_hi - c_lo) * (part + 1)) / NPART;  // my live chunks
   mbar_wait_warp(bar_mma, 0);
   tc_fence_after();
 
@@ -261,11 +278,12 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_st_32x16(trow + c * 16, s);
     }
     tmem_wait_st();
-    s_red[half * 128 + row] = mx;
+    s_red[part * 128 + row] = mx;
   }
   __syncthreads();  // max exchange; every S column has been read, so P may overwrite Q/K
   if (warp_live) {
-    mx = fmaxf(mx, s_red[(half ^ 1) * 128 + row]);
+#pragma unroll
+    for (int i = 0; i < NPART; ++i) mx = fmaxf(mx, s_red[i * 128 + row]);
     if (mx == -INFINITY) mx = 0.f;
     const DropCfg dc = make_drop(p.dropout_p);
     const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
@@ -299,13 +317,13 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   }
   // columns outside the live span (other sequences' keys) and rows of dead warps: P = 0
-  for (int c = half; c < nchunk; c += 2) {
+  for (int c = part; c < nchunk; c += NPART) {
     if (warp_live && c >= c_lo && c < c_hi) continue;
     st_shared_v4(sP_addr + swz_off(row, c * 16), 0u, 0u, 0u, 0u);
     st_shared_v4(sP_addr + swz_off(row, c * 16 + 8), 0u, 0u, 0u, 0u);
   }
-  __syncthreads();  // every thread has read its partner's max before the slots are reused for the sums
-  if (warp_live) s_red[half * 128 + row] = sum;
+  __syncthreads();  // every thread has read its partners' max before the slots are reused for the sums
+  if (warp_live) s_red[part * 128 + row] = sum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -325,12 +343,14 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncwarp();
   mbar_wait_warp(bar_mma, 1);
   tc_fence_after();
-  if (warp_live) {  // each half writes 32 of the 64 output dims of its rows
-    const float tot = sum + s_red[(half ^ 1) * 128 + row];
+  if (warp_live) {  // each part writes 64 / NPART of the 64 output dims of its rows
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPART; ++i) tot += s_red[i * 128 + row];
     const float inv = tot > 0.f ? 1.0f / tot : 0.f;
-    __nv_bfloat16* dst = p.o + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_o + h * 64 + half * 32;
-    store_row32_bf16(dst, trow + half * 32, inv, ri.ok);
-    if (ri.ok && half == 0) p.lse[(static_cast<int64_t>(ri.b) * p.H + h) * p.Lq + ri.q] = mx + log2f(tot);
+    __nv_bfloat16* dst = p.o + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_o + h * 64;
+    store_row_part<NPART>(dst, trow, part, inv, ri.ok);
+    if (ri.ok && part == 0) p.lse[(static_cast<int64_t>(ri.b) * p.H + h) * p.Lq + ri.q] = mx + log2f(tot);
   }
   tc_fence_before();
   __syncthreads();
@@ -347,21 +367,23 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t TM_DK = 256, TM_DV = 384;
 
-__global__ void __launch_bounds__(PK_THREADS, 1)
+template <int NPART>
+__global__ void __launch_bounds__(NPART * 128, 1)
 attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                      const PackParams p) {
   const int grp = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, half = warp >> 2;
+  const int quad = warp & 3, part = warp >> 2;
   const int row = quad * 32 + lane;
+  constexpr int NT = NPART * 128;
   const int N = p.N, nchunk = N >> 4, ntile = (N + 127) >> 7;
   int first_item = grp, n_items = 1;
   if (p.cross) {
     first_item = __ldg(p.table + PK_HDR_INTS + grp);
     n_items = __ldg(p.table + PK_HDR_INTS + grp + 1) - first_item;
     if (n_items <= 0) {  // a K/V source nobody looked at: its gradient is zero (CTA-uniform exit)
-      for (int i = threadIdx.x; i < p.Lk * 8; i += PK_THREADS) {
+      for (int i = threadIdx.x; i < p.Lk * 8; i += NT) {
         const int64_t r = static_cast<int64_t>(grp) * p.Lk + (i >> 3);
         const int c = (i & 7) * 8;
         *reinterpret_cast<uint4*>(p.dk + r * p.ld_dk + h * 64 + c) = make_uint4(0u, 0u, 0u, 0u);
@@ -370,6 +392,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       return;
     }
   }
+  PK_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -403,17 +426,18 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
-  zero_smem(sbase + q_rows * 128, (128 - q_rows) * 128, threadIdx.x);
-  zero_smem(sbase + p.off_do + q_rows * 128, (128 - q_rows) * 128, threadIdx.x);
+  zero_smem(sbase + q_rows * 128, (128 - q_rows) * 128, threadIdx.x, NT);
+  zero_smem(sbase + p.off_do + q_rows * 128, (128 - q_rows) * 128, threadIdx.x, NT);
   if (!p.cross) {
-    zero_smem(sbase + p.off_k + k_rows * 128, (N - k_rows) * 128, threadIdx.x);
-    zero_smem(sbase + p.off_v + k_rows * 128, (N - k_rows) * 128, threadIdx.x);
+    zero_smem(sbase + p.off_k + k_rows * 128, (N - k_rows) * 128, threadIdx.x, NT);
+    zero_smem(sbase + p.off_v + k_rows * 128, (N - k_rows) * 128, threadIdx.x, NT);
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  PK_TRACE(1);
   const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const uint32_t aq = sbase, ado = sbase + p.off_do, ak = sbase + p.off_k, av = sbase + p.off_v;
   const uint32_t ap = sbase + p.off_p, ads = sbase + p.off_ds;
@@ -424,12 +448,12 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
   int c_lo, c_hi;
   chunk_span(p, quad, c_lo, c_hi);
-  const int c_mid = (c_lo + c_hi + 1) >> 1;
-  const int cb = half == 0 ? c_lo : c_mid, ce = half == 0 ? c_mid : c_hi;
+  const int cb = c_lo + ((c_hi - c_lo) * part) / NPART, ce = c_lo + ((c_hi - c_lo) * (part + 1)) / NPART;
   uint32_t mma_phase = 0;
 
   for (int ci = 0; ci < n_items; ++ci) {
     const int item = first_item + ci;
+    PK_TRACE(2 + ci * 10);
     if (threadIdx.x == 0) {
       int bs[PK_MAX_G];
 #pragma unroll
@@ -460,10 +484,12 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
       }
     }
+    PK_TRACE(3 + ci * 10);
     if (threadIdx.x == 0) {
       if (ci == 0) mbar_wait(bar_kv, 0);
       mbar_wait(bar_q, ci & 1);
       tc_fence_after();
+      PK_TRACE(4 + ci * 10);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s, k != 0);
@@ -479,6 +505,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_wait_warp(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    PK_TRACE(5 + ci * 10);
 
     // ---- pass 1: P (and, when dP is already there, dS) for this thread's row and column half ----
     if (warp_live) {
@@ -530,7 +557,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
     // columns outside the live span / rows of dead warps contribute nothing: P = dS = 0
-    for (int c = half; c < nchunk; c += 2) {
+    for (int c = part; c < nchunk; c += NPART) {
       if (warp_live && c >= c_lo && c < c_hi) continue;
       const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
       st_shared_v4(ap + o0, 0u, 0u, 0u, 0u);
@@ -538,6 +565,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       st_shared_v4(ads + o0, 0u, 0u, 0u, 0u);
       st_shared_v4(ads + o1, 0u, 0u, 0u, 0u);
     }
+    PK_TRACE(6 + ci * 10);
     if (!dual) {
       // ---- dP = dO · Vᵀ into the columns S occupied, then pass 2: dS = P ∘ (dP·keep − delta) ----
       tc_fence_before();
@@ -553,6 +581,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait_warp(bar_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
+      PK_TRACE(7 + ci * 10);
       if (warp_live) {
 #pragma unroll 1
         for (int c = cb; c < ce; ++c) {
@@ -579,9 +608,11 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
     }
+    PK_TRACE(8 + ci * 10);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    PK_TRACE(9 + ci * 10);
 
     if (threadIdx.x == 0) {
       tc_fence_after();
@@ -605,15 +636,16 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_wait_warp(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    PK_TRACE(10 + ci * 10);
     if (warp_live)
-      store_row32_bf16(p.dq + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_dq + h * 64 + half * 32, trow + half * 32,
-                       p.scale, ri.ok);
+      store_row_part<NPART>(p.dq + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_dq + h * 64, trow, part, p.scale, ri.ok);
     tc_fence_before();
     __syncthreads();  // X, Q, dO, P, dS are free for the next item
     tc_fence_after();
+    PK_TRACE(11 + ci * 10);
   }
 
-  // ---- drain dK / dV: thread == key row of tile t, each half stores 32 of the 64 dims ----
+  // ---- drain dK / dV: thread == key row of tile t, each part stores 64 / NPART of the 64 dims ----
   for (int t = 0; t < ntile; ++t) {
     const int key = t * 128 + row;
     bool kvalid;
@@ -627,15 +659,17 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       kvalid = key < N && b >= 0 && kk < p.Lk;
       r = static_cast<int64_t>(b) * p.Lk + kk;
     }
-    store_row32_bf16(p.dk + r * p.ld_dk + h * 64 + half * 32, trow + TM_DK + t * 64 + half * 32, p.scale, kvalid);
-    store_row32_bf16(p.dv + r * p.ld_dv + h * 64 + half * 32, trow + TM_DV + t * 64 + half * 32, 1.0f, kvalid);
+    store_row_part<NPART>(p.dk + r * p.ld_dk + h * 64, trow + TM_DK + t * 64, part, p.scale, kvalid);
+    store_row_part<NPART>(p.dv + r * p.ld_dv + h * 64, trow + TM_DV + t * 64, part, 1.0f, kvalid);
   }
+  PK_TRACE(62);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  PK_TRACE(63);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,6 +749,18 @@ attn_group_build_kernel(const int32_t* __restrict__ kv_index, int B, int n_kv, i
   }
 }
 
+// threads per CTA / 128 = how many warps share a TMEM lane quadrant (each takes a column part of the rows).
+// Tuning override: X2K_PACK_PARTS_FWD / X2K_PACK_PARTS_BWD = 2 | 4 (read once).
+int pack_parts(bool backward) {
+  static int cached[2] = {0, 0};
+  int& c = cached[backward ? 1 : 0];
+  if (c == 0) {
+    const char* e = getenv(backward ? "X2K_PACK_PARTS_BWD" : "X2K_PACK_PARTS_FWD");
+    c = (e && atoi(e) == 2) ? 2 : 4;
+  }
+  return c;
+}
+
 int pack_slots(int Lq) {
   const int Lq8 = (Lq + 7) & ~7;
   if (Lq <= 0 || Lq8 > 64) return 0;
@@ -761,7 +807,7 @@ int attn_pack_plan(const X2kAttnArgs& a, bool backward, PackParams& p) {
     p.off_v = max(16384 + kv_bytes, p_bytes);
     p.off_p = 0; p.off_ds = 0;
     p.off_red = p.off_v + kv_bytes;
-    p.off_bar = p.off_red + 1024;
+    p.off_bar = p.off_red + 2048;
     p.tmem_cols = p.N <= 128 ? 128 : 256;
   } else {
     p.off_do = 16384;
@@ -787,13 +833,17 @@ int attn_pack_fwd_launch(const X2kAttnArgs& a, PackParams& p, cudaStream_t strea
   const int smem = p.off_bar + 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
     attr_set = true;
   }
   X2K_REQUIRE(smem <= 116 * 1024, "x2k_attn_fwd (packed): %d bytes of shared memory", smem);
   const int n_items = p.cross ? (a.B + p.n_kv * (p.G - 1)) / p.G : (a.B + p.G - 1) / p.G;
   dim3 grid(n_items, a.H);
-  attn_pack_fwd_kernel<<<grid, PK_THREADS, smem, stream>>>(tq, tk, tv, p);
+  if (pack_parts(false) == 4)
+    attn_pack_fwd_kernel<4><<<grid, 512, smem, stream>>>(tq, tk, tv, p);
+  else
+    attn_pack_fwd_kernel<2><<<grid, 256, smem, stream>>>(tq, tk, tv, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;
@@ -811,12 +861,16 @@ int attn_pack_bwd_launch(const X2kAttnArgs& a, PackParams& p, cudaStream_t strea
   const int smem = p.off_bar + 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_pack_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   X2K_REQUIRE(smem <= 227 * 1024, "x2k_attn_bwd (packed): %d bytes of shared memory", smem);
   dim3 grid(p.cross ? p.n_kv : (a.B + p.G - 1) / p.G, a.H);
-  attn_pack_bwd_kernel<<<grid, PK_THREADS, smem, stream>>>(tq, tk, tv, tdo, p);
+  if (pack_parts(true) == 4)
+    attn_pack_bwd_kernel<4><<<grid, 512, smem, stream>>>(tq, tk, tv, tdo, p);
+  else
+    attn_pack_bwd_kernel<2><<<grid, 256, smem, stream>>>(tq, tk, tv, tdo, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;
@@ -841,6 +895,12 @@ int attn_pack_bwd(const X2kAttnArgs& a, cudaStream_t stream) {
 }  // namespace x2k
 
 using namespace x2k;
+
+#ifdef X2K_PACK_TRACE
+extern "C" int x2k_debug_pack_trace(long long* out128) {
+  return cudaMemcpyFromSymbol(out128, g_pack_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int32_t x2k_attn_group_slots(int32_t Lq) { return pack_slots(Lq); }
 

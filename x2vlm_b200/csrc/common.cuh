@@ -31,6 +31,11 @@ EncodeTiledFn encode_tiled_fn();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// 3-D view [n_seq][seq_rows][cols] (box [1][box_rows][64], 128B swizzle): box rows past seq_rows are zero-filled by
+// loads and skipped by stores.
+int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows);
+
 // attn_pack.cu: packed short-sequence attention.  0 = launched, 1 = shape not eligible (use attn.cu), < 0 = error.
 int attn_pack_fwd(const X2kAttnArgs& a, cudaStream_t stream);
 int attn_pack_bwd(const X2kAttnArgs& a, cudaStream_t stream);
@@ -187,6 +192,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 3-D tiled load / store (coordinates: column, row inside the sequence, sequence)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (the CTA may exit / reuse it)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

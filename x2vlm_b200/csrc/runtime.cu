@@ -72,6 +72,36 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return X2K_OK;
 }
 
+// 3-D view [n_seq][seq_rows][cols] of a row-major matrix whose sequences are seq_rows consecutive rows: box =
+// [1][box_rows][64].  Rows of a box beyond seq_rows are out of bounds in dim 1: loads zero-fill them, stores skip
+// them — a tile may be taller than the sequence without touching its neighbour.
+int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return X2K_ERR_CUDA;
+  }
+  if (box_rows > 256 || box_rows == 0) {
+    set_error("make_tmap_seq3d: bad box rows %u", box_rows);
+    return X2K_ERR_ARG;
+  }
+  cuuint64_t gdim[3] = {cols, seq_rows, n_seq};
+  cuuint64_t gstride[2] = {ld * 2, seq_rows * ld * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d) failed: %d (n_seq=%llu rows=%llu cols=%llu ld=%llu box_rows=%u base=%p)", (int)r,
+              (unsigned long long)n_seq, (unsigned long long)seq_rows, (unsigned long long)cols, (unsigned long long)ld,
+              box_rows, base);
+    return X2K_ERR_CUDA;
+  }
+  return X2K_OK;
+}
+
 }  // namespace x2k
 
 extern "C" int x2k_version(void) { return X2K_VERSION; }

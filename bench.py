@@ -239,11 +239,33 @@ def run_ours(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    teardown(graphed, world)
+
+
+def teardown(graphed, world):
+    """Leave cleanly: NCCL's communicator destroy waits for every CUDA graph that captured one of its collectives to be
+    released first (persistent references), so the step graph goes before the process group; a watchdog bounds it."""
+    if graphed is not None:
+        graphed.release()
+    torch.cuda.synchronize()
+    if world > 1:
+        import threading
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            finally:
+                done.set()
+        t = threading.Thread(target=_destroy, daemon=True)
+        t.start()
+        if not done.wait(60.0):
+            sys.stderr.write("[bench] process-group teardown timed out; exiting\n")
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def dominant_kernel_roofline(step_fn, peak_sustained, src):

@@ -94,6 +94,74 @@ def main():
                     "cfg": dict(vocab_size=1024, hidden_size=128, num_hidden_layers=3, num_attention_heads=2,
                                 intermediate_size=512, max_position_embeddings=64, fusion_layer=2, encoder_width=128)},
                    os.path.join(OUT, "text_small.pt"))
+        # ---- generation paths: BertLMHeadModel (VQA answer decoder) and the captioning history_states loop ----
+        dcfg = rxbert.BertConfig(vocab_size=1024, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                 intermediate_size=512, max_position_embeddings=64, type_vocab_size=2, pad_token_id=0,
+                                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12)
+        dcfg.fusion_layer, dcfg.encoder_width, dcfg.embedding_dim = 0, 128, 128
+        torch.manual_seed(3)
+        dec = rxbert.BertLMHeadModel(dcfg, label_smoothing=0.0)
+        perturb(dec, 4)
+        dec.eval()
+        g = torch.Generator().manual_seed(11)
+        a_ids = torch.randint(5, 1024, (4, 9), generator=g)
+        a_atts = torch.ones(4, 9, dtype=torch.long)
+        a_atts[1, 6:] = 0
+        a_atts[3, 4:] = 0
+        targets = a_ids.masked_fill(a_atts == 0, -100)
+        q_states = torch.randn(4, 21, 128, generator=g)
+        q_atts = torch.ones(4, 21, dtype=torch.long)
+        q_atts[2, 15:] = 0
+        with torch.no_grad():
+            vqa = dec(a_ids, attention_mask=a_atts, encoder_hidden_states=q_states, encoder_attention_mask=q_atts,
+                      labels=targets, return_dict=True, reduction='none')
+            dec.label_smoothing = 0.1
+            vqa_ls = dec(a_ids, attention_mask=a_atts, encoder_hidden_states=q_states, encoder_attention_mask=q_atts,
+                         labels=targets, return_dict=True, reduction='mean')
+            dec.label_smoothing = 0.0
+            # HF-style cache: prompt of 5 tokens fills the cache, then two single-token steps
+            st0 = dec(a_ids[:, :5], encoder_hidden_states=q_states, encoder_attention_mask=q_atts, use_cache=True,
+                      return_dict=True)
+            st1 = dec(a_ids[:, 5:6], attention_mask=torch.ones(4, 6, dtype=torch.long), encoder_hidden_states=q_states,
+                      encoder_attention_mask=q_atts, past_key_values=st0.past_key_values, use_cache=True, return_dict=True)
+            st2 = dec(a_ids[:, 6:7], attention_mask=torch.ones(4, 7, dtype=torch.long), encoder_hidden_states=q_states,
+                      encoder_attention_mask=q_atts, past_key_values=st1.past_key_values, use_cache=True, return_dict=True)
+            full7 = dec(a_ids[:, :7], encoder_hidden_states=q_states, encoder_attention_mask=q_atts, use_cache=False,
+                        return_dict=True)
+            # captioning loop (model_generation.py:172-252, beam bookkeeping left out): [tokens..., MASK] with the
+            # cached layer INPUTS of the previous positions as history_states
+            Ltot = 12
+            tril = torch.tril(torch.ones(Ltot, Ltot, dtype=torch.long)).view(1, Ltot, Ltot).expand(4, Ltot, Ltot)
+            pos = torch.arange(Ltot).view(1, -1).expand(4, -1)
+            tt = torch.zeros(4, Ltot, dtype=torch.long)
+            img = torch.randn(4, 197, 128, generator=g)
+            iatt = torch.ones(4, 197, dtype=torch.long)
+            mask_tok = torch.full((4, 1), 103, dtype=torch.long)
+            curr, prev, next_pos = a_ids[:, :4], None, 4
+            hist_logits, hist_last = [], []
+            for step in range(3):
+                L = curr.shape[1]
+                start = next_pos - L
+                x_ids = torch.cat((curr, mask_tok), dim=1)
+                o = dec.bert(x_ids, attention_mask=tril[:, start:next_pos + 1, :next_pos + 1],
+                             token_type_ids=tt[:, start:next_pos + 1], position_ids=pos[:, start:next_pos + 1],
+                             encoder_hidden_states=img, encoder_attention_mask=iatt, output_hidden_states=True,
+                             history_states=prev, is_decoder=True, return_dict=True)
+                new = o.hidden_states
+                hist_last.append(new[-1][:, -1:, :].clone())
+                hist_logits.append(dec.cls(new[-1][:, -1:, :]).clone())
+                prev = [x[:, :-1, :] for x in new] if prev is None else \
+                    [torch.cat((h, x[:, :-1, :]), dim=1) for h, x in zip(prev, new)]
+                curr = a_ids[:, next_pos:next_pos + 1]
+                next_pos += 1
+        torch.save({"state_dict": {k: v.clone() for k, v in dec.state_dict().items()}, "a_ids": a_ids, "a_atts": a_atts,
+                    "targets": targets, "q_states": q_states, "q_atts": q_atts, "vqa_loss": vqa.loss, "vqa_logits": vqa.logits,
+                    "vqa_ls_loss": vqa_ls.loss, "st0_logits": st0.logits, "st1_logits": st1.logits, "st2_logits": st2.logits,
+                    "st1_k0": st1.past_key_values[0][0], "st1_v1": st1.past_key_values[1][1], "full7_logits": full7.logits,
+                    "img": img, "iatt": iatt, "hist_logits": torch.stack(hist_logits), "hist_last": torch.stack(hist_last),
+                    "cfg": dict(vocab_size=1024, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                intermediate_size=512, max_position_embeddings=64, fusion_layer=0, encoder_width=128)},
+                   os.path.join(OUT, "decoder_small.pt"))
     finally:
         os.chdir(cwd)
     for f in sorted(os.listdir(OUT)):

@@ -286,6 +286,103 @@ def bbox_loss(output_coord, target_bbox, is_image=None):
     return l1.sum() / n, giou.sum() / n
 
 
+
+# ------------------------------------------------------------------------------------------------
+# generation paths: causal decoder, HF-style key/value cache, captioning history_states
+# ------------------------------------------------------------------------------------------------
+def decoder_self_mask(attention_mask, Lq):
+    """get_extended_attention_mask with is_decoder=True (models/xbert.py:1013-1073): a 2-D key mask [B, Lk] is
+    combined with a causal mask over the last Lq positions (cached prefix positions are all visible); a 3-D mask
+    [B, Lq, Lk] is taken as is.  Returns the additive mask [B, 1, Lq, Lk]."""
+    if attention_mask.dim() == 3:
+        ext = attention_mask[:, None, :, :]
+    else:
+        B, Lk = attention_mask.shape
+        ids = torch.arange(Lq)
+        causal = (ids[None, None, :].repeat(B, Lq, 1) <= ids[None, :, None]).to(attention_mask.dtype)
+        if Lq < Lk:
+            causal = torch.cat([torch.ones(B, Lq, Lk - Lq, dtype=causal.dtype), causal], dim=-1)
+        ext = causal[:, None, :, :] * attention_mask[:, None, None, :]
+    return (1.0 - ext.float()) * -10000.0
+
+
+def bert_layer_cached(hidden, self_mask, sd, pfx, num_heads, enc_hidden=None, cross_mask=None, history=None, past=None):
+    """BertLayer with the key/value sources of the generation paths (models/xbert.py:349-359): keys/values from
+    cat(history, hidden) (history_states) or cat(past K/V, new K/V) (past_key_value).  Returns (out, (K, V))."""
+    B, L, C = hidden.shape
+    d = C // num_heads
+    a = pfx + "attention.self."
+
+    def split(t):
+        return t.reshape(t.shape[0], t.shape[1], num_heads, d).permute(0, 2, 1, 3)
+
+    q = split(F.linear(hidden, sd[a + "query.weight"], sd[a + "query.bias"]))
+    src = torch.cat((history, hidden), dim=1) if history is not None else hidden
+    k = split(F.linear(src, sd[a + "key.weight"], sd[a + "key.bias"]))
+    v = split(F.linear(src, sd[a + "value.weight"], sd[a + "value.bias"]))
+    if past is not None:
+        assert history is None
+        k, v = torch.cat([past[0], k], dim=2), torch.cat([past[1], v], dim=2)
+    probs = (q @ k.transpose(-1, -2) / math.sqrt(d) + self_mask).softmax(dim=-1)
+    ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, L, C)
+    x = bert_output_ln(ctx, hidden, sd, pfx + "attention.output.")
+    if enc_hidden is not None and (pfx + "crossattention.self.query.weight") in sd:
+        c2, _ = bert_attention_core(x, enc_hidden, cross_mask, sd, pfx + "crossattention.self.", num_heads)
+        x = bert_output_ln(c2, x, sd, pfx + "crossattention.output.")
+    inter = F.gelu(F.linear(x, sd[pfx + "intermediate.dense.weight"], sd[pfx + "intermediate.dense.bias"]))
+    return bert_output_ln(inter, x, sd, pfx + "output."), (k, v)
+
+
+def bert_decoder(sd, pfx, num_heads, num_layers, input_ids, attention_mask=None, enc_hidden=None, enc_mask=None,
+                 position_ids=None, past=None, history=None):
+    """BertModel.forward with is_decoder=True (models/xbert.py:1075-1220, eval): embeddings at positions offset by the
+    cache length, causal/3-D self mask, every layer through bert_layer_cached.
+    Returns (last hidden, presents per layer, hidden states incl. the embedding output)."""
+    B, L = input_ids.shape
+    n_past = past[0][0].shape[2] if past is not None else 0
+    if position_ids is None:
+        position_ids = torch.arange(n_past, n_past + L)[None].expand(B, -1)
+    e = pfx + "embeddings."
+    h = sd[e + "word_embeddings.weight"][input_ids] + sd[e + "token_type_embeddings.weight"][0] \
+        + sd[e + "position_embeddings.weight"][position_ids]
+    h = F.layer_norm(h, (h.shape[-1],), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], 1e-12)
+    if attention_mask is None:
+        attention_mask = torch.ones(B, L + n_past)
+    self_mask = decoder_self_mask(attention_mask, L)
+    cross_mask = None
+    if enc_hidden is not None:
+        cross_mask = extended_cross_mask(enc_mask if enc_mask is not None else torch.ones(enc_hidden.shape[:2]), h.dtype)
+    presents, hiddens = [], [h]
+    for i in range(num_layers):
+        h, kv = bert_layer_cached(h, self_mask, sd, "%sencoder.layer.%d." % (pfx, i), num_heads, enc_hidden, cross_mask,
+                                  history=history[i] if history is not None else None,
+                                  past=past[i] if past is not None else None)
+        presents.append(kv)
+        hiddens.append(h)
+    return h, presents, hiddens
+
+
+def lm_loss(logits, labels, label_smoothing=0.0, reduction="mean"):
+    """Shifted next-token loss of BertLMHeadModel (models/xbert.py:1369-1383) with LabelSmoothSoftmaxCEV1
+    (:1223-1263): smoothed target = (1-s) on the label, s/C elsewhere; ignore_index -100."""
+    B, L, V = logits.shape
+    lg = logits[:, :-1].reshape(-1, V)
+    lb = labels[:, 1:].reshape(-1)
+    if label_smoothing > 0:
+        logp = lg.float().log_softmax(dim=1)
+        ignore = lb.eq(-100)
+        t = torch.full_like(logp, label_smoothing / V)
+        t.scatter_(1, lb.masked_fill(ignore, 0)[:, None], 1.0 - label_smoothing)
+        loss = -(logp * t).sum(dim=1)
+        loss[ignore] = 0
+        if reduction == "mean":
+            return loss.sum() / ignore.eq(0).sum()
+        loss = loss.sum() if reduction == "sum" else loss
+    else:
+        loss = F.cross_entropy(lg, lb, reduction=reduction)
+    return loss.view(B, -1).sum(1) if reduction == "none" else loss
+
+
 class Shapes:
     """Model shape of a config (base: 12 vision blocks / 12 heads, 12 text + 6 fusion layers)."""
 

@@ -66,6 +66,6 @@ def test_bucketed_allreduce_nccl_2gpu():
     res = [q.get(timeout=600) for _ in procs]
     [p.join(60) for p in procs]
     for rank, err, same, n_buckets, first, nonzero in res:
-        assert nonzero and same
-        assert err < 1e-5, (rank, err)            # fp32 sum of two ranks, then x0.5: exact up to atomics order
-        assert n_buckets >= 15 and first > n_buckets // 2   # later parameters' buckets are reduced first (overlap)
+        assert nonzero and same, res
+        assert err < 1e-4, res                    # fp32 sum of two ranks, then x0.5: equal up to atomics / split-K order
+        assert n_buckets >= 15 and first > n_buckets // 2, res   # later parameters' buckets are reduced first (overlap)

@@ -61,3 +61,44 @@ def test_restate_text_matches_reference_golden():
     assert torch.allclose(t3, g["text3d"], atol=2e-5, rtol=1e-5)
     # index/argmax surface is bit-exact
     assert torch.equal(logits.argmax(-1), g["mlm_logits"].argmax(-1))
+
+
+def test_restate_decoder_matches_reference_golden():
+    """Generation paths (BertLMHeadModel: causal mask, labels/reduction/label smoothing, key/value cache; captioning
+    history_states loop) against the unmodified reference's outputs."""
+    g = torch.load(os.path.join(GOLD, "decoder_small.pt"))
+    sd, c = g["state_dict"], g["cfg"]
+    kw = dict(sd=sd, pfx="bert.", num_heads=c["num_attention_heads"], num_layers=c["num_hidden_layers"])
+    head = lambda h: restate.mlm_head(h, sd, "cls.predictions.")
+    h, _, _ = restate.bert_decoder(input_ids=g["a_ids"], attention_mask=g["a_atts"], enc_hidden=g["q_states"],
+                                   enc_mask=g["q_atts"], **kw)
+    logits = head(h)
+    assert torch.allclose(logits, g["vqa_logits"], atol=5e-5, rtol=1e-5)
+    assert torch.allclose(restate.lm_loss(logits, g["targets"], reduction="none"), g["vqa_loss"], atol=1e-4, rtol=1e-5)
+    assert abs(float(restate.lm_loss(logits, g["targets"], 0.1, "mean")) - float(g["vqa_ls_loss"])) < 1e-5
+    # cache: prompt, then two single-token steps == the uncached 7-token pass
+    h0, p0, _ = restate.bert_decoder(input_ids=g["a_ids"][:, :5], enc_hidden=g["q_states"], enc_mask=g["q_atts"], **kw)
+    h1, p1, _ = restate.bert_decoder(input_ids=g["a_ids"][:, 5:6], enc_hidden=g["q_states"], enc_mask=g["q_atts"], past=p0, **kw)
+    h2, _, _ = restate.bert_decoder(input_ids=g["a_ids"][:, 6:7], enc_hidden=g["q_states"], enc_mask=g["q_atts"], past=p1, **kw)
+    assert torch.allclose(head(h0), g["st0_logits"], atol=5e-5, rtol=1e-5)
+    assert torch.allclose(head(h1), g["st1_logits"], atol=5e-5, rtol=1e-5)
+    assert torch.allclose(head(h2), g["st2_logits"], atol=5e-5, rtol=1e-5)
+    assert torch.allclose(p1[0][0], g["st1_k0"], atol=2e-5) and torch.allclose(p1[1][1], g["st1_v1"], atol=2e-5)
+    assert torch.allclose(torch.cat((head(h0), head(h1), head(h2)), 1), g["full7_logits"], atol=1e-4, rtol=1e-5)
+    # captioning: history_states
+    Ltot = 12
+    tril = torch.tril(torch.ones(Ltot, Ltot, dtype=torch.long)).view(1, Ltot, Ltot).expand(4, Ltot, Ltot)
+    pos = torch.arange(Ltot).view(1, -1).expand(4, -1)
+    mask_tok = torch.full((4, 1), 103, dtype=torch.long)
+    curr, prev, next_pos = g["a_ids"][:, :4], None, 4
+    for step in range(3):
+        L = curr.shape[1]
+        start = next_pos - L
+        _, _, hs = restate.bert_decoder(input_ids=torch.cat((curr, mask_tok), 1), attention_mask=tril[:, start:next_pos + 1, :next_pos + 1],
+                                        position_ids=pos[:, start:next_pos + 1], enc_hidden=g["img"], enc_mask=g["iatt"],
+                                        history=prev, **kw)
+        assert torch.allclose(hs[-1][:, -1:], g["hist_last"][step], atol=2e-5, rtol=1e-5)
+        assert torch.allclose(head(hs[-1][:, -1:]), g["hist_logits"][step], atol=5e-5, rtol=1e-5)
+        prev = [x[:, :-1] for x in hs] if prev is None else [torch.cat((p, x[:, :-1]), 1) for p, x in zip(prev, hs)]
+        curr = g["a_ids"][:, next_pos:next_pos + 1]
+        next_pos += 1

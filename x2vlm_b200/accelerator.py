@@ -260,6 +260,13 @@ class GraphedStep:
             base.add_(self.dropout_offsets_per_step)
         self.replays = 0
 
+    def release(self):
+        """Destroy the captured graph (NCCL will not tear a communicator down while a graph still holds its kernels)."""
+        self.static_out = None
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+
     @staticmethod
     def _clone_tree(tree):
         if isinstance(tree, torch.Tensor):

@@ -750,13 +750,15 @@ attn_group_build_kernel(const int32_t* __restrict__ kv_index, int B, int n_kv, i
 }
 
 // threads per CTA / 128 = how many warps share a TMEM lane quadrant (each takes a column part of the rows).
+// Measured on B200 (gpurun_out s3_attn_ab): 2 parts win for the 40-token self-attention shapes (53 vs 60 us fwd, 121 vs
+// 132 us bwd at B=256) and tie for cross-attention, so 2 is the default.
 // Tuning override: X2K_PACK_PARTS_FWD / X2K_PACK_PARTS_BWD = 2 | 4 (read once).
 int pack_parts(bool backward) {
   static int cached[2] = {0, 0};
   int& c = cached[backward ? 1 : 0];
   if (c == 0) {
     const char* e = getenv(backward ? "X2K_PACK_PARTS_BWD" : "X2K_PACK_PARTS_FWD");
-    c = (e && atoi(e) == 2) ? 2 : 4;
+    c = (e && atoi(e) == 4) ? 4 : 2;
   }
   return c;
 }

@@ -547,3 +547,104 @@ def bert_layer(x, xb, layer, cfg, enc=None, encb=None):
     return _BertLayerFn.apply(x, xb, enc, encb, layer, cfg, b_qkv, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
                               b_qc, b_kvc, b_oc, lncw, lncb, layer.intermediate.dense.bias, layer.output.dense.bias,
                               layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, *weights)
+
+
+# ----------------------------------------------------------------------------------------------
+# BERT layer, generation paths (inference only): history_states / past_key_value / use_cache
+# ----------------------------------------------------------------------------------------------
+def _kv_rows(t, B, H):
+    """Cached keys/values in the reference layout [B, H, L, 64] -> token-major bf16 rows [B, L, H*64]."""
+    L = t.shape[2]
+    return t.permute(0, 2, 1, 3).reshape(B, L, H * t.shape[3]).to(torch.bfloat16)
+
+
+def _kv_heads(rows, B, H):
+    """token-major [B, L, H*64] -> reference cache layout [B, H, L, 64] (a view)."""
+    L = rows.shape[1]
+    return rows.view(B, L, H, -1).permute(0, 2, 1, 3)
+
+
+@torch.no_grad()
+def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=None):
+    """One BertLayer forward for the generation paths of models/xbert.py:322-415 (no autograd graph):
+
+    * `history` [B, Lh, D] — the layer's cached INPUT states (model_generation.py:180-188): keys/values are projected
+      from cat(history, x) while queries come from x only (xbert.py:349-353);
+    * `past_kv` (K, V) each [B, H, Lp, 64] — HF-style cache: new keys/values are appended (xbert.py:355-359).
+
+    cfg['self_mask'] covers all Lk = Lh|Lp + Lq keys.  Returns (y fp32 [B,Lq,D], (K, V) in the cache layout)."""
+    if history is not None and past_kv is not None:
+        raise ValueError("history_states and past_key_value are mutually exclusive (xbert.py:350)")
+    B, Lq, D = x.shape
+    M = B * Lq
+    dev = x.device
+    sh = layer._x2k
+    at, so = layer.attention.self, layer.attention.output
+    H = at.num_attention_heads
+    scale = 1.0 / math.sqrt(D // H)
+    eps = cfg["eps"]
+    w_qkv = sh["qkv"].get()
+    b_qkv = sh["bqkv"].get_f32() if sh["bqkv"].arena is not None else torch.cat((at.query.bias, at.key.bias, at.value.bias))
+    x2 = x.contiguous().view(M, D).float()
+    xb2 = ops.to_bf16(x2)
+    if history is not None:
+        Lh = history.shape[1]
+        xs = ops.to_bf16(torch.cat((history.float(), x.float()), dim=1).contiguous().view(B * (Lh + Lq), D))
+        q = _empty_bf16(M, D, dev=dev)
+        ops.gemm(xb2, w_qkv[:D], M, D, D, bias=b_qkv[:D], out_bf16=q)
+        kv = _empty_bf16(B * (Lh + Lq), 2 * D, dev=dev)
+        ops.gemm(xs, w_qkv[D:], B * (Lh + Lq), 2 * D, D, bias=b_qkv[D:], out_bf16=kv)
+        Lk = Lh + Lq
+        k_rows, v_rows = kv[:, :D], kv[:, D:]
+    else:
+        qkv = _empty_bf16(M, 3 * D, dev=dev)
+        ops.gemm(xb2, w_qkv, M, 3 * D, D, bias=b_qkv, out_bf16=qkv)
+        q = qkv[:, :D]
+        if past_kv is not None:
+            pk, pv = _kv_rows(past_kv[0], B, H), _kv_rows(past_kv[1], B, H)
+            Lk = pk.shape[1] + Lq
+            kv = torch.cat((torch.cat((pk, qkv.view(B, Lq, 3 * D)[:, :, D:2 * D]), dim=1),
+                            torch.cat((pv, qkv.view(B, Lq, 3 * D)[:, :, 2 * D:]), dim=1)), dim=2).view(B * Lk, 2 * D)
+            k_rows, v_rows = kv[:, :D], kv[:, D:]
+        else:
+            Lk = Lq
+            kv = qkv[:, D:]
+            k_rows, v_rows = qkv[:, D:2 * D], qkv[:, 2 * D:]
+    present = (_kv_heads(k_rows.reshape(B, Lk, D), B, H), _kv_heads(v_rows.reshape(B, Lk, D), B, H))
+    ctx1 = _empty_bf16(M, D, dev=dev)
+    lse1 = torch.empty(B, H, Lq, dtype=torch.float32, device=dev)
+    ops.attn_fwd(q, k_rows, v_rows, B, H, Lq, Lk, scale, ctx1, lse1, n_kv=B, mask=cfg["self_mask"],
+                 mask_per_query=cfg["self_mask_3d"])
+    s1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+    ops.gemm(ctx1, sh["o"].get(), M, D, D, bias=so.dense.bias, residual=x2, out_f32=s1)
+    x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
+    x1b = _empty_bf16(M, D, dev=dev)
+    ops.layernorm_fwd(s1, so.LayerNorm.weight, so.LayerNorm.bias, eps, y_bf16=x1b, y_f32=x1)
+    if enc is not None and layer.has_cross_attention:
+        ca, co = layer.crossattention.self, layer.crossattention.output
+        n_kv, Nk, Dv = enc.shape
+        enc2 = encb.view(n_kv * Nk, Dv) if encb is not None else ops.to_bf16(enc.contiguous().view(n_kv * Nk, Dv))
+        b_kvc = sh["bkvc"].get_f32() if sh["bkvc"].arena is not None else torch.cat((ca.key.bias, ca.value.bias))
+        qc = _empty_bf16(M, D, dev=dev)
+        ops.gemm(x1b, sh["qc"].get(), M, D, D, bias=ca.query.bias, out_bf16=qc)
+        kvc = _empty_bf16(n_kv * Nk, 2 * D, dev=dev)
+        ops.gemm(enc2, sh["kvc"].get(), n_kv * Nk, 2 * D, Dv, bias=b_kvc, out_bf16=kvc)
+        ctx2 = _empty_bf16(M, D, dev=dev)
+        lse2 = torch.empty(B, H, Lq, dtype=torch.float32, device=dev)
+        ops.attn_fwd(qc, kvc[:, :D], kvc[:, D:], B, H, Lq, Nk, scale, ctx2, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
+                     kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"])
+        s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.gemm(ctx2, sh["oc"].get(), M, D, D, bias=co.dense.bias, residual=x1, out_f32=s2)
+        xa = torch.empty(M, D, dtype=torch.float32, device=dev)
+        xab = _empty_bf16(M, D, dev=dev)
+        ops.layernorm_fwd(s2, co.LayerNorm.weight, co.LayerNorm.bias, eps, y_bf16=xab, y_f32=xa)
+    else:
+        xa, xab = x1, x1b
+    Di = sh["i"].total_rows
+    act = _empty_bf16(M, Di, dev=dev)
+    ops.gemm(xab, sh["i"].get(), M, Di, D, bias=layer.intermediate.dense.bias, act=ACT_GELU, out_bf16=act)
+    s3 = torch.empty(M, D, dtype=torch.float32, device=dev)
+    ops.gemm(act, sh["out"].get(), M, D, Di, bias=layer.output.dense.bias, residual=xa, out_f32=s3)
+    y = torch.empty(M, D, dtype=torch.float32, device=dev)
+    ops.layernorm_fwd(s3, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, eps, y_f32=y)
+    return y.view(B, Lq, D), present

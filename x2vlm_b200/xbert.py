@@ -13,8 +13,11 @@ One extension beyond the reference API: `encoder_kv_index` (int32 [B]) lets seve
 attend to the SAME image's keys/values — the image K/V projection of a fusion layer is then computed
 once per image instead of once per (text, image) pair.
 
-Out of this round's scope (raise NotImplementedError): decoder KV-cache generation
-(past_key_values / use_cache), history_states, head pruning / head_mask, output_attentions.
+Generation paths (`history_states` of the captioning beam search, model_generation.py:180-188; HF-style
+`past_key_values` / `use_cache` of `BertLMHeadModel`, xbert.py:355-359) run forward-only on the same
+kernels (x2vlm_b200.functional.bert_layer_decode) and refuse to record an autograd graph.
+
+Not built (raise NotImplementedError): head pruning / head_mask, output_attentions, split_lengths.
 """
 import math
 
@@ -23,7 +26,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 from transformers import BertConfig  # noqa: F401  (re-exported, models/xvlm.py:25 imports it from here)
 from transformers.modeling_outputs import (BaseModelOutputWithPastAndCrossAttentions,
-                                           BaseModelOutputWithPoolingAndCrossAttentions, MaskedLMOutput)
+                                           BaseModelOutputWithPoolingAndCrossAttentions, CausalLMOutputWithCrossAttentions,
+                                           MaskedLMOutput)
 
 from . import functional as XF
 from . import ops
@@ -163,17 +167,31 @@ class BertLayer(nn.Module):
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, past_key_value=None, output_attentions=False, split_lengths=None,
                 history_states=None):
-        """Reference-shaped entry point: extended additive masks in, tuple out."""
-        if head_mask is not None or past_key_value is not None or output_attentions or history_states is not None:
-            raise NotImplementedError("x2k BertLayer: head_mask / past_key_value / output_attentions / history_states")
-        cfg = _layer_cfg(self.config, self.training, attention_mask, encoder_attention_mask, None,
-                         hidden_states.shape[0], hidden_states.shape[1],
-                         encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0, hidden_states.device)
+        """Reference-shaped entry point: extended additive masks in, tuple out (layer output, present key/value)."""
+        if head_mask is not None or output_attentions or split_lengths:
+            raise NotImplementedError("x2k BertLayer: head_mask / output_attentions / split_lengths")
+        B, L = hidden_states.shape[:2]
+        decode = past_key_value is not None or history_states is not None
+        n_past = (past_key_value[0].shape[2] if past_key_value is not None else 0) + \
+                 (history_states.shape[1] if history_states is not None else 0)
+        cfg = _layer_cfg(self.config, self.training and not decode, attention_mask, encoder_attention_mask, None, B, L,
+                         encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0, hidden_states.device,
+                         Lk_self=L + n_past)
         if encoder_hidden_states is not None:
             cfg["n_kv"] = encoder_hidden_states.shape[0]
-            _group_cross(cfg, hidden_states.shape[0], hidden_states.shape[1], encoder_hidden_states.shape[1], hidden_states.device)
+            _group_cross(cfg, B, L, encoder_hidden_states.shape[1], hidden_states.device)
+        if decode:
+            _no_grad_only("past_key_value / history_states")
+            y, present = XF.bert_layer_decode(hidden_states, self, cfg, encoder_hidden_states,
+                                              history=history_states, past_kv=past_key_value[:2] if past_key_value else None)
+            return (y, present)
         y, _ = self.fused(hidden_states, None, cfg, encoder_hidden_states)
         return (y, None)
+
+
+def _no_grad_only(what):
+    if torch.is_grad_enabled():
+        raise NotImplementedError("x2k xbert: %s is a forward-only (generation) path; call it under torch.no_grad()" % what)
 
 
 def _pad_mask(ext_mask, B, Lq, Lk, device):
@@ -194,8 +212,8 @@ def _pad_mask(ext_mask, B, Lq, Lk, device):
     return (out if per_query else out[:, 0].contiguous()), per_query
 
 
-def _layer_cfg(config, training, ext_self_mask, ext_cross_mask, kv_index, B, L, Nk, device):
-    self_mask, self_3d = _pad_mask(ext_self_mask, B, L, L, device)
+def _layer_cfg(config, training, ext_self_mask, ext_cross_mask, kv_index, B, L, Nk, device, Lk_self=None):
+    self_mask, self_3d = _pad_mask(ext_self_mask, B, L, Lk_self if Lk_self is not None else L, device)
     cross_mask, cross_3d = _pad_mask(ext_cross_mask, B, L, Nk, device) if Nk else (None, False)
     if cross_3d:
         raise NotImplementedError("per-query cross-attention masks")
@@ -231,8 +249,8 @@ class BertEncoder(nn.Module):
                 encoder_attention_mask=None, past_key_values=None, use_cache=None, output_attentions=False,
                 output_hidden_states=False, return_dict=True, mode='multi_modal', split_lengths=None, history_states=None,
                 encoder_kv_index=None):
-        if output_attentions or use_cache or past_key_values is not None or history_states is not None or split_lengths:
-            raise NotImplementedError("x2k BertEncoder: output_attentions / use_cache / past_key_values / history_states")
+        if output_attentions or split_lengths:
+            raise NotImplementedError("x2k BertEncoder: output_attentions / split_lengths")
         if head_mask is not None and any(h is not None for h in head_mask):
             raise NotImplementedError("x2k BertEncoder: head_mask")
         if mode == 'text':
@@ -248,8 +266,15 @@ class BertEncoder(nn.Module):
         if isinstance(enc, list):
             raise ValueError("no this case since we do not use ALBEF-NLVR anymore")
         Nk = enc.shape[1] if enc is not None else 0
-        cfg = _layer_cfg(self.config, self.training, attention_mask, encoder_attention_mask, encoder_kv_index, B, L, Nk,
-                         hidden_states.device)
+        decode = bool(use_cache) or past_key_values is not None or history_states is not None
+        n_past = 0
+        if past_key_values is not None:
+            n_past = past_key_values[start_layer][0].shape[2]
+        elif history_states is not None:
+            assert isinstance(history_states, list) and len(history_states) == (output_layer - start_layer + 1)
+            n_past = history_states[0].shape[1]
+        cfg = _layer_cfg(self.config, self.training and not decode, attention_mask, encoder_attention_mask, encoder_kv_index,
+                         B, L, Nk, hidden_states.device, Lk_self=L + n_past)
         encb = None
         if enc is not None:
             enc = enc.float().contiguous()
@@ -260,16 +285,27 @@ class BertEncoder(nn.Module):
             if output_layer > self.config.fusion_layer:
                 encb = ops.to_bf16(enc)  # one bf16 copy feeds the K/V projection of every fusion layer
         all_hidden_states = () if output_hidden_states else None
+        next_decoder_cache = () if use_cache else None
         x, xb = hidden_states.float().contiguous(), None
+        if decode:
+            _no_grad_only("use_cache / past_key_values / history_states")
         for i in range(start_layer, output_layer):
             if output_hidden_states:
                 all_hidden_states = all_hidden_states + (x,)
-            x, xb = self.layer[i].fused(x, xb, cfg, enc, encb)
+            if decode:
+                x, present = XF.bert_layer_decode(
+                    x, self.layer[i], cfg, enc, encb,
+                    history=history_states[i - start_layer] if history_states is not None else None,
+                    past_kv=past_key_values[i][:2] if past_key_values is not None else None)
+                if use_cache:
+                    next_decoder_cache += (present,)
+            else:
+                x, xb = self.layer[i].fused(x, xb, cfg, enc, encb)
         if output_hidden_states:
             all_hidden_states = all_hidden_states + (x,)
         if not return_dict:
-            return tuple(v for v in [x, all_hidden_states] if v is not None)
-        return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=x, past_key_values=None,
+            return tuple(v for v in [x, next_decoder_cache, all_hidden_states] if v is not None)
+        return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=x, past_key_values=next_decoder_cache,
                                                          hidden_states=all_hidden_states, attentions=None,
                                                          cross_attentions=None)
 
@@ -435,8 +471,12 @@ class BertModel(BertPreTrainedModel):
         output_attentions = output_attentions if output_attentions is not None else getattr(self.config, "output_attentions", False)
         output_hidden_states = output_hidden_states if output_hidden_states is not None else getattr(self.config, "output_hidden_states", False)
         return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
-        if past_key_values is not None or use_cache or history_states is not None:
-            raise NotImplementedError("x2k BertModel: past_key_values / use_cache / history_states (generation) — next round")
+        if is_decoder:
+            use_cache = use_cache if use_cache is not None else getattr(self.config, "use_cache", True)
+            if use_cache and torch.is_grad_enabled():
+                use_cache = False  # the cache is a forward-only product; training never reads it (xbert.py:1349-1350)
+        else:
+            use_cache = False
         if input_ids is not None and inputs_embeds is not None:
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         elif input_ids is not None:
@@ -448,8 +488,9 @@ class BertModel(BertPreTrainedModel):
         else:
             raise ValueError("You have to specify either input_ids or inputs_embeds or encoder_embeds")
         batch_size, seq_length = input_shape
+        past_key_values_length = past_key_values[0][0].shape[2] if past_key_values is not None else 0
         if attention_mask is None:
-            attention_mask = torch.ones((batch_size, seq_length), device=device)
+            attention_mask = torch.ones((batch_size, seq_length + past_key_values_length), device=device)
         if token_type_ids is None:
             token_type_ids = torch.zeros(input_shape, dtype=torch.long, device=device)
         extended_attention_mask = self.get_extended_attention_mask(attention_mask, input_shape, device, is_decoder)
@@ -465,21 +506,135 @@ class BertModel(BertPreTrainedModel):
         head_mask = self.get_head_mask(head_mask, self.config.num_hidden_layers)
         if encoder_embeds is None:
             embedding_output = self.embeddings(input_ids=input_ids, position_ids=position_ids, token_type_ids=token_type_ids,
-                                               inputs_embeds=inputs_embeds, past_key_values_length=0)
+                                               inputs_embeds=inputs_embeds, past_key_values_length=past_key_values_length)
         else:
             embedding_output = encoder_embeds
         encoder_outputs = self.encoder(embedding_output, attention_mask=extended_attention_mask, head_mask=head_mask,
                                        encoder_hidden_states=encoder_hidden_states,
                                        encoder_attention_mask=encoder_extended_attention_mask,
+                                       past_key_values=past_key_values, history_states=history_states, use_cache=use_cache,
                                        output_attentions=output_attentions, output_hidden_states=output_hidden_states,
-                                       return_dict=return_dict, mode=mode, encoder_kv_index=encoder_kv_index)
+                                       return_dict=return_dict, mode=mode, split_lengths=split_lengths,
+                                       encoder_kv_index=encoder_kv_index)
         sequence_output = encoder_outputs[0]
         pooled_output = self.pooler(sequence_output) if self.pooler is not None else None
         if not return_dict:
             return (sequence_output, pooled_output) + encoder_outputs[1:]
         return BaseModelOutputWithPoolingAndCrossAttentions(
-            last_hidden_state=sequence_output, pooler_output=pooled_output, past_key_values=None,
+            last_hidden_state=sequence_output, pooler_output=pooled_output, past_key_values=encoder_outputs.past_key_values,
             hidden_states=encoder_outputs.hidden_states, attentions=None, cross_attentions=None)
+
+
+class LabelSmoothSoftmaxCEV1(nn.Module):
+    """Label-smoothed cross entropy with ignore_index (models/xbert.py:1223-1263): target distribution
+    (1 - s) on the label and s / C on every class; ignored rows contribute 0 and are excluded from the mean."""
+
+    def __init__(self, lb_smooth=0.1, reduction='mean', ignore_index=-100):
+        super().__init__()
+        self.lb_smooth, self.reduction, self.lb_ignore = lb_smooth, reduction, ignore_index
+
+    def forward(self, logits, label):
+        logs = F.log_softmax(logits.float(), dim=1)
+        ignore = label.eq(self.lb_ignore)
+        safe = label.masked_fill(ignore, 0)
+        n_cls = logits.size(1)
+        lb_pos, lb_neg = 1.0 - self.lb_smooth, self.lb_smooth / n_cls
+        # -sum_c t_c * logp_c with t = lb_neg everywhere, lb_pos on the label (which overwrites, not adds to, lb_neg)
+        loss = -(lb_neg * logs.sum(dim=1) + (lb_pos - lb_neg) * logs.gather(1, safe.unsqueeze(1)).squeeze(1))
+        loss = loss.masked_fill(ignore, 0.0)
+        if self.reduction == 'mean':
+            return loss.sum() / ignore.eq(0).sum()
+        if self.reduction == 'sum':
+            return loss.sum()
+        return loss
+
+
+class BertLMHeadModel(BertPreTrainedModel):
+    """BERT decoder with the LM head (models/xbert.py:1268-1413): VQA answer decoder and captioning language model
+    (models/model_generation.py:443,647).  Causal masking comes from `is_decoder=True`; `labels` give the shifted
+    next-token loss with optional label smoothing and `reduction='none'` (per-sequence sums)."""
+
+    def __init__(self, config, label_smoothing=0.0):
+        super().__init__(config)
+        self.bert = BertModel(config, add_pooling_layer=False)
+        self.cls = BertOnlyMLMHead(config)
+        self.label_smoothing = label_smoothing
+        self.init_weights()
+        self.bert.embeddings.word_embeddings.weight._x2k_autograd_too = True  # embedding lookup + tied decoder GEMM
+
+    def get_input_embeddings(self):
+        return self.bert.embeddings.word_embeddings
+
+    def get_output_embeddings(self):
+        return self.cls.predictions.decoder
+
+    def set_output_embeddings(self, new_embeddings):
+        self.cls.predictions.decoder = new_embeddings
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
+                inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, labels=None,
+                past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                is_decoder=True, reduction='mean', mode='multi_modal', return_logits=False):
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        if labels is not None:
+            use_cache = False
+        outputs = self.bert(input_ids, attention_mask=attention_mask, token_type_ids=token_type_ids, position_ids=position_ids,
+                            head_mask=head_mask, inputs_embeds=inputs_embeds, encoder_hidden_states=encoder_hidden_states,
+                            encoder_attention_mask=encoder_attention_mask, past_key_values=past_key_values,
+                            use_cache=use_cache, output_attentions=output_attentions,
+                            output_hidden_states=output_hidden_states, return_dict=return_dict, is_decoder=is_decoder, mode=mode)
+        sequence_output = outputs[0]
+        prediction_scores = self.cls(sequence_output)
+        if return_logits:
+            return prediction_scores[:, :-1, :].contiguous()
+        lm_loss = None
+        if labels is not None:
+            shifted = prediction_scores[:, :-1, :].contiguous()
+            labels = labels[:, 1:].contiguous()
+            if self.label_smoothing > 0:
+                loss_fct = LabelSmoothSoftmaxCEV1(lb_smooth=self.label_smoothing, reduction=reduction)
+            else:
+                loss_fct = nn.CrossEntropyLoss(reduction=reduction)
+            lm_loss = loss_fct(shifted.view(-1, self.config.vocab_size), labels.view(-1))
+            if reduction == 'none':
+                lm_loss = lm_loss.view(prediction_scores.size(0), -1).sum(1)
+        if not return_dict:
+            output = (prediction_scores,) + outputs[2:]
+            return ((lm_loss,) + output) if lm_loss is not None else output
+        return CausalLMOutputWithCrossAttentions(loss=lm_loss, logits=prediction_scores, past_key_values=outputs.past_key_values,
+                                                 hidden_states=outputs.hidden_states, attentions=None, cross_attentions=None)
+
+    def prepare_inputs_for_generation(self, input_ids, past=None, attention_mask=None, **model_kwargs):
+        """Cut the prompt to its last token once a cache exists (models/xbert.py:1390-1407)."""
+        if attention_mask is None:
+            attention_mask = input_ids.new_ones(input_ids.shape)
+        if past is not None:
+            input_ids = input_ids[:, -1:]
+        return {"input_ids": input_ids, "attention_mask": attention_mask, "past_key_values": past,
+                "encoder_hidden_states": model_kwargs.get("encoder_hidden_states", None),
+                "encoder_attention_mask": model_kwargs.get("encoder_attention_mask", None), "is_decoder": True}
+
+    def _reorder_cache(self, past, beam_idx):
+        return tuple(tuple(t.index_select(0, beam_idx) for t in layer_past) for layer_past in past)
+
+    @torch.no_grad()
+    def greedy_decode(self, input_ids, max_length, eos_token_id=None, pad_token_id=0, **model_kwargs):
+        """Cached greedy decoding (the num_beams == 1, do_sample == False case of the reference's generate loop,
+        models/xbert.py:1415-1490): one prompt pass that fills the cache, then one token per step."""
+        past, cur = None, input_ids
+        unfinished = torch.ones(input_ids.shape[0], dtype=torch.long, device=input_ids.device)
+        while cur.shape[1] < max_length:
+            inp = self.prepare_inputs_for_generation(cur, past=past, **model_kwargs)
+            out = self(**inp, use_cache=True, return_dict=True)
+            past = out.past_key_values
+            nxt = out.logits[:, -1, :].argmax(dim=-1)
+            if eos_token_id is not None:
+                nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
+                unfinished = unfinished * nxt.ne(eos_token_id).long()
+            cur = torch.cat([cur, nxt[:, None]], dim=1)
+            if eos_token_id is not None and unfinished.max() == 0:
+                break
+        return cur
 
 
 class BertForMaskedLM(BertPreTrainedModel):

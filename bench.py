@@ -210,7 +210,8 @@ def run_ours(args):
     burst, sustained, hbm, src = peaks()
     step_tflops = flop_step_gpu * args.steps / (ms / 1e3) / 1e12  # per GPU (ms is the max over ranks)
 
-    roof = dominant_kernel_roofline(lambda: eager_step(ib_d, rb_d, False), sustained, src)  # every rank steps (collectives)
+    roof = dominant_kernel_roofline(lambda: eager_step(ib_d, rb_d, False), sustained, src,  # every rank steps (collectives)
+                                    table_path=args.kernel_table if rank == 0 else None)
     out = None
     if rank == 0:
         sys.stderr.write("[bench] timed: %.2f ms/step resident (host enqueue %.2f ms/step), %.2f ms/step e2e\n"
@@ -268,7 +269,7 @@ def teardown(graphed, world):
         os._exit(0)
 
 
-def dominant_kernel_roofline(step_fn, peak_sustained, src):
+def dominant_kernel_roofline(step_fn, peak_sustained, src, table_path=None):
     """The dominant kernel is the tcgen05 GEMM (x2k gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel: ~47% of the
     step's GPU time in profiles/).  One extra, instrumented step after the timed region brackets EVERY GEMM and
     attention launch with CUDA events on the launching stream; achieved = sum of algorithmic flops (2MNK per
@@ -278,6 +279,12 @@ def dominant_kernel_roofline(step_fn, peak_sustained, src):
     with ops.kernel_timing() as kt:
         step_fn()
     tot = kt.totals()
+    if table_path:  # per-shape table (markdown) for profiles/: which GEMM shapes / epilogues sit below the average
+        rows = sorted(kt.by_shape().items(), key=lambda kv: -kv[1][2])
+        with open(table_path, "w") as fh:
+            fh.write("| family | shape / epilogue | launches | ms / step | avg us | TFLOP/s |\n|---|---|---:|---:|---:|---:|\n")
+            for (fam, tag), (cnt, fl, t) in rows:
+                fh.write("| %s | %s | %d | %.3f | %.1f | %.0f |\n" % (fam, tag, cnt, t, t / cnt * 1e3, fl / (t / 1e3) / 1e12))
     n, flops, ms = tot["gemm"]
     tf = flops / (ms / 1e3) / 1e12
     other = {k: {"launches": v[0], "ms_per_step": v[2], "tflops": v[1] / (v[2] / 1e3) / 1e12,
@@ -395,6 +402,7 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=48.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--kernel-table", default=None, help="write the per-shape GEMM / attention timing table (markdown) here")
     ap.add_argument("--profile", action="store_true", help="one step inside cudaProfilerStart/Stop, no JSON (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

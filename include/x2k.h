@@ -53,6 +53,9 @@ int64_t x2k_launch_count(void);
  *   if preact_out:  preact_out[m,n] = bf16(v)            (saved for GELU backward)
  *   if act == X2K_ACT_GELU:       v = gelu_erf(v)
  *   if act == X2K_ACT_GELU_BWD:   v = v * gelu_erf'(aux[m,n])   (aux = saved pre-activation)
+ *   if act == X2K_ACT_GELU_SAVE_GRAD:  preact_out[m,n] = bf16(gelu_erf'(v)) INSTEAD of bf16(v), then v = gelu_erf(v)
+ *                                 (needs preact_out; the derivative is evaluated once, next to the activation)
+ *   if act == X2K_ACT_MUL_AUX:    v = v * aux[m,n]              (aux = derivative saved by GELU_SAVE_GRAD)
  *   if dropout_p > 0:  v = keep(e) ? v*s : 0,  e = m*N+n     (16 random bits per element from
  *                      Philox4x32-7(key = seed, counter = offset + e/8): word (e%8)/2, low half for
  *                      even e; keep iff bits >= thr = round(p*65536); s = 65536/(65536-thr))
@@ -70,6 +73,8 @@ int64_t x2k_launch_count(void);
 #define X2K_ACT_NONE 0
 #define X2K_ACT_GELU 1
 #define X2K_ACT_GELU_BWD 2
+#define X2K_ACT_GELU_SAVE_GRAD 3
+#define X2K_ACT_MUL_AUX 4
 
 typedef struct X2kGemmArgs {
   const void* A; /* bf16 */
@@ -80,7 +85,7 @@ typedef struct X2kGemmArgs {
   /* epilogue */
   const float* bias;       /* [N] or NULL */
   int32_t act;             /* X2K_ACT_* */
-  const void* aux;         /* bf16 [M, ld_aux], for X2K_ACT_GELU_BWD */
+  const void* aux;         /* bf16 [M, ld_aux], for X2K_ACT_GELU_BWD / X2K_ACT_MUL_AUX */
   int64_t ld_aux;
   void* preact_out;        /* bf16 [M, ld_preact] or NULL */
   int64_t ld_preact;

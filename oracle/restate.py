@@ -439,3 +439,40 @@ def pretrain_forward(sd, shp, image, text_ids, text_atts, text_ids_masked, maske
         out.update(image_embeds=image_embeds, text_embeds=text_embeds, image_feat=image_feat, text_feat=text_feat,
                    cross_pos=cross_pos, cross_neg=cross_neg, itm_logits=itm_logits, mlm_logits=mlm_logits)
     return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# retrieval scoring (Retrieval.py:71-157) and video input (models/xvlm.py:615-661)
+# ------------------------------------------------------------------------------------------------
+def video_forward(frames, sd, shp, frame_pos=None):
+    """video_encoding == 'avgpool': frames [B, F, 3, H, W] -> every frame through the vision encoder, + per-frame
+    offset, mean over F (models/xvlm.py:615-645).  Returns [B, 197, D]."""
+    B, n_f = frames.shape[:2]
+    emb = vision_forward(frames.reshape(B * n_f, *frames.shape[2:]), sd, "vision_encoder.", shp.vision_depth, shp.vision_heads)
+    emb = emb.view(B, n_f, emb.shape[1], emb.shape[2])
+    if frame_pos is not None:
+        emb = emb + frame_pos
+    return emb.mean(dim=1)
+
+
+def retrieval_scores(sd, shp, image_embeds, text_embeds, text_atts, sims_matrix, k_test, topk_i2t=None, topk_t2i=None):
+    """The two re-ranking loops of Retrieval.py:118-151, one fusion call of k_test sequences per image / caption.
+    `topk_*` override the candidate lists (to score exactly the pairs another implementation picked)."""
+    bert = dict(sd=sd, pfx="text_encoder.bert.", num_heads=shp.text_heads, fusion_layer=shp.fusion_layer,
+                num_layers=shp.num_layers)
+    n_img, n_txt = sims_matrix.shape
+    s_i2t = torch.full((n_img, n_txt), -100.0)
+    s_t2i = torch.full((n_txt, n_img), -100.0)
+    for i in range(n_img):
+        idx = topk_i2t[i] if topk_i2t is not None else sims_matrix[i].topk(k=min(k_test, n_txt), dim=0).indices
+        enc = image_embeds[i].repeat(len(idx), 1, 1)
+        out = bert_model(encoder_embeds=text_embeds[idx], attention_mask=text_atts[idx], enc_hidden=enc,
+                         enc_mask=torch.ones(enc.shape[:2], dtype=torch.long), mode="fusion", **bert)
+        s_i2t[i, idx] = mlp_head(out[:, 0], sd, "itm_head.")[:, 1]
+    for j in range(n_txt):
+        idx = topk_t2i[j] if topk_t2i is not None else sims_matrix[:, j].topk(k=min(k_test, n_img), dim=0).indices
+        enc = image_embeds[idx]
+        out = bert_model(encoder_embeds=text_embeds[j].repeat(len(idx), 1, 1), attention_mask=text_atts[j].repeat(len(idx), 1),
+                         enc_hidden=enc, enc_mask=torch.ones(enc.shape[:2], dtype=torch.long), mode="fusion", **bert)
+        s_t2i[j, idx] = mlp_head(out[:, 0], sd, "itm_head.")[:, 1]
+    return s_i2t, s_t2i

@@ -55,7 +55,7 @@ def test_gemm_split_k_wgrad(dev):
 
 def test_gemm_epilogues(dev):
     from x2vlm_b200 import ops
-    from x2vlm_b200._capi import ACT_GELU, ACT_GELU_BWD
+    from x2vlm_b200._capi import ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX
     from oracle import philox
     M, N, K = 394, 768, 768
     g = torch.Generator(device=dev).manual_seed(0)
@@ -75,6 +75,21 @@ def test_gemm_epilogues(dev):
     ops.gemm(A, W, M, N, K, act=ACT_GELU_BWD, aux=h, out_bf16=o)
     hf = h.float().requires_grad_(True); torch.nn.functional.gelu(hf).sum().backward()
     assert (o.float() - acc * hf.grad).abs().max() < 0.02 * (acc * hf.grad).abs().max()
+    # the hot-path pair: forward stores GELU'(pre) next to GELU(pre), backward multiplies by the stored derivative
+    dg = torch.empty_like(o)
+    ops.gemm(A, W, M, N, K, bias=bias, act=ACT_GELU_SAVE_GRAD, preact_out=dg, out_bf16=o)
+    xf = (acc + bias).clone().requires_grad_(True); torch.nn.functional.gelu(xf).sum().backward()
+    assert (o.float() - torch.nn.functional.gelu(acc + bias)).abs().max() < 0.04
+    assert (dg.float() - xf.grad).abs().max() < 6e-3          # |GELU'| <= 1.13: half a bf16 ulp is 3.9e-3
+    o2 = torch.empty_like(o)
+    ops.gemm(A, W, M, N, K, act=ACT_MUL_AUX, aux=h, out_bf16=o2)
+    assert (o2.float() - acc * h.float()).abs().max() < 0.01 * (acc * h.float()).abs().max()
+    # fp32 accuracy of the GELU formulas themselves (large-|x| tails included), through an fp32 output
+    xs = torch.linspace(-9, 9, M * N, device=dev).view(M, N)
+    eye_a = torch.zeros(M, K, device=dev); eye_w = torch.zeros(N, K, device=dev)   # acc == 0, bias carries x per column only
+    xs_col = torch.linspace(-9, 9, N, device=dev)
+    ops.gemm(_bf(eye_a), _bf(eye_w), M, N, K, bias=xs_col, act=ACT_GELU, out_f32=o32)
+    assert (o32[0] - torch.nn.functional.gelu(xs_col.double()).float()).abs().max() < 2e-6
     o32b = o32.clone()
     ops.gemm(A, W, M, N, K, accumulate=True, out_f32=o32b)
     assert (o32b - (o32 + acc)).abs().max() < 1e-4 * o32.abs().max()

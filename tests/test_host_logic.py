@@ -163,3 +163,37 @@ def test_flat_adamw_groups(xvlm):
     names = {id(p): n for n, p in m.named_parameters()}
     assert all(("bias" in names[id(p)] or "LayerNorm" in names[id(p)]) for p in nd)
     assert int(opt.seg_end[-1]) == arena.numel
+
+
+def test_retrieval_recall_bookkeeping():
+    """itm_eval (Retrieval.py:160-209) on a hand-checked case: ranks of the best ground-truth caption / the image."""
+    from x2vlm_b200 import retrieval
+    s_i2t = torch.tensor([[0.9, 0.1, 0.3, -100.0], [0.2, 0.8, -100.0, 0.7]])      # 2 images x 4 captions
+    s_t2i = torch.tensor([[0.9, 0.1], [0.3, 0.6], [0.8, 0.2], [0.9, 0.1]])        # caption 3 ranks its image second
+    r = retrieval.itm_eval(s_i2t, s_t2i, txt2img={0: 0, 1: 1, 2: 0, 3: 1}, img2txt={0: [0, 2], 1: [1, 3]})
+    assert r["txt_r1"] == 100.0 and r["img_r1"] == 75.0 and r["img_r5"] == 100.0
+    assert abs(r["r_mean"] - (100.0 + (75.0 + 100.0 + 100.0) / 3) / 2) < 1e-9
+    assert retrieval._rank_slice(1000) == (0, 1000, 1)   # single process: all rows
+
+
+def test_generation_surface_on_cpu():
+    """BertLMHeadModel constructs with the reference's state_dict keys; label-smoothed CE equals its definition."""
+    from x2vlm_b200 import xbert
+    cfg = xbert.BertConfig(vocab_size=64, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                           max_position_embeddings=32)
+    cfg.fusion_layer, cfg.encoder_width = 0, 128
+    m = xbert.BertLMHeadModel(cfg, label_smoothing=0.1)
+    keys = set(m.state_dict().keys())
+    assert "bert.encoder.layer.1.crossattention.self.key.weight" in keys and "cls.predictions.decoder.weight" in keys
+    assert m.cls.predictions.decoder.weight is m.bert.embeddings.word_embeddings.weight      # tied
+    g = torch.Generator().manual_seed(0)
+    logits, labels = torch.randn(7, 64, generator=g), torch.tensor([3, -100, 5, 0, 63, -100, 9])
+    got = xbert.LabelSmoothSoftmaxCEV1(0.1, "mean")(logits, labels)
+    logp = logits.log_softmax(1)
+    t = torch.full_like(logp, 0.1 / 64)
+    valid = labels != -100
+    t[valid, labels[valid]] = 0.9
+    want = -(logp * t).sum(1)[valid].sum() / valid.sum()
+    assert abs(float(got) - float(want)) < 1e-6
+    out = m.prepare_inputs_for_generation(torch.ones(2, 5, dtype=torch.long), past=((None,),))
+    assert out["input_ids"].shape == (2, 1) and out["is_decoder"] is True

@@ -11,6 +11,12 @@ WANT = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg",
     "sm__cycles_elapsed.max", "gpc__cycles_elapsed.avg.per_second", "sm__cycles_active.avg",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sectors_op_read.sum",
+    "lts__t_sectors_op_write.sum", "lts__t_sectors_srcunit_tex.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_bytes.sum", "sm__inst_executed.sum", "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+    "launch__local_mem_per_thread" ,
 ]
 
 

@@ -65,7 +65,7 @@ class X2kAttnArgs(ctypes.Structure):
     ]
 
 
-ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX = 0, 1, 2, 3, 4
 
 # every symbol include/x2k.h declares: name -> (restype, argtypes)
 SYMBOLS = {

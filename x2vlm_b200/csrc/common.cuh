@@ -309,32 +309,43 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 
 // ---- numerics ----
 // Exact (erf) GELU and its derivative, models/beit2.py:62 / models/xbert.py:498 (nn.GELU / ACT2FN["gelu"]).
-// erfc(|u|) = (a1 t + ... + a5 t^5) e^{-u^2}, t = 1/(1 + p|u|)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7), evaluated
-// with one MUFU.EX2 and one MUFU.RCP: measured max abs error vs float64 erf: 4.2e-7 (GELU), 3.0e-7 (GELU') on [-12, 12]
-// — three orders of magnitude below the bf16 rounding of the stored result.  (erff() costs ~2x the instructions and
-// made the epilogue, not the MMA, the limiter of the fc1 / fc2-dgrad GEMMs.)
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float u = x * 0.70710678118654752f;
-  const float au = fabsf(u);
+// With h(x) = 0.5 erfc(|x| / sqrt 2) = (a1 t + ... + a5 t^5) e^{-x^2/2} / 2, t = 1 / (1 + p |x| / sqrt 2)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7; the 1/2 and the 1/sqrt 2 are folded into the constants):
+//   Phi(x)   = x >= 0 ? 1 - h : h            GELU(x) = x Phi(x) = max(x, 0) - |x| h
+//   GELU'(x) = Phi(x) + x phi(x),  phi(x) = e^{-x^2/2} / sqrt(2 pi)
+// One MUFU.RCP + one MUFU.EX2 and 11 FMA-pipe instructions per GELU: the epilogue warps of the K = 768 GEMMs are
+// issue-bound, so every instruction here is on the critical path of fc1 (erff() costs ~2x as many).
+__device__ __forceinline__ void gelu_parts(float x, float& h, float& e) {
+  const float ax = fabsf(x);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, au, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(au * au) * 1.4426950408889634f));  // e^{-u^2} = e^{-x^2/2}
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float half_erfc = 0.5f * poly * t * e;  // 0.5 * erfc(|u|)
-  cdf = u >= 0.f ? 1.0f - half_erfc : half_erfc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * -0.72134752f));  // e^{-x^2/2}
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  h = (poly * t) * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+  float h, e;
+  gelu_parts(x, h, e);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ float gelu_grad_from_parts(float x, float h, float e) {
+  const float cdf = 0.5f + copysignf(0.5f - h, x);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+  float h, e;
+  gelu_parts(x, h, e);
+  return gelu_grad_from_parts(x, h, e);
+}
+// GELU and GELU' of the same argument (the forward fc1 epilogue stores GELU' for the backward pass)
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& dg) {
+  float h, e;
+  gelu_parts(x, h, e);
+  g = fmaf(-fabsf(x), h, fmaxf(x, 0.0f));
+  dg = gelu_grad_from_parts(x, h, e);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

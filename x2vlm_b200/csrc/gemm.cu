@@ -72,7 +72,8 @@ struct Cfg {
 };
 
 
-// Apply the fused epilogue to 32 consecutive columns [n0, n0+32) of row m.
+// Apply the fused epilogue to 32 consecutive columns [n0, n0+32) of row m (thread-per-row global accesses: only the
+// ragged last chunk of an N % 32 != 0 output — the vocabulary GEMM — comes here).
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0, uint32_t (&acc)[32]) {
   float v[32];
 #pragma unroll
@@ -91,7 +92,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
         if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
     }
   }
-  if (p.preact_out) {
+  if (p.act == X2K_ACT_GELU_SAVE_GRAD) {  // preact_out receives GELU'(v), v becomes GELU(v)
+    __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float g, dg;
+      gelu_erf_both(v[j], g, dg);
+      v[j] = g;
+      if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(dg);
+    }
+  } else if (p.preact_out) {
     __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
     if (full) {
 #pragma unroll
@@ -110,6 +120,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
   if (p.act == X2K_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == X2K_ACT_MUL_AUX) {
+    const __nv_bfloat16* src = p.aux + static_cast<int64_t>(m) * p.ld_aux + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < p.N) v[j] *= __bfloat162float(src[j]);
   } else if (p.act == X2K_ACT_GELU_BWD) {
     const __nv_bfloat16* src = p.aux + static_cast<int64_t>(m) * p.ld_aux + n0;
     if (full) {
@@ -288,7 +303,8 @@ __device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&w)[16]) 
 // slots on the critical path of a K = 768 tile) plus a generic variant that tests the runtime pointers.
 enum : int {
   EF_BIAS = 1, EF_PREACT = 2, EF_GELU = 4, EF_GELU_BWD = 8, EF_DROPOUT = 16, EF_SCALE = 32 /*gamma and/or row_scale*/,
-  EF_RESIDUAL = 64, EF_OUT_F32 = 128, EF_OUT_BF16 = 256, EF_GENERIC = 1 << 20
+  EF_RESIDUAL = 64, EF_OUT_F32 = 128, EF_OUT_BF16 = 256, EF_GELU_SAVE = 512 /*GELU + stored GELU'*/, EF_MUL_AUX = 1024,
+  EF_GENERIC = 1 << 20
 };
 template <int EPI, int F>
 __device__ __forceinline__ bool has(bool runtime) {
@@ -313,7 +329,26 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (has<EPI, EF_PREACT>(p.preact_out != nullptr)) {
+  if (has<EPI, EF_GELU_SAVE>(p.act == X2K_ACT_GELU_SAVE_GRAD)) {
+    // staged over 16 elements at a time (all reciprocals, all exponentials, then the polynomials): 16 independent
+    // MUFU -> FMA chains in flight per thread instead of the ~4 the scheduler interleaves on its own
+#pragma unroll
+    for (int hb = 0; hb < 32; hb += 16) {
+      float hh[16], ee[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gelu_parts(v[hb + j], hh[j], ee[j]);
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float x0 = v[hb + j], x1 = v[hb + j + 1];
+        w[(hb + j) >> 1] = pack_bf16x2(gelu_grad_from_parts(x0, hh[j], ee[j]), gelu_grad_from_parts(x1, hh[j + 1], ee[j + 1]));
+        v[hb + j] = fmaf(-fabsf(x0), hh[j], fmaxf(x0, 0.0f));
+        v[hb + j + 1] = fmaf(-fabsf(x1), hh[j + 1], fmaxf(x1, 0.0f));
+      }
+    }
+    tile_put(sa, lane, w);
+    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
+               rows, false);
+  } else if (has<EPI, EF_PREACT>(p.preact_out != nullptr)) {
     pack32(v, w);
     tile_put(sa, lane, w);
     tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
@@ -322,6 +357,14 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uin
   if (has<EPI, EF_GELU>(p.act == X2K_ACT_GELU)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (has<EPI, EF_MUL_AUX>(p.act == X2K_ACT_MUL_AUX)) {
+    tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
+    tile_get(sa, lane, w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[2 * j] *= bf16_lo(w[j]);
+      v[2 * j + 1] *= bf16_hi(w[j]);
+    }
   } else if (has<EPI, EF_GELU_BWD>(p.act == X2K_ACT_GELU_BWD)) {
     tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
     tile_get(sa, lane, w);
@@ -521,6 +564,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int t = tile / split_k;
       const int m0 = (p.raster_m ? t % m_tiles : t / n_tiles) * BLOCK_M;
       const int n0 = (p.raster_m ? t / m_tiles : t % n_tiles) * BLOCK_N;
+      const int mw = m0 + quad * 32;  // first row of this warp
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const int m = m0 + quad * 32 + lane;
@@ -535,9 +579,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_wait_ld();
         if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
         const int n = n0 + half * COLS_PER_WARP + ci * 32;
-        const int mw = m0 + quad * 32;  // first row of this warp
         if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N) epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
+          if (n + 32 <= p.N)
+            epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
           else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);  // ragged last chunk: thread-per-row path
         }
       }
@@ -702,6 +746,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int t = tile / split_k;
       const int m0 = (t / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
       const int n0 = (t % n_tiles) * BLOCK_N;
+      const int mw = m0 + quad * 32;
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const int m = m0 + quad * 32 + lane;
@@ -714,9 +759,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tmem_wait_ld();
         if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
         const int n = n0 + half * COLS_PER_WARP + ci * 32;
-        const int mw = m0 + quad * 32;
         if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N) epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
+          if (n + 32 <= p.N)
+            epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
           else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);
         }
       }
@@ -831,6 +876,8 @@ int epi_mask(const X2kGemmArgs& a) {
   if (a.preact_out) m |= EF_PREACT;
   if (a.act == X2K_ACT_GELU) m |= EF_GELU;
   if (a.act == X2K_ACT_GELU_BWD) m |= EF_GELU_BWD;
+  if (a.act == X2K_ACT_GELU_SAVE_GRAD) m |= EF_GELU_SAVE;
+  if (a.act == X2K_ACT_MUL_AUX) m |= EF_MUL_AUX;
   if (a.dropout_p > 0.f) m |= EF_DROPOUT;
   if (a.gamma || a.row_scale) m |= EF_SCALE;
   if (a.residual) m |= EF_RESIDUAL;
@@ -844,12 +891,12 @@ int epi_mask(const X2kGemmArgs& a) {
 #define X2K_EPI_LIST(X)                                                                   \
   X(0, EF_OUT_BF16)                                               /* plain dgrad */                        \
   X(1, EF_BIAS | EF_OUT_BF16)                                     /* qkv / q / kv projections */           \
-  X(2, EF_BIAS | EF_PREACT | EF_GELU | EF_OUT_BF16)               /* fc1 / intermediate */                 \
+  X(2, EF_BIAS | EF_PREACT | EF_GELU_SAVE | EF_OUT_BF16)          /* fc1 / intermediate: GELU, GELU' saved */ \
   X(3, EF_BIAS | EF_PREACT | EF_SCALE | EF_RESIDUAL | EF_OUT_F32) /* BEiT proj / fc2 (LayerScale, DropPath) */ \
   X(4, EF_BIAS | EF_PREACT | EF_RESIDUAL | EF_OUT_F32)            /* same without LayerScale / DropPath */ \
   X(5, EF_BIAS | EF_DROPOUT | EF_RESIDUAL | EF_OUT_F32)           /* BERT dense + dropout + residual */    \
   X(6, EF_BIAS | EF_RESIDUAL | EF_OUT_F32)                        /* BERT dense + residual (eval) */       \
-  X(7, EF_GELU_BWD | EF_OUT_BF16)                                 /* dgrad through GELU */                 \
+  X(7, EF_MUL_AUX | EF_OUT_BF16)                                  /* dgrad through GELU (saved GELU') */    \
   X(8, EF_OUT_F32)                                                /* wgrad (accumulate / split-K atomics) */ \
   X(9, EF_RESIDUAL | EF_OUT_F32)                                  /* dgrad + residual-stream gradient */   \
   X(10, EF_GENERIC)                                               /* anything else: runtime tests */
@@ -915,7 +962,9 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
               "x2k_gemm: A/B must be 16-byte aligned");
   X2K_REQUIRE(a.out_bf16 || a.out_f32 || a.preact_out, "x2k_gemm: no output");
   X2K_REQUIRE(!a.accumulate || a.out_f32, "x2k_gemm: accumulate needs out_f32");
-  X2K_REQUIRE(a.act != X2K_ACT_GELU_BWD || a.aux, "x2k_gemm: GELU_BWD needs aux");
+  X2K_REQUIRE(a.act >= X2K_ACT_NONE && a.act <= X2K_ACT_MUL_AUX, "x2k_gemm: unknown act %d", a.act);
+  X2K_REQUIRE((a.act != X2K_ACT_GELU_BWD && a.act != X2K_ACT_MUL_AUX) || a.aux, "x2k_gemm: GELU_BWD / MUL_AUX need aux");
+  X2K_REQUIRE(a.act != X2K_ACT_GELU_SAVE_GRAD || a.preact_out, "x2k_gemm: GELU_SAVE_GRAD needs preact_out");
   X2K_REQUIRE(!(a.dropout_p > 0.f) || (a.N % 8 == 0 && a.dropout_p < 1.f), "x2k_gemm: dropout needs N%%8==0, p<1");
   X2K_REQUIRE(!a.row_scale || a.rows_per_scale > 0, "x2k_gemm: rows_per_scale must be > 0");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

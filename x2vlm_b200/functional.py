@@ -15,7 +15,7 @@ import threading
 import torch
 
 from . import ops
-from ._capi import ACT_GELU, ACT_GELU_BWD, ACT_NONE
+from ._capi import ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE
 
 
 # ----------------------------------------------------------------------------------------------
@@ -121,10 +121,10 @@ class _LinearFn(torch.autograd.Function):
         pre = _empty_bf16(M, ld, dev=dev) if gelu else None
         if out_bf16:
             y = _empty_bf16(M, ld, dev=dev)
-            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU if gelu else ACT_NONE, preact_out=pre, out_bf16=y)
+            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU_SAVE_GRAD if gelu else ACT_NONE, preact_out=pre, out_bf16=y)
         else:
             y = torch.empty(M, ld, dtype=torch.float32, device=dev)
-            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU if gelu else ACT_NONE, preact_out=pre, out_f32=y)
+            ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU_SAVE_GRAD if gelu else ACT_NONE, preact_out=pre, out_f32=y)
         ctx.shadow, ctx.gelu, ctx.dims, ctx.x_dtype = shadow, gelu, (M, N, K, ld), x.dtype
         ctx.has_bias = bias is not None
         ctx.save_for_backward(xb, pre)
@@ -145,10 +145,9 @@ class _LinearFn(torch.autograd.Function):
         else:
             dyb = ops.to_bf16(dy.float() if dy.dtype != torch.float32 else dy)
         if ctx.gelu:
-            # dpre = dy * gelu'(pre): identity GEMM is wasteful, so do it elementwise in torch (small uses only)
-            p = pre[:, :N].float()
-            dpre = dyb[:, :N].float() * (0.5 * (1 + torch.erf(p * 0.7071067811865476)) +
-                                         p * torch.exp(-0.5 * p * p) * 0.3989422804014327)
+            # dpre = dy * gelu'(pre); `pre` holds gelu'(pre-activation) itself (X2K_ACT_GELU_SAVE_GRAD).  Small uses only
+            # (MLM transform), so the product is taken elementwise in torch instead of a GEMM epilogue.
+            dpre = dyb[:, :N].float() * pre[:, :N].float()
             dyb = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
             dyb[:, :N].copy_(dpre)
         dbias = None
@@ -242,7 +241,8 @@ class _BeitBlockFn(torch.autograd.Function):
         Dh = sh["fc1"].total_rows
         hpre = _empty_bf16(M, Dh, dev=dev)
         act = _empty_bf16(M, Dh, dev=dev)
-        ops.gemm(ln2, sh["fc1"].get(), M, Dh, D, bias=fc1b, preact_out=hpre, act=ACT_GELU, out_bf16=act)
+        # hpre receives GELU'(pre-activation) (evaluated next to GELU itself): the backward dgrad only multiplies by it
+        ops.gemm(ln2, sh["fc1"].get(), M, Dh, D, bias=fc1b, preact_out=hpre, act=ACT_GELU_SAVE_GRAD, out_bf16=act)
         y2 = _empty_bf16(M, D, dev=dev)
         out = torch.empty(M, D, dtype=torch.float32, device=dev)
         ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale,
@@ -269,7 +269,7 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.scale_cast_colsum(dx2, M, D, g_bf16=g2b, gamma=g2, row_scale=dp_scale, rows_per_scale=N,
                               y_bf16=y2 if g2 is not None else None, dbias=P_fc2b.buf, dgamma=P_g2.buf)
         dh = _empty_bf16(M, Dh, dev=dev)
-        ops.gemm(g2b, sh["fc2"].get_nograd(), M, Dh, D, b_mn=True, act=ACT_GELU_BWD, aux=hpre, out_bf16=dh)
+        ops.gemm(g2b, sh["fc2"].get_nograd(), M, Dh, D, b_mn=True, act=ACT_MUL_AUX, aux=hpre, out_bf16=dh)
         wg_fc2 = _wgrad(sh["fc2"], g2b, act, D, Dh, M)
         del act, g2b
         ops.colsum_bf16(dh, M, Dh, P_fc1b.buf)
@@ -391,7 +391,7 @@ class _BertLayerFn(torch.autograd.Function):
         Di = sh["i"].total_rows
         hpre = _empty_bf16(M, Di, dev=dev)
         act = _empty_bf16(M, Di, dev=dev)
-        ops.gemm(xab, sh["i"].get(), M, Di, D, bias=b_i, preact_out=hpre, act=ACT_GELU, out_bf16=act)
+        ops.gemm(xab, sh["i"].get(), M, Di, D, bias=b_i, preact_out=hpre, act=ACT_GELU_SAVE_GRAD, out_bf16=act)  # hpre = GELU''
         s3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         d_h3 = _drop(p_h, train, M * D)
         ops.gemm(act, sh["out"].get(), M, D, Di, bias=b_out, dropout_p=d_h3[0], dropout_seed=d_h3[1], dropout_offset=d_h3[2],
@@ -435,7 +435,7 @@ class _BertLayerFn(torch.autograd.Function):
         p, seed, off = sv["d_h3"]
         ops.scale_cast_colsum(ds3, M, D, g_bf16=g3, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_bout.buf)
         dh = _empty_bf16(M, Di, dev=dev)
-        ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_GELU_BWD, aux=sv["hpre"], out_bf16=dh)
+        ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_MUL_AUX, aux=sv["hpre"], out_bf16=dh)
         wg_out = _wgrad(sh["out"], g3, sv["act"], D, Di, M)
         ops.colsum_bf16(dh, M, Di, P_bi.buf)
         dxab = _empty_bf16(M, D, dev=dev)

@@ -57,20 +57,29 @@ class kernel_timing:
     def totals(self):
         torch.cuda.synchronize()
         out = {}
-        for fam, flops, st, en in self.records:
+        for fam, flops, st, en, _tag in self.records:
             n, f, ms = out.get(fam, (0, 0.0, 0.0))
             out[fam] = (n + 1, f + flops, ms + st.elapsed_time(en))
         return out
 
+    def by_shape(self):
+        """{(family, shape tag): (launches, flops, ms)} — which shapes / epilogues run below the family average."""
+        torch.cuda.synchronize()
+        out = {}
+        for fam, flops, st, en, tag in self.records:
+            n, f, ms = out.get((fam, tag), (0, 0.0, 0.0))
+            out[(fam, tag)] = (n + 1, f + flops, ms + st.elapsed_time(en))
+        return out
 
-def _timed(family, flops, call):
+
+def _timed(family, flops, call, tag=""):
     if _timing is None:
         return call()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st.record()
     r = call()
     en.record()
-    _timing.append((family, flops, st, en))
+    _timing.append((family, flops, st, en, tag() if callable(tag) else tag))
     return r
 
 
@@ -128,7 +137,13 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
         g.out_f32, g.ld_out_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.tile_n = tile_n
     g.split_k = split_k
-    _timed("gemm", 2.0 * M * N * K, lambda: C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm"))
+    def tag():
+        epi = "+".join(n for n, on in (("bias", bias is not None), ("preact", preact_out is not None), ("gelu", act == C.ACT_GELU),
+                                       ("gelu'", act == C.ACT_GELU_BWD), ("drop", dropout_p > 0.0),
+                                       ("scale", gamma is not None or row_scale is not None), ("res", residual is not None),
+                                       ("acc", accumulate), ("f32", out_f32 is not None), ("bf16", out_bf16 is not None)) if on)
+        return "%dx%dx%d %s%s %s" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", epi)
+    _timed("gemm", 2.0 * M * N * K, lambda: C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm"), tag)
 
 
 def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
@@ -236,7 +251,7 @@ def attn_fwd(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw):
     """q/k/v/o: 2-D bf16 views [rows, >= H*64] (rows = B*Lq or n_kv*Lk) with row stride = ld."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, o, lse, **kw)
     _timed("attn_fwd", 4.0 * B * H * Lq * Lk * 64,
-           lambda: C.check(C.lib().x2k_attn_fwd(ctypes.byref(a), _stream()), "x2k_attn_fwd"))
+           lambda: C.check(C.lib().x2k_attn_fwd(ctypes.byref(a), _stream()), "x2k_attn_fwd"), "B%d Lq%d Lk%d" % (B, Lq, Lk))
 
 
 def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None, **kw):
@@ -251,7 +266,7 @@ def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None,
         a.ds_out = ds_out.data_ptr()
         a.ds_b_stride, a.ds_h_stride, a.ds_q_stride = ds_out.stride(0), ds_out.stride(1), ds_out.stride(2)
     _timed("attn_bwd", 10.0 * B * H * Lq * Lk * 64,
-           lambda: C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd"))
+           lambda: C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd"), "B%d Lq%d Lk%d" % (B, Lq, Lk))
 
 
 def relpos_bias_gather(table, index, N, H, out):

@@ -127,13 +127,43 @@ class XVLM(nn.Module):
         self.itm_head = build_mlp(input_dim=self.text_width, output_dim=2)
         self.bbox_head = build_mlp(input_dim=self.text_width, output_dim=4)
         self.init_params = []
+        # video input (models/xvlm.py:483-501): frames go through the image encoder, then a mean over time
+        self.video_encoding = config.get("video_encoding", "")
+        if self.video_encoding not in ("", "avgpool"):
+            raise NotImplementedError("video_encoding == %r (the reference raises for everything but 'avgpool' too, "
+                                      "models/xvlm.py:651-654)" % (self.video_encoding,))
+        if self.video_encoding:
+            self.frame_len = config["frame_len"]
+            self.add_frame_pos = config["add_frame_pos"]
+            if self.add_frame_pos:
+                self.absolute_frame_pos_embed = nn.Parameter(torch.zeros(1, self.frame_len, 1, self.vision_width))
+                beit2._trunc_normal_(self.absolute_frame_pos_embed, std=.02)
+                self.init_params.append("absolute_frame_pos_embed")
 
     # ------------------------------------------------------------------ reference-shaped methods
+    def get_frame_embeds(self, frames):
+        """models/xvlm.py:615-661, video_encoding == 'avgpool': every frame through the vision encoder as one batch of
+        bsz * frame_len images, learned per-frame offset, mean over the frame axis.  frames: [bsz, F, 3, H, W]."""
+        assert frames.dim() == 5 and self.video_encoding == "avgpool"
+        bsz, n_f = frames.shape[:2]
+        emb = self.vision_encoder(frames.reshape(bsz * n_f, *frames.shape[2:]))
+        emb = emb.view(bsz, n_f, emb.shape[1], emb.shape[2])
+        if self.add_frame_pos:
+            emb = emb + self.absolute_frame_pos_embed
+        emb = emb.mean(dim=1)
+        return emb, torch.ones(emb.size()[:-1], dtype=torch.long, device=frames.device)
+
     def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None):
-        """models/xvlm.py:663-713 (image case)."""
+        """models/xvlm.py:663-713."""
+        if image.dim() == 5:
+            assert idx_to_group_img is None, "not supported"
+            return self.get_frame_embeds(image)
         if idx_to_group_img is None:
             image_embeds = self.vision_encoder(image)
             return image_embeds, torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        if image_atts is None:  # fewer images than samples, full attention (models/xvlm.py:679-690)
+            full = self.vision_encoder(image)[idx_to_group_img]
+            return full, torch.ones(full.size()[:-1], dtype=torch.long, device=image.device)
         image_embeds, full = self.vision_encoder(image, idx_to_group_img=idx_to_group_img, image_atts=image_atts)
         return image_embeds, image_atts, full[idx_to_group_img]
 

@@ -208,6 +208,10 @@ typedef struct X2kAttnArgs {
    * summed over the query sequences that share the source (zeros for a source nobody reads). */
   const int32_t* kv_groups;
   const uint64_t* dropout_offset_dev; /* optional device counter added to dropout_offset (see X2kGemmArgs) */
+  /* backward, optional workspace: fp32 [B,H,Lq].  When given, x2k_attn_bwd first runs a streaming pre-kernel that
+   * writes delta[b,h,i] = sum_d O[b,i,h,d] * dO[b,i,h,d] there, and the attention kernels read one float per row
+   * instead of fetching the row's O and dO at their start (a DRAM round trip on every CTA's critical path). */
+  float* delta_ws;
 } X2kAttnArgs;
 
 int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);

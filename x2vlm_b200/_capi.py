@@ -62,6 +62,7 @@ class X2kAttnArgs(ctypes.Structure):
         ("ds_b_stride", c_int64), ("ds_h_stride", c_int64), ("ds_q_stride", c_int64),
         ("kv_groups", c_void_p),
         ("dropout_offset_dev", c_void_p),
+        ("delta_ws", c_void_p),
     ]
 
 

@@ -41,6 +41,7 @@ struct AttnParams {
   int64_t ld_dq, ld_dk, ld_dv;
   __nv_bfloat16* ds_out;
   int64_t ds_b_stride, ds_h_stride, ds_q_stride;
+  const float* delta;  // [B,H,Lq] rowsum(dO ∘ O) from attn_delta_kernel, or nullptr (computed in the kernel)
 };
 
 // byte offset of the 16-byte chunk holding elements [k0, k0+8) of row `row` inside a K-major,
@@ -403,6 +404,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int q = qb * 128 + row;
     if (q < p.Lq) {
       lse2[qb] = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q];
+      if (p.delta) {
+        delta[qb] = __ldg(p.delta + (static_cast<int64_t>(b) * p.H + h) * p.Lq + q);
+        continue;
+      }
       const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64);
       const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_do + h * 64);
       float acc = 0.f;
@@ -645,6 +650,7 @@ void fill_params(const X2kAttnArgs& a, AttnParams& p) {
   p.ld_dq = a.ld_dq; p.ld_dk = a.ld_dk; p.ld_dv = a.ld_dv;
   p.ds_out = static_cast<__nv_bfloat16*>(a.ds_out);
   p.ds_b_stride = a.ds_b_stride; p.ds_h_stride = a.ds_h_stride; p.ds_q_stride = a.ds_q_stride;
+  p.delta = a.delta_ws;
 }
 
 }  // namespace
@@ -682,6 +688,43 @@ extern "C" int x2k_attn_fwd(const X2kAttnArgs* args, void* stream_) {
   return X2K_OK;
 }
 
+namespace x2k {
+// delta[b,h,i] = sum_d O[b,i,h,d] * dO[b,i,h,d]: one warp per token row, lane -> 16-byte chunk (8 bf16) of the row,
+// 8 consecutive lanes = one head, reduced with three xor-shuffles.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ld_o, const __nv_bfloat16* __restrict__ d_o, int64_t ld_do,
+                  int rows, int H, int Lq, float* __restrict__ delta) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / Lq, i = row - b * Lq;
+  const uint4* po = reinterpret_cast<const uint4*>(o + static_cast<int64_t>(row) * ld_o);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + static_cast<int64_t>(row) * ld_do);
+  for (int c0 = 0; c0 < H * 8; c0 += 32) {
+    const int c = c0 + lane;
+    float acc = 0.f;
+    if (c < H * 8) {
+      const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+      acc = bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y) +
+            bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) + bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((lane & 7) == 0 && c < H * 8) delta[(static_cast<int64_t>(b) * H + (c >> 3)) * Lq + i] = acc;
+  }
+}
+
+int attn_delta_launch(const X2kAttnArgs& a, cudaStream_t stream) {
+  const int rows = a.B * a.Lq;
+  attn_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.o), a.ld_o,
+                                                        static_cast<const __nv_bfloat16*>(a.d_o), a.ld_do, rows, a.H, a.Lq,
+                                                        a.delta_ws);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}
+}  // namespace x2k
+
 extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
   X2K_REQUIRE(args != nullptr, "x2k_attn_bwd: args is NULL");
   const X2kAttnArgs& a = *args;
@@ -689,6 +732,11 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
   if (int rc = check_common(a, "x2k_attn_bwd")) return rc;
   X2K_REQUIRE(a.d_o && a.dq && a.dk && a.dv, "x2k_attn_bwd: NULL d_o/dq/dk/dv");
   X2K_REQUIRE(a.ld_do % 8 == 0 && a.ld_dq % 8 == 0 && a.ld_dk % 8 == 0 && a.ld_dv % 8 == 0, "x2k_attn_bwd: ld alignment");
+  if (a.delta_ws) {
+    X2K_REQUIRE(a.ld_o % 8 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.d_o) & 15) == 0,
+                "x2k_attn_bwd: o / d_o must be 16-byte aligned rows for the delta pre-kernel");
+    if (int rc = attn_delta_launch(a, stream)) return rc;
+  }
   {
     const int rc = attn_pack_bwd(a, stream);
     if (rc <= 0) return rc;

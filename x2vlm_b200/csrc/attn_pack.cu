@@ -41,6 +41,7 @@ __device__ long long g_pack_trace[2][64];
 #endif
 
 struct PackParams {
+  const float* delta;  // [B,H,Lq] rowsum(dO ∘ O) from the pre-kernel, or nullptr
   int B, H, Lq, Lk, Lq8, Lk8, G;
   int N;        // key columns of the tile, multiple of 16 (self: pad16(G*Lk8), cross: pad16(Lk))
   int Lk_pad;   // pad16(Lk): row stride of the dropout element index (same stream as attn.cu)
@@ -474,6 +475,10 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     float my_lse = 0.f, my_delta = 0.f;
     if (ri.ok) {
       my_lse = p.lse[(static_cast<int64_t>(ri.b) * p.H + h) * p.Lq + ri.q];
+    }
+    if (ri.ok && p.delta) {
+      my_delta = __ldg(p.delta + (static_cast<int64_t>(ri.b) * p.H + h) * p.Lq + ri.q);
+    } else if (ri.ok) {
       const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_o + h * 64);
       const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_do + h * 64);
 #pragma unroll
@@ -798,6 +803,7 @@ int attn_pack_plan(const X2kAttnArgs& a, bool backward, PackParams& p) {
   p.dropout_p = a.dropout_p; p.seed = a.dropout_seed; p.offset = a.dropout_offset; p.offset_dev = a.dropout_offset_dev;
   p.o = static_cast<__nv_bfloat16*>(a.o); p.ld_o = a.ld_o; p.lse = a.lse;
   p.d_o = static_cast<const __nv_bfloat16*>(a.d_o); p.ld_do = a.ld_do;
+  p.delta = backward ? a.delta_ws : nullptr;
   p.dq = static_cast<__nv_bfloat16*>(a.dq); p.dk = static_cast<__nv_bfloat16*>(a.dk); p.dv = static_cast<__nv_bfloat16*>(a.dv);
   p.ld_dq = a.ld_dq; p.ld_dk = a.ld_dk; p.ld_dv = a.ld_dv;
   const uint32_t kv_bytes = (static_cast<uint32_t>(p.N) * 128 + 1023) & ~1023u;

@@ -57,7 +57,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;  // 4 per TMEM lane quadrant, each takes a quarter of the tile's columns
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 
@@ -65,37 +65,28 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;  // 192 KB of operand stages + 32 KB of epilogue tiles
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 80;  // per-warp transpose tile (EPI_TILE_BYTES)
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 64;  // per-warp transpose tile (EPI_TILE_BYTES)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 
-// Apply the fused epilogue to 32 consecutive columns [n0, n0+32) of row m (thread-per-row global accesses: only the
-// ragged last chunk of an N % 32 != 0 output — the vocabulary GEMM — comes here).
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0, uint32_t (&acc)[32]) {
-  float v[32];
+// Apply the fused epilogue to the 16 columns [n0, n0+16) of row m with thread-per-row global accesses and a bounds
+// test per element: only the ragged last chunk of an N % 32 != 0 output (the vocabulary GEMM, N < 32 heads) comes here.
+__device__ __forceinline__ void epilogue_tail16(const EpiParams& p, int m, int n0, uint32_t (&acc)[16]) {
+  float v[16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  const bool full = (n0 + 32 <= p.N);
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   if (p.bias) {
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-    }
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
   }
   if (p.act == X2K_ACT_GELU_SAVE_GRAD) {  // preact_out receives GELU'(v), v becomes GELU(v)
     __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 16; ++j) {
       float g, dg;
       gelu_erf_both(v[j], g, dg);
       v[j] = g;
@@ -103,44 +94,21 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
     }
   } else if (p.preact_out) {
     __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(dst + j) = q;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-    }
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
   }
   if (p.act == X2K_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == X2K_ACT_MUL_AUX) {
+    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == X2K_ACT_MUL_AUX || p.act == X2K_ACT_GELU_BWD) {
     const __nv_bfloat16* src = p.aux + static_cast<int64_t>(m) * p.ld_aux + n0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n0 + j < p.N) v[j] *= __bfloat162float(src[j]);
-  } else if (p.act == X2K_ACT_GELU_BWD) {
-    const __nv_bfloat16* src = p.aux + static_cast<int64_t>(m) * p.ld_aux + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + j));
-        v[j] *= gelu_erf_grad(bf16_lo(q.x)); v[j + 1] *= gelu_erf_grad(bf16_hi(q.x));
-        v[j + 2] *= gelu_erf_grad(bf16_lo(q.y)); v[j + 3] *= gelu_erf_grad(bf16_hi(q.y));
-        v[j + 4] *= gelu_erf_grad(bf16_lo(q.z)); v[j + 5] *= gelu_erf_grad(bf16_hi(q.z));
-        v[j + 6] *= gelu_erf_grad(bf16_lo(q.w)); v[j + 7] *= gelu_erf_grad(bf16_hi(q.w));
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) {
+        const float a = __bfloat162float(src[j]);
+        v[j] *= p.act == X2K_ACT_MUL_AUX ? a : gelu_erf_grad(a);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] *= gelu_erf_grad(__bfloat162float(src[j]));
-    }
   }
   if (p.dropout_p > 0.0f) {
     const DropCfg dc = make_drop(p.dropout_p);
@@ -148,7 +116,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
     const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
     // N is a multiple of 8 whenever dropout is used (checked on the host), so base % 8 == 0.
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < 16; j += 8) {
       float k[8];
       drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
 #pragma unroll
@@ -156,77 +124,35 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
     }
   }
   if (p.gamma) {
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
-        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] *= __ldg(p.gamma + n0 + j);
-    }
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) v[j] *= __ldg(p.gamma + n0 + j);
   }
   if (p.row_scale) {
     const float s = __ldg(p.row_scale + m / p.rows_per_scale);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= s;
+    for (int j = 0; j < 16; ++j) v[j] *= s;
   }
   if (p.residual) {
     const float* src = p.residual + static_cast<int64_t>(m) * p.ld_res + n0;
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(src + j));
-        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __ldg(src + j);
-    }
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) v[j] += __ldg(src + j);
   }
   if (p.out_f32) {
     float* dst = p.out_f32 + static_cast<int64_t>(m) * p.ld_out_f32 + n0;
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (p.split_k > 1) {
-          atomicAdd(reinterpret_cast<float4*>(dst + j), o);  // red.global.add.v4.f32 (sm_90+)
-          continue;
-        }
-        if (p.accumulate) {
-          const float4 c = *reinterpret_cast<const float4*>(dst + j);
-          o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-        }
-        *reinterpret_cast<float4*>(dst + j) = o;
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) {
+        if (p.split_k > 1) atomicAdd(dst + j, v[j]);
+        else dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) {
-          if (p.split_k > 1) atomicAdd(dst + j, v[j]);
-          else dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
-        }
-    }
   }
   if (p.out_bf16) {
     __nv_bfloat16* dst = p.out_bf16 + static_cast<int64_t>(m) * p.ld_out_bf16 + n0;
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(dst + j) = q;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-    }
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
   }
 }
 
@@ -234,13 +160,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0
 // Coalesced epilogue.  tcgen05.ld hands every thread one ROW of the accumulator, but a warp-wide global access in
 // which each lane touches a different row costs 32 L1 wavefronts / 32 half-filled sectors per instruction.  Every
 // per-element tensor of the epilogue (pre-activation, aux, residual, outputs) therefore goes through a per-warp
-// transpose tile in shared memory: 32 rows x 64 payload bytes (32 bf16 or 16 fp32 columns) with an 80-byte row
-// pitch, which keeps 16-byte accesses conflict-free on the thread-per-row side (8 lanes x 80 B hit disjoint bank
-// quads).  On the global side lane l handles 16 bytes of row 8*it + l/4: every instruction moves 8 rows x 64
-// contiguous bytes.  fp32 tensors are processed as two 16-column halves.
+// transpose tile in shared memory: 32 rows x 64 payload bytes (32 bf16 or 16 fp32 columns), rows 64 bytes apart, the
+// 16-byte chunk c of row r stored at chunk c ^ ((r >> 1) & 3).  That XOR keeps 16-byte accesses conflict-free on both
+// sides: thread-per-row (8 lanes = 8 rows, one chunk each: even rows fall into one 64-byte bank half with four
+// different physical chunks, odd rows into the other) and global side (lane l handles chunk l%4 of row 8*it + l/4:
+// 8 lanes = 2 rows x 4 chunks).  On the global side every instruction moves 8 rows x 64 contiguous bytes.
+// fp32 tensors are processed as 16-column halves.
 // ---------------------------------------------------------------------------------------------
-constexpr int EPI_ROW_PITCH = 80;
-constexpr int EPI_TILE_BYTES = 32 * EPI_ROW_PITCH;  // 2560 B per epilogue warp
+constexpr int EPI_TILE_BYTES = 32 * 64;  // 2 KB per epilogue warp
+
+__device__ __forceinline__ uint32_t epi_off(int r, int c) { return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -252,16 +181,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 // thread-per-row side: this thread's 16 words <-> row `lane` of the tile
 __device__ __forceinline__ void tile_put(uint32_t sa, int lane, const uint32_t (&w)[16]) {
-  const uint32_t r = sa + lane * EPI_ROW_PITCH;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) sts128(r + 16 * j, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  for (int j = 0; j < 4; ++j) sts128(sa + epi_off(lane, j), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
   __syncwarp();
 }
 __device__ __forceinline__ void tile_get(uint32_t sa, int lane, uint32_t (&w)[16]) {
-  const uint32_t r = sa + lane * EPI_ROW_PITCH;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint4 q = lds128(r + 16 * j);
+    const uint4 q = lds128(sa + epi_off(lane, j));
     w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
   }
   __syncwarp();
@@ -270,10 +197,10 @@ __device__ __forceinline__ void tile_get(uint32_t sa, int lane, uint32_t (&w)[16
 __device__ __forceinline__ void tile_store(uint32_t sa, int lane, uint8_t* g, int64_t ld_bytes, int rows, bool atomic_f32) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2), ch = (lane & 3) * 16;
-    const uint4 q = lds128(sa + r * EPI_ROW_PITCH + ch);
+    const int r = it * 8 + (lane >> 2), c = lane & 3;
+    const uint4 q = lds128(sa + epi_off(r, c));
     if (r < rows) {
-      uint8_t* dst = g + r * ld_bytes + ch;
+      uint8_t* dst = g + r * ld_bytes + c * 16;
       if (atomic_f32)
         atomicAdd(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
                                                                __uint_as_float(q.w)));
@@ -286,10 +213,10 @@ __device__ __forceinline__ void tile_store(uint32_t sa, int lane, uint8_t* g, in
 __device__ __forceinline__ void tile_load(uint32_t sa, int lane, const uint8_t* g, int64_t ld_bytes, int rows) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2), ch = (lane & 3) * 16;
+    const int r = it * 8 + (lane >> 2), c = lane & 3;
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) q = *reinterpret_cast<const uint4*>(g + r * ld_bytes + ch);
-    sts128(sa + r * EPI_ROW_PITCH + ch, q.x, q.y, q.z, q.w);
+    if (r < rows) q = *reinterpret_cast<const uint4*>(g + r * ld_bytes + c * 16);
+    sts128(sa + epi_off(r, c), q.x, q.y, q.z, q.w);
   }
   __syncwarp();
 }
@@ -312,124 +239,184 @@ __device__ __forceinline__ bool has(bool runtime) {
   else return (EPI & F) != 0;
 }
 
-// Fused epilogue of a full 32-column chunk for the 32 rows [mw, mw+32) owned by this warp (thread == row mw+lane);
-// `rows` = number of those rows inside the matrix.  Same arithmetic, in the same order, as epilogue_chunk.
+// Fused epilogue of a full 32-column chunk [n0, n0+32) for the 32 rows [mw, mw+32) owned by this warp (thread == row
+// mw+lane; `rows` = number of those rows inside the matrix), read from TMEM at `taddr`.
+//
+// The CTA runs 16 epilogue warps (4 per scheduler): with 8, the K = 768 GEMMs of the step were bound by the latency of
+// their epilogue chains (ncu, profiles/: issue slots 17-40% busy, long-scoreboard stalls on the residual loads, tensor
+// pipe 18-36% busy while the plain bf16 epilogue reached 73%).  18 warps leave ~100 registers per thread, so the chunk
+// is processed as two 16-column halves: fp32 tensors (residual, out_f32) move one half = one 64-byte tile row at a
+// time anyway; bf16 tensors (pre-activation, aux, out_bf16) are packed per half and cross the transpose tile once per
+// chunk (32 bf16 columns = 64 bytes per row).  Same arithmetic, in the same order, as epilogue_tail16.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& p, uint32_t sa, int lane, int mw, int rows, int n0,
-                                                         uint32_t (&acc)[32]) {
-  float v[32];
-  uint32_t w[16];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+__device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t sa, int lane, int mw, int rows, int n0,
+                                                 uint32_t taddr) {
   const int m = mw + lane;
-  if (has<EPI, EF_BIAS>(p.bias != nullptr)) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
+  uint32_t wpre[16], wout[16], waux[16], w[16];
+  constexpr bool kGeneric = EPI == EF_GENERIC;
+  const bool f_save = has<EPI, EF_GELU_SAVE>(p.act == X2K_ACT_GELU_SAVE_GRAD);
+  const bool f_pre = has<EPI, EF_PREACT>(p.preact_out != nullptr) || f_save;
+  const bool f_gelu = has<EPI, EF_GELU>(p.act == X2K_ACT_GELU);
+  const bool f_mul = has<EPI, EF_MUL_AUX>(p.act == X2K_ACT_MUL_AUX);
+  const bool f_gbwd = has<EPI, EF_GELU_BWD>(p.act == X2K_ACT_GELU_BWD);
+  (void)kGeneric;
+  if (f_mul || f_gbwd) {
+    tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
+    tile_get(sa, lane, waux);
   }
-  if (has<EPI, EF_GELU_SAVE>(p.act == X2K_ACT_GELU_SAVE_GRAD)) {
-    // staged over 16 elements at a time (all reciprocals, all exponentials, then the polynomials): 16 independent
-    // MUFU -> FMA chains in flight per thread instead of the ~4 the scheduler interleaves on its own
+  // light epilogues (no activation math, dropout or residual) have registers to spare: both halves are fetched from
+  // TMEM up front, so the second load is in flight while the first half is processed
+  constexpr bool kPrefetch = EPI != EF_GENERIC && (EPI & (EF_GELU | EF_GELU_SAVE | EF_GELU_BWD | EF_DROPOUT | EF_RESIDUAL)) == 0;
+  uint32_t acc2[2][16];
+  if (kPrefetch) {
+    tmem_ld_32x16(taddr, acc2[0]);
+    tmem_ld_32x16(taddr + 16, acc2[1]);
+  }
 #pragma unroll
-    for (int hb = 0; hb < 32; hb += 16) {
-      float hh[16], ee[16];
+  for (int hf = 0; hf < 2; ++hf) {
+    const int nh = n0 + 16 * hf;
+    float v[16];
+    if (kPrefetch) {
+      if (hf == 0) tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) gelu_parts(v[hb + j], hh[j], ee[j]);
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc2[hf][j]);
+    } else {
+      uint32_t acc[16];
+      tmem_ld_32x16(taddr + 16 * hf, acc);
+      tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float x0 = v[hb + j], x1 = v[hb + j + 1];
-        w[(hb + j) >> 1] = pack_bf16x2(gelu_grad_from_parts(x0, hh[j], ee[j]), gelu_grad_from_parts(x1, hh[j + 1], ee[j + 1]));
-        v[hb + j] = fmaf(-fabsf(x0), hh[j], fmaxf(x0, 0.0f));
-        v[hb + j + 1] = fmaf(-fabsf(x1), hh[j + 1], fmaxf(x1, 0.0f));
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+    }
+    if (has<EPI, EF_BIAS>(p.bias != nullptr)) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nh + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
-    tile_put(sa, lane, w);
-    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
-               rows, false);
-  } else if (has<EPI, EF_PREACT>(p.preact_out != nullptr)) {
-    pack32(v, w);
-    tile_put(sa, lane, w);
-    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
-               rows, false);
-  }
-  if (has<EPI, EF_GELU>(p.act == X2K_ACT_GELU)) {
+    if (f_save) {
+      // staged 8 elements at a time (all reciprocals / exponentials, then the polynomials): 8 independent
+      // MUFU -> FMA chains in flight per thread
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (has<EPI, EF_MUL_AUX>(p.act == X2K_ACT_MUL_AUX)) {
-    tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
-    tile_get(sa, lane, w);
+      for (int hb = 0; hb < 16; hb += 8) {
+        float hh[8], ee[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[2 * j] *= bf16_lo(w[j]);
-      v[2 * j + 1] *= bf16_hi(w[j]);
+        for (int j = 0; j < 8; ++j) gelu_parts(v[hb + j], hh[j], ee[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float x0 = v[hb + j], x1 = v[hb + j + 1];
+          wpre[8 * hf + ((hb + j) >> 1)] =
+              pack_bf16x2(gelu_grad_from_parts(x0, hh[j], ee[j]), gelu_grad_from_parts(x1, hh[j + 1], ee[j + 1]));
+          v[hb + j] = fmaf(-fabsf(x0), hh[j], fmaxf(x0, 0.0f));
+          v[hb + j + 1] = fmaf(-fabsf(x1), hh[j + 1], fmaxf(x1, 0.0f));
+        }
+      }
+    } else if (f_pre) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wpre[8 * hf + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
     }
-  } else if (has<EPI, EF_GELU_BWD>(p.act == X2K_ACT_GELU_BWD)) {
-    tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.aux + static_cast<int64_t>(mw) * p.ld_aux + n0), p.ld_aux * 2, rows);
-    tile_get(sa, lane, w);
+    if (f_gelu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[2 * j] *= gelu_erf_grad(bf16_lo(w[j]));
-      v[2 * j + 1] *= gelu_erf_grad(bf16_hi(w[j]));
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+    } else if (f_mul) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] *= bf16_lo(waux[8 * hf + j]);
+        v[2 * j + 1] *= bf16_hi(waux[8 * hf + j]);
+      }
+    } else if (f_gbwd) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] *= gelu_erf_grad(bf16_lo(waux[8 * hf + j]));
+        v[2 * j + 1] *= gelu_erf_grad(bf16_hi(waux[8 * hf + j]));
+      }
     }
-  }
-  if (has<EPI, EF_DROPOUT>(true) && p.dropout_p > 0.0f) {
-    const DropCfg dc = make_drop(p.dropout_p);
-    const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(n0);
-    const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
+    if (has<EPI, EF_DROPOUT>(true) && p.dropout_p > 0.0f) {
+      const DropCfg dc = make_drop(p.dropout_p);
+      const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(nh);
+      const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      float k[8];
-      drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
+      for (int j = 0; j < 16; j += 8) {
+        float k[8];
+        drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
+        for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
+      }
     }
-  }
-  if (has<EPI, EF_SCALE>(true) && p.gamma) {
+    if (has<EPI, EF_SCALE>(true) && p.gamma) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
-      v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      for (int j = 0; j < 16; j += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + nh + j));
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
     }
-  }
-  if (has<EPI, EF_SCALE>(true) && p.row_scale) {
-    const float sc = __ldg(p.row_scale + min(m, p.M - 1) / p.rows_per_scale);
+    if (has<EPI, EF_SCALE>(true) && p.row_scale) {
+      const float sc = __ldg(p.row_scale + min(m, p.M - 1) / p.rows_per_scale);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= sc;
-  }
-  if (has<EPI, EF_RESIDUAL>(p.residual != nullptr)) {
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.residual + static_cast<int64_t>(mw) * p.ld_res + n0 + 16 * hf),
-                p.ld_res * 4, rows);
+      for (int j = 0; j < 16; ++j) v[j] *= sc;
+    }
+    if (has<EPI, EF_RESIDUAL>(p.residual != nullptr)) {
+      tile_load(sa, lane, reinterpret_cast<const uint8_t*>(p.residual + static_cast<int64_t>(mw) * p.ld_res + nh), p.ld_res * 4,
+                rows);
       tile_get(sa, lane, w);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[16 * hf + j] += __uint_as_float(w[j]);
+      for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(w[j]);
     }
-  }
-  if (has<EPI, EF_OUT_F32>(p.out_f32 != nullptr)) {
-    const bool atomic = p.split_k > 1;
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      uint8_t* dst = reinterpret_cast<uint8_t*>(p.out_f32 + static_cast<int64_t>(mw) * p.ld_out_f32 + n0 + 16 * hf);
+    if (has<EPI, EF_OUT_F32>(p.out_f32 != nullptr)) {
+      const bool atomic = p.split_k > 1;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p.out_f32 + static_cast<int64_t>(mw) * p.ld_out_f32 + nh);
       if (p.accumulate && !atomic) {
         tile_load(sa, lane, dst, p.ld_out_f32 * 4, rows);
         tile_get(sa, lane, w);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[16 * hf + j] += __uint_as_float(w[j]);
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(w[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[16 * hf + j]);
+      for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[j]);
       tile_put(sa, lane, w);
       tile_store(sa, lane, dst, p.ld_out_f32 * 4, rows, atomic);
     }
+    if (has<EPI, EF_OUT_BF16>(p.out_bf16 != nullptr)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wout[8 * hf + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    }
+  }
+  if (f_pre) {
+    tile_put(sa, lane, wpre);
+    tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0), p.ld_preact * 2,
+               rows, false);
   }
   if (has<EPI, EF_OUT_BF16>(p.out_bf16 != nullptr)) {
-    pack32(v, w);
-    tile_put(sa, lane, w);
+    tile_put(sa, lane, wout);
     tile_store(sa, lane, reinterpret_cast<uint8_t*>(p.out_bf16 + static_cast<int64_t>(mw) * p.ld_out_bf16 + n0), p.ld_out_bf16 * 2,
                rows, false);
+  }
+}
+
+// The 32-column chunks of one warp: full chunks through the coalesced path, a ragged last chunk (N % 32 != 0) through
+// the thread-per-row path.  Warp-uniform control flow around every tcgen05.ld.
+template <int EPI, int NCH>
+__device__ __forceinline__ void epilogue_warp_columns(const EpiParams& p, uint32_t sa, int lane, int mw, int n_first,
+                                                      uint32_t taddr) {
+  const int m = mw + lane;
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int n = n_first + ci * 32;
+    if (mw < p.M && n < p.N) {
+      if (n + 32 <= p.N) {
+        epilogue_chunk32<EPI>(p, sa, lane, mw, min(32, p.M - mw), n, taddr + ci * 32);
+      } else {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (n + 16 * hf < p.N) {
+            uint32_t acc[16];
+            tmem_ld_32x16(taddr + ci * 32 + 16 * hf, acc);
+            tmem_wait_ld();
+            if (m < p.M) epilogue_tail16(p, m, n + 16 * hf, acc);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -554,37 +541,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;            // 0..7
+    const int ew = warp - 2;            // 0..15
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;           // which half of the BLOCK_N columns
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const int part = ew >> 2;           // which quarter of the BLOCK_N columns
+    constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int t = tile / split_k;
       const int m0 = (p.raster_m ? t % m_tiles : t / n_tiles) * BLOCK_M;
       const int n0 = (p.raster_m ? t / m_tiles : t % n_tiles) * BLOCK_N;
-      const int mw = m0 + quad * 32;  // first row of this warp
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
-      const int m = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
-      // software-pipelined over the warp's 32-column chunks: the TMEM load of chunk c+1 is in flight while chunk c
-      // goes through the epilogue
-      constexpr int NCH = COLS_PER_WARP / 32;
-      uint32_t acc[2][32];
-      tmem_ld_32x32(taddr, acc[0]);
-#pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        tmem_wait_ld();
-        if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
-        const int n = n0 + half * COLS_PER_WARP + ci * 32;
-        if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N)
-            epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
-          else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);  // ragged last chunk: thread-per-row path
-        }
-      }
+      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + part * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+      epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_TILE_BYTES, lane, m0 + quad * 32,
+                                                     n0 + part * COLS_PER_WARP, taddr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
@@ -616,7 +587,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   constexpr int BLOCK_N = 256;
   constexpr int HALF_N = 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + HALF_N * BLOCK_K * 2;  // 32 KB
-  constexpr int STAGES = 6;
+  constexpr int STAGES = 6;  // 6 x 32 KB + 32 KB of epilogue transpose tiles
   constexpr int TMEM_COLS = 512;
 
   extern __shared__ uint8_t smem_raw[];
@@ -738,33 +709,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue (both CTAs, each on its own 128 rows) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;
-    const int half = ew >> 2;
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const int part = ew >> 2;
+    constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int t = tile / split_k;
       const int m0 = (t / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
       const int n0 = (t % n_tiles) * BLOCK_N;
-      const int mw = m0 + quad * 32;
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
-      const int m = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
-      constexpr int NCH = COLS_PER_WARP / 32;
-      uint32_t acc[2][32];
-      tmem_ld_32x32(taddr, acc[0]);
-#pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        tmem_wait_ld();
-        if (ci + 1 < NCH) tmem_ld_32x32(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
-        const int n = n0 + half * COLS_PER_WARP + ci * 32;
-        if (mw < p.M && n < p.N) {
-          if (n + 32 <= p.N)
-            epilogue_chunk_coalesced<EPI>(p, epi_stage + ew * EPI_TILE_BYTES, lane, mw, min(32, p.M - mw), n, acc[ci & 1]);
-          else if (m < p.M) epilogue_chunk(p, m, n, acc[ci & 1]);
-        }
-      }
+      const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + part * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+      epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_TILE_BYTES, lane, m0 + quad * 32,
+                                                     n0 + part * COLS_PER_WARP, taddr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta0(&tmem_empty_bar[acc_stage]);

@@ -262,6 +262,8 @@ def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None,
     a.d_o, a.ld_do = d_o.data_ptr(), d_o.stride(0)
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     a.ld_dq, a.ld_dk, a.ld_dv = dq.stride(0), dk.stride(0), dv.stride(0)
+    delta_ws = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)  # rowsum(dO * O), filled by a pre-kernel
+    a.delta_ws = delta_ws.data_ptr()
     if ds_out is not None:  # [B, H, Lq, ld]
         a.ds_out = ds_out.data_ptr()
         a.ds_b_stride, a.ds_h_stride, a.ds_q_stride = ds_out.stride(0), ds_out.stride(1), ds_out.stride(2)

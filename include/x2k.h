@@ -127,6 +127,15 @@ int x2k_layernorm_fwd(const float* x, const float* w, const float* b, int32_t M,
 int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* w,
                       const float* mean, const float* rstd, const float* dx_residual, int32_t M,
                       int32_t D, float* dx, float* dw, float* db, void* stream);
+/* x2k_layernorm_bwd_dropcast: x2k_layernorm_bwd followed, in the same pass, by what x2k_scale_cast_colsum(dx, dropout)
+ * computes: g_bf16[m,n] = bf16(dx[m,n] * keepscale(m,n)) (Philox element index m*D+n, seed/offset of the forward
+ * GEMM's dropout) and dbias[n] += sum_m dx[m,n] * keepscale(m,n) (dbias may be NULL).  Backward of the post-LN BERT
+ * "LayerNorm(dropout(dense(h)) + residual)" (models/xbert.py:427-431, :511-515) without re-reading dx. */
+int x2k_layernorm_bwd_dropcast(const void* dy_bf16, const float* dy_f32, const float* x, const float* w,
+                               const float* mean, const float* rstd, const float* dx_residual, int32_t M,
+                               int32_t D, float* dx, float* dw, float* db, float dropout_p,
+                               uint64_t dropout_seed, uint64_t dropout_offset,
+                               const uint64_t* dropout_offset_dev, void* g_bf16, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * x2k_scale_cast_colsum: backward of the "dropout / LayerScale / DropPath + residual" epilogue.

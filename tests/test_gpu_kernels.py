@@ -118,6 +118,19 @@ def test_layernorm(dev, M, D, eps):
     ops.layernorm_bwd((dy, dyb), x, w, mean, rstd, dx, dw, db, dx_residual=res)
     assert (dx - (xr.grad + res)).abs().max() < 1e-3
     assert (dw - wr.grad).abs().max() < 1e-3 * wr.grad.abs().max() and (db - br.grad).abs().max() < 1e-3 * br.grad.abs().max()
+    # fused variant: same dx/dw/db plus g = bf16(dx * Philox keep-scale) and dbias += colsum(dx * keep-scale)
+    from oracle import philox
+    dx2 = torch.empty(M, D, device=dev); dw2 = torch.zeros(D, device=dev); db2 = torch.zeros(D, device=dev)
+    gb = torch.empty(M, D, device=dev, dtype=torch.bfloat16); dbias = torch.zeros(D, device=dev)
+    ops.layernorm_bwd((dy, dyb), x, w, mean, rstd, dx2, dw2, db2, dx_residual=res, g_bf16=gb, dbias=dbias, dropout_p=0.1,
+                      dropout_seed=11, dropout_offset=5)
+    assert (dx2 - dx).abs().max() <= 1e-5 * dx.abs().max()       # same math; FMA contraction may differ between the two instantiations
+    assert (dw2 - dw).abs().max() <= 1e-4 * dw.abs().max() and (db2 - db).abs().max() <= 1e-4 * db.abs().max()
+    keep = torch.from_numpy(philox.keep_scale(11, 5, M * D, 0.1)).view(M, D).to(dev)
+    assert (gb.float() - dx * keep).abs().max() < 0.01 * (dx * keep).abs().max()
+    assert (dbias - (dx * keep).sum(0)).abs().max() < 1e-3 * (dx * keep).sum(0).abs().max() + 1e-3
+    ops.layernorm_bwd((dy, dyb), x, w, mean, rstd, dx2, dw2, db2, g_bf16=gb, dbias=dbias)      # p = 0: plain cast
+    assert (gb.float() - dx2).abs().max() < 0.01 * dx2.abs().max()
 
 
 def test_scale_cast_colsum_and_friends(dev):

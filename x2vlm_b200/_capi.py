@@ -79,6 +79,9 @@ SYMBOLS = {
     "x2k_layernorm_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
+    "x2k_layernorm_bwd_dropcast": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                                  c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "x2k_scale_cast_colsum": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                              c_int32, c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_int64,
                                              c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

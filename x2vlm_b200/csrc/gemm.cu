@@ -393,6 +393,29 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t sa
   }
 }
 
+// L2 prefetch of the per-element epilogue INPUTS (fp32 residual, bf16 aux, fp32 accumulate target) of this warp's part
+// of its NEXT tile: lane l touches the 128-byte lines of row mw + l.  Issued one tile ahead, so the loads inside the
+// chunk epilogue hit L2 (~250 cycles) instead of paying a loaded-DRAM round trip on every chunk's critical path (ncu:
+// the top stall of the "+ residual" epilogues was the st.shared that waits for the residual load).
+template <int EPI, int COLS>
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& p, int lane, int mw, int n_first) {
+  const int m = mw + lane;
+  if (m >= p.M || n_first >= p.N) return;
+  const int cols = min(COLS, p.N - n_first);
+  if (has<EPI, EF_RESIDUAL>(p.residual != nullptr)) {
+    const char* a = reinterpret_cast<const char*>(p.residual + static_cast<int64_t>(m) * p.ld_res + n_first);
+    for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+  }
+  if (has<EPI, EF_MUL_AUX>(p.act == X2K_ACT_MUL_AUX) || has<EPI, EF_GELU_BWD>(p.act == X2K_ACT_GELU_BWD)) {
+    const char* a = reinterpret_cast<const char*>(p.aux + static_cast<int64_t>(m) * p.ld_aux + n_first);
+    for (int b = 0; b < cols * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+  }
+  if (has<EPI, EF_OUT_F32>(p.out_f32 != nullptr) && p.accumulate && p.split_k <= 1) {
+    const char* a = reinterpret_cast<const char*>(p.out_f32 + static_cast<int64_t>(m) * p.ld_out_f32 + n_first);
+    for (int b = 0; b < cols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+  }
+}
+
 // The 32-column chunks of one warp: full chunks through the coalesced path, a ragged last chunk (N % 32 != 0) through
 // the thread-per-row path.  Warp-uniform control flow around every tcgen05.ld.
 template <int EPI, int NCH>
@@ -554,6 +577,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + part * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) {  // inputs of the next tile -> L2
+        const int tn = (tile + static_cast<int>(gridDim.x)) / split_k;
+        const int m0n = (p.raster_m ? tn % m_tiles : tn / n_tiles) * BLOCK_M;
+        const int n0n = (p.raster_m ? tn / m_tiles : tn % n_tiles) * BLOCK_N;
+        epilogue_prefetch<EPI, COLS_PER_WARP>(p, lane, m0n + quad * 32, n0n + part * COLS_PER_WARP);
+      }
       epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_TILE_BYTES, lane, m0 + quad * 32,
                                                      n0 + part * COLS_PER_WARP, taddr);
       tc_fence_before();
@@ -720,6 +749,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + part * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+      if (tile + num_pairs < num_tiles) {  // inputs of the next tile -> L2
+        const int tn = (tile + num_pairs) / split_k;
+        epilogue_prefetch<EPI, COLS_PER_WARP>(p, lane, (tn / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32,
+                                              (tn % n_tiles) * BLOCK_N + part * COLS_PER_WARP);
+      }
       epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_TILE_BYTES, lane, m0 + quad * 32,
                                                      n0 + part * COLS_PER_WARP, taddr);
       tc_fence_before();

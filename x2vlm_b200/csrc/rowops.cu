@@ -68,15 +68,35 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // LayerNorm backward: warps stride over rows, keep per-column dw/db partials in registers,
 // reduce across the block's warps in smem, then one atomicAdd per column per block.
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
+// FUSE: the kernel also produces what x2k_scale_cast_colsum would compute from dx in a second pass over it (the BERT
+// "dense + dropout + residual -> LayerNorm" backward): g = bf16(dx * keepscale) and dbias += colsum(dx * keepscale).
+struct LnFuse {
+  float dropout_p;
+  uint64_t seed, offset;
+  const uint64_t* offset_dev;
+  __nv_bfloat16* g;
+  float* dbias;
+};
+
+template <int VEC, bool FUSE>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16,
                                                             const float* __restrict__ dy_f32, const float* __restrict__ x,
                                                             const float* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
                                                             const float* __restrict__ dx_residual, int M, int D,
                                                             float* __restrict__ dx, float* __restrict__ dw,
-                                                            float* __restrict__ db) {
-  extern __shared__ float red[];  // [warps][2*D]
+                                                            float* __restrict__ db, const LnFuse f) {
+  extern __shared__ float red[];  // [warps][(FUSE ? 3 : 2)*D]
+  constexpr int NRED = FUSE ? 3 : 2;
+  float4 adg[FUSE ? VEC : 1];
+  DropCfg dc = make_drop(0.f);
+  uint64_t doff = 0;
+  if (FUSE) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) adg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dc = make_drop(f.dropout_p);
+    doff = f.offset + ((f.dropout_p > 0.f && f.offset_dev) ? __ldg(f.offset_dev) : 0ull);
+  }
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -125,22 +145,38 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       reinterpret_cast<float4*>(dx + static_cast<int64_t>(row) * D)[c4] = o;
+      if (FUSE) {
+        if (f.dropout_p > 0.f) {
+          const uint64_t idx = static_cast<uint64_t>(row) * static_cast<uint64_t>(D) + static_cast<uint64_t>(c4 * 4);
+          float k[8];
+          drop8(f.seed, doff, idx >> 3, dc, k);
+          const int h = static_cast<int>(idx & 4);  // this lane's 4 columns are the low or the high half of the group
+          o.x *= k[h]; o.y *= k[h + 1]; o.z *= k[h + 2]; o.w *= k[h + 3];
+        }
+        adg[j].x += o.x; adg[j].y += o.y; adg[j].z += o.z; adg[j].w += o.w;
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(f.g + static_cast<int64_t>(row) * D)[c4] = pk;
+      }
     }
   }
-  // block reduction of dw/db partials
+  // block reduction of dw/db(/dbias) partials
   float4* red4 = reinterpret_cast<float4*>(red);
   const int D4 = D / 4;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    red4[wib * 2 * D4 + lane + 32 * j] = adw[j];
-    red4[wib * 2 * D4 + D4 + lane + 32 * j] = adb[j];
+    red4[wib * NRED * D4 + lane + 32 * j] = adw[j];
+    red4[wib * NRED * D4 + D4 + lane + 32 * j] = adb[j];
+    if (FUSE) red4[wib * NRED * D4 + 2 * D4 + lane + 32 * j] = adg[j];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+  for (int c = threadIdx.x; c < NRED * D; c += blockDim.x) {
     float s = 0.f;
-    for (int ww_ = 0; ww_ < warps_per_block; ++ww_) s += red[ww_ * 2 * D + c];
+    for (int ww_ = 0; ww_ < warps_per_block; ++ww_) s += red[ww_ * NRED * D + c];
     if (c < D) atomicAdd(dw + c, s);
-    else atomicAdd(db + (c - D), s);
+    else if (c < 2 * D) atomicAdd(db + (c - D), s);
+    else if (f.dbias) atomicAdd(f.dbias + (c - 2 * D), s);
   }
 }
 
@@ -432,10 +468,38 @@ extern "C" int x2k_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
   if (grid * warps > M) grid = (M + warps - 1) / warps;
   const size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
   return dispatch_vec(D, [&](auto vec) {
-    auto kern = layernorm_bwd_kernel<decltype(vec)::value>;
+    auto kern = layernorm_bwd_kernel<decltype(vec)::value, false>;
     if (smem > 48 * 1024) X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, w, mean, rstd,
-                                             dx_residual, M, D, dx, dw, db);
+                                             dx_residual, M, D, dx, dw, db, LnFuse{});
+    X2K_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return X2K_OK;
+  });
+}
+
+extern "C" int x2k_layernorm_bwd_dropcast(const void* dy_bf16, const float* dy_f32, const float* x, const float* w,
+                                          const float* mean, const float* rstd, const float* dx_residual, int32_t M,
+                                          int32_t D, float* dx, float* dw, float* db, float dropout_p,
+                                          uint64_t dropout_seed, uint64_t dropout_offset,
+                                          const uint64_t* dropout_offset_dev, void* g_bf16, float* dbias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "x2k_layernorm_bwd_dropcast: dy_bf16 and/or dy_f32 must be given");
+  X2K_REQUIRE(x && w && mean && rstd && dx && dw && db && g_bf16, "x2k_layernorm_bwd_dropcast: NULL argument");
+  X2K_REQUIRE(M > 0 && D % 128 == 0 && D <= 1024, "x2k_layernorm_bwd_dropcast: D=%d must be a multiple of 128, <= 1024", D);
+  X2K_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "x2k_layernorm_bwd_dropcast: dropout_p");
+  const int warps = 8;
+  int grid = sm_count() * 2;
+  if (grid * warps > M) grid = (M + warps - 1) / warps;
+  const size_t smem = static_cast<size_t>(warps) * 3 * D * sizeof(float);
+  LnFuse f;
+  f.dropout_p = dropout_p; f.seed = dropout_seed; f.offset = dropout_offset; f.offset_dev = dropout_offset_dev;
+  f.g = static_cast<__nv_bfloat16*>(g_bf16); f.dbias = dbias;
+  return dispatch_vec(D, [&](auto vec) {
+    auto kern = layernorm_bwd_kernel<decltype(vec)::value, true>;
+    if (smem > 48 * 1024) X2K_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, w, mean, rstd,
+                                             dx_residual, M, D, dx, dw, db, f);
     X2K_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return X2K_OK;

@@ -429,11 +429,12 @@ class _BertLayerFn(torch.autograd.Function):
             return (_zeros(n, dev) if tensor is not None else None), None
 
         # ---- feed-forward ----
+        # LayerNorm backward, dropout mask, bf16 cast and bias-gradient column sum in ONE pass over the rows
         ds3 = torch.empty(M, D, dtype=torch.float32, device=dev)
-        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, P_ln2w.buf, P_ln2b.buf)
         g3 = _empty_bf16(M, D, dev=dev)
         p, seed, off = sv["d_h3"]
-        ops.scale_cast_colsum(ds3, M, D, g_bf16=g3, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_bout.buf)
+        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, P_ln2w.buf, P_ln2b.buf, g_bf16=g3,
+                          dbias=P_bout.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
         dh = _empty_bf16(M, Di, dev=dev)
         ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_MUL_AUX, aux=sv["hpre"], out_bf16=dh)
         wg_out = _wgrad(sh["out"], g3, sv["act"], D, Di, M)
@@ -448,10 +449,10 @@ class _BertLayerFn(torch.autograd.Function):
         if ctx.has_cross:
             n_kv, Nk, Dv = sv["dims_c"]
             ds2 = torch.empty(M, D, dtype=torch.float32, device=dev)
-            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, P_lncw.buf, P_lncb.buf)
             g2 = _empty_bf16(M, D, dev=dev)
             p, seed, off = sv["d_h2"]
-            ops.scale_cast_colsum(ds2, M, D, g_bf16=g2, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_boc.buf)
+            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, P_lncw.buf, P_lncb.buf, g_bf16=g2,
+                              dbias=P_boc.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
             dctx2 = _empty_bf16(M, D, dev=dev)
             ops.gemm(g2, sh["oc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx2)
             wg_oc = _wgrad(sh["oc"], g2, sv["ctx2"], D, D, M)
@@ -487,10 +488,10 @@ class _BertLayerFn(torch.autograd.Function):
             res_f32, res_bf16 = ds3, dxab
         # ---- self-attention ----
         ds1 = torch.empty(M, D, dtype=torch.float32, device=dev)
-        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, P_ln1w.buf, P_ln1b.buf)
         g1 = _empty_bf16(M, D, dev=dev)
         p, seed, off = sv["d_h1"]
-        ops.scale_cast_colsum(ds1, M, D, g_bf16=g1, dropout_p=p, dropout_seed=seed, dropout_offset=off, dbias=P_bo.buf)
+        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, P_ln1w.buf, P_ln1b.buf, g_bf16=g1,
+                          dbias=P_bo.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
         dctx1 = _empty_bf16(M, D, dev=dev)
         ops.gemm(g1, sh["o"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx1)
         wg_o = _wgrad(sh["o"], g1, sv["ctx1"], D, D, M)

@@ -153,14 +153,27 @@ def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):
                                       _stream()), "x2k_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, dx_residual=None):
-    """dy: bf16 or fp32 [M,D], or a (fp32, bf16) pair that is summed; dw/db are accumulated into."""
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db, dx_residual=None, g_bf16=None, dbias=None, dropout_p=0.0, dropout_seed=0,
+                  dropout_offset=0):
+    """dy: bf16 or fp32 [M,D], or a (fp32, bf16) pair that is summed; dw/db are accumulated into.
+    With g_bf16: also g = bf16(dx * dropout keep-scale) and dbias += colsum(dx * keep-scale) in the same pass
+    (x2k_layernorm_bwd_dropcast)."""
     M, D = x.shape
     if isinstance(dy, (tuple, list)):
         dy_f, dy_b = dy
     else:
         dy_b = dy if dy.dtype == torch.bfloat16 else None
         dy_f = dy if dy.dtype == torch.float32 else None
+    if g_bf16 is not None:
+        _req(g_bf16, torch.bfloat16, "g_bf16"); _req(dbias, torch.float32, "dbias")
+        if g_bf16.stride(0) != D:
+            raise C.X2kError("g_bf16 must be contiguous [M, D]")
+        C.check(C.lib().x2k_layernorm_bwd_dropcast(
+            _p(dy_b), _p(dy_f), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_residual), M, D, _p(dx), _p(dw), _p(db),
+            float(dropout_p), int(dropout_seed), int(dropout_offset),
+            _p(dropout_base(x.device)) if dropout_p > 0.0 else None, _p(g_bf16), _p(dbias), _stream()),
+            "x2k_layernorm_bwd_dropcast")
+        return
     C.check(C.lib().x2k_layernorm_bwd(_p(dy_b), _p(dy_f), _p(x), _p(w), _p(mean), _p(rstd), _p(dx_residual), M, D, _p(dx),
                                       _p(dw), _p(db), _stream()), "x2k_layernorm_bwd")
 

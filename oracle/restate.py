@@ -155,22 +155,36 @@ def bert_attention_core(hidden, kv_src, ext_mask, sd, pfx, num_heads, train=Fals
     return ctx, probs
 
 
-def bert_output_ln(h, residual, sd, pfx, train=False, p_hidden=0.1):
-    """LayerNorm(dropout(dense(h)) + residual), eps 1e-12 (models/xbert.py:427-431, :511-515)."""
+def drop_path_scale(L, drop_prob):
+    """xbert's DropPath mask (models/xbert.py:518-535) as a per-position scale [L]: floor(keep + U(0,1)) / keep, ONE
+    draw per sequence position shared by the whole batch (shape (1, L, 1) in the reference).  Consumes torch's global
+    RNG exactly like the reference's torch.rand((1, L, 1))."""
+    keep = 1.0 - drop_prob
+    return torch.floor(keep + torch.rand((1, L, 1))).view(L) / keep
+
+
+def bert_output_ln(h, residual, sd, pfx, train=False, p_hidden=0.1, pos_scale=None):
+    """LayerNorm(drop_path(dropout(dense(h))) + residual), eps 1e-12 (models/xbert.py:427-431, :511-515);
+    pos_scale [L] = the DropPath scale per sequence position (None: DropPath off)."""
     y = F.dropout(F.linear(h, sd[pfx + "dense.weight"], sd[pfx + "dense.bias"]), p_hidden, training=train)
+    if pos_scale is not None:
+        y = y * pos_scale[None, :, None]
     return F.layer_norm(y + residual, (y.shape[-1],), sd[pfx + "LayerNorm.weight"], sd[pfx + "LayerNorm.bias"], 1e-12)
 
 
-def bert_layer(hidden, self_mask, sd, pfx, num_heads, enc_hidden=None, cross_mask=None, train=False):
+def bert_layer(hidden, self_mask, sd, pfx, num_heads, enc_hidden=None, cross_mask=None, train=False, p_attn=0.1, p_hidden=0.1,
+               dp_scales=None):
     """self-attn -> (cross-attn if the layer has one AND encoder states are given) -> FFN
-    (models/xbert.py:566-625)."""
-    ctx, _ = bert_attention_core(hidden, hidden, self_mask, sd, pfx + "attention.self.", num_heads, train)
-    x = bert_output_ln(ctx, hidden, sd, pfx + "attention.output.", train)
+    (models/xbert.py:566-625).  dp_scales: {'self','cross','ffn'} -> per-position DropPath scale [L] of the three
+    output modules (None: off)."""
+    dp = dp_scales or {}
+    ctx, _ = bert_attention_core(hidden, hidden, self_mask, sd, pfx + "attention.self.", num_heads, train, p_attn)
+    x = bert_output_ln(ctx, hidden, sd, pfx + "attention.output.", train, p_hidden, dp.get("self"))
     if enc_hidden is not None and (pfx + "crossattention.self.query.weight") in sd:
-        ctx, _ = bert_attention_core(x, enc_hidden, cross_mask, sd, pfx + "crossattention.self.", num_heads, train)
-        x = bert_output_ln(ctx, x, sd, pfx + "crossattention.output.", train)
+        ctx, _ = bert_attention_core(x, enc_hidden, cross_mask, sd, pfx + "crossattention.self.", num_heads, train, p_attn)
+        x = bert_output_ln(ctx, x, sd, pfx + "crossattention.output.", train, p_hidden, dp.get("cross"))
     inter = F.gelu(F.linear(x, sd[pfx + "intermediate.dense.weight"], sd[pfx + "intermediate.dense.bias"]))
-    return bert_output_ln(inter, x, sd, pfx + "output.", train)
+    return bert_output_ln(inter, x, sd, pfx + "output.", train, p_hidden, dp.get("ffn"))
 
 
 def bert_encoder(hidden, attention_mask, sd, pfx, num_heads, fusion_layer, num_layers, mode="multi_modal",

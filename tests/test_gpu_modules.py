@@ -155,6 +155,53 @@ def test_bert_fusion_layer_backward_vs_oracle(dev):
         assert grad_ok(n, p.grad.cpu(), want, 3e-2), (n, rel_l2(p.grad.cpu(), want))
 
 
+def test_bert_layer_position_drop_path_vs_oracle(dev):
+    """xbert's per-position DropPath (models/xbert.py:518-548) folded into the dense GEMM epilogues as a per-row scale:
+    forward and every gradient against the oracle with the same (pinned) per-position scales; plus the sampled path."""
+    from oracle import restate
+    from x2vlm_b200 import functional as XF, xbert
+    g = torch.load(os.path.join(GOLD, "text_small.pt"))
+    m = _small_text(g, dev)
+    layer = m.bert.encoder.layer[2]
+    gen = torch.Generator().manual_seed(2)
+    B, L, D, Nk = 4, 24, 128, 197
+    x = torch.randn(B, L, D, generator=gen); dy = torch.randn(B, L, D, generator=gen)
+    enc = torch.randn(B, Nk, D, generator=gen)
+    keep = 0.6
+    dp = {k: torch.floor(keep + torch.rand(L, generator=gen)) / keep for k in ("self", "cross", "ffn")}
+    assert all((v == 0).any() and (v > 0).any() for v in dp.values())
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state_dict"].items()}
+    xr, encr = x.clone().requires_grad_(True), enc.clone().requires_grad_(True)
+    yr = restate.bert_layer(xr, None, sd, "bert.encoder.layer.2.", 2, encr, None, dp_scales=dp)
+    yr.backward(dy)
+    cfg = xbert._layer_cfg(m.config, False, None, None, None, B, L, Nk, dev)
+    cfg["n_kv"] = B
+    cfg["drop_path_scales"] = dp
+    xg, encg = x.to(dev).requires_grad_(True), enc.to(dev).requires_grad_(True)
+    y, _ = XF.bert_layer(xg, None, layer, cfg, encg, None)
+    y.backward(dy.to(dev))
+    assert rel_l2(y.detach().cpu(), yr.detach()) < 1e-2
+    assert rel_l2(xg.grad.cpu(), xr.grad) < 3e-2 and rel_l2(encg.grad.cpu(), encr.grad) < 3e-2
+    for n, p in layer.named_parameters():
+        want = sd["bert.encoder.layer.2." + n].grad
+        assert p.grad is not None, n
+        assert grad_ok(n, p.grad.cpu(), want, 3e-2), (n, rel_l2(p.grad.cpu(), want))
+    # sampled path: a layer built with a drop-path rate zeroes whole positions of the branch outputs in train mode
+    c2 = xbert.BertConfig(vocab_size=64, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                          max_position_embeddings=32, attention_probs_dropout_prob=0.0)
+    c2.fusion_layer, c2.encoder_width = 2, 128
+    c2.text_drop_path_rate, c2.cross_drop_path_rate = 0.5, 0.5
+    enc2 = xbert.BertEncoder(c2).to(dev).train()
+    assert c2.hidden_dropout_prob == 0.0 and isinstance(enc2.layer[1].output.drop_path, xbert.DropPath)
+    torch.manual_seed(0)
+    h = torch.randn(3, 16, 128, device=dev)
+    out = enc2(h, mode="text").last_hidden_state
+    assert torch.isfinite(out).all()
+    enc2.eval()
+    o1, o2 = enc2(h, mode="text").last_hidden_state, enc2(h, mode="text").last_hidden_state
+    assert torch.equal(o1, o2) and not torch.allclose(o1, out)
+
+
 @pytest.fixture(scope="module")
 def xvlm_pair(dev):
     """Base-size XVLM (254.76 M parameters) on the GPU + its fp32 state_dict on the CPU for the oracle."""

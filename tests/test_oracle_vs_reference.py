@@ -112,3 +112,34 @@ def test_pretrain_bbox_losses_match_reference(ref, monkeypatch):
                                      is_image=rb["is_image"], ret_bbox_loss=True)
     for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou"):
         assert abs(float(l[k]) - float(l_ref[k])) < 2e-4 * max(1.0, abs(float(l_ref[k]))), k
+
+
+def test_xbert_drop_path_matches_reference():
+    """xbert's per-POSITION DropPath (models/xbert.py:518-548; only configs/finetune/refcoco_grounding_large.yaml turns
+    it on): the reference layer in train mode and the oracle consume the same three torch.rand((1, L, 1)) draws."""
+    ref_shim.install()
+    from models import xbert as rxbert
+    cfg = rxbert.BertConfig(vocab_size=64, hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256,
+                            max_position_embeddings=32, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.0)
+    cfg.fusion_layer, cfg.encoder_width = 1, 128
+    cfg.text_drop_path_rate, cfg.cross_drop_path_rate = 0.4, 0.4
+    torch.manual_seed(3)
+    enc = rxbert.BertEncoder(cfg)
+    assert cfg.hidden_dropout_prob == 0.0                      # the reference zeroes it when drop path is on (:637-640)
+    layer = enc.layer[2]                                        # fusion layer with the full cross rate
+    assert abs(layer.output.drop_path.drop_prob - 0.4) < 1e-6
+    sd = {"l." + k: v.detach() for k, v in layer.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    B, L = 3, 11
+    hidden, img = torch.randn(B, L, 128, generator=g), torch.randn(B, 17, 128, generator=g)
+    layer.train()
+    torch.manual_seed(77)
+    with torch.no_grad():
+        want = layer(hidden, None, None, img, None)[0]
+    torch.manual_seed(77)
+    dp = {k: restate.drop_path_scale(L, 0.4) for k in ("self", "cross", "ffn")}   # same order as the reference's draws
+    assert any((v == 0).any() for v in dp.values()) and any((v > 0).any() for v in dp.values())
+    with torch.no_grad():
+        got = restate.bert_layer(hidden, None, sd, "l.", 2, enc_hidden=img, cross_mask=None, train=True, p_attn=0.0, p_hidden=0.0,
+                                 dp_scales=dp)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)

@@ -330,6 +330,35 @@ def _drop(p, train, n):
     return 0.0, 0, 0
 
 
+def _pos_drop_path(mod, cfg, key, Bt, L, dev):
+    """Per-row scale [Bt*L] of xbert's DropPath on one output module (models/xbert.py:518-535): floor(keep + U)/keep
+    drawn once per sequence position and shared by the batch; None when inactive.  cfg['drop_path_scales'][key] may
+    pin the [L] scale (tests)."""
+    rate = getattr(getattr(mod, "drop_path", None), "drop_prob", None) or 0.0
+    pinned = (cfg.get("drop_path_scales") or {}).get(key)
+    if pinned is not None:
+        scale = pinned.to(device=dev, dtype=torch.float32)
+    elif cfg["train"] and rate > 0.0:
+        keep = 1.0 - rate
+        scale = torch.floor(keep + torch.rand(L, device=dev)) / keep
+    else:
+        return None
+    return scale.repeat(Bt).contiguous()  # row m = b*L + l
+
+
+def _dense_bwd(dy, s_in, lnw, mean, rstd, ds, P_lnw, P_lnb, g, dbias, drop, dp_rows, M, D):
+    """Backward of LayerNorm(drop_path(dropout(dense(h))) + residual) up to the dense output: ds = LN'(dy) (the
+    residual-stream gradient) and g = bf16(ds * dropout keep-scale * drop-path row scale), dbias += colsum(g)."""
+    p, seed, off = drop
+    if dp_rows is None:  # one fused pass
+        ops.layernorm_bwd(dy, s_in, lnw, mean, rstd, ds, P_lnw.buf, P_lnb.buf, g_bf16=g, dbias=dbias, dropout_p=p,
+                          dropout_seed=seed, dropout_offset=off)
+    else:
+        ops.layernorm_bwd(dy, s_in, lnw, mean, rstd, ds, P_lnw.buf, P_lnb.buf)
+        ops.scale_cast_colsum(ds, M, D, g_bf16=g, row_scale=dp_rows, rows_per_scale=1, dropout_p=p, dropout_seed=seed,
+                              dropout_offset=off, dbias=dbias)
+
+
 class _BertLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, xb, enc, encb, layer, cfg, b_qkv, b_o, ln1w, ln1b, b_qc, b_kvc, b_oc, lncw, lncb, b_i, b_out, ln2w,
@@ -356,8 +385,9 @@ class _BertLayerFn(torch.autograd.Function):
                      mask_per_query=cfg["self_mask_3d"], dropout_p=d_a1[0], dropout_seed=d_a1[1], dropout_offset=d_a1[2])
         s1 = torch.empty(M, D, dtype=torch.float32, device=dev)
         d_h1 = _drop(p_h, train, M * D)
+        dp1 = _pos_drop_path(layer.attention.output, cfg, "self", Bt, L, dev)
         ops.gemm(ctx1, sh["o"].get(), M, D, D, bias=b_o, dropout_p=d_h1[0], dropout_seed=d_h1[1], dropout_offset=d_h1[2],
-                 residual=x2, out_f32=s1)
+                 row_scale=dp1, rows_per_scale=1, residual=x2, out_f32=s1)
         x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
         x1b = _empty_bf16(M, D, dev=dev)
         m1, r1 = torch.empty(M, device=dev), torch.empty(M, device=dev)
@@ -377,14 +407,15 @@ class _BertLayerFn(torch.autograd.Function):
                          kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"], dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
             s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
             d_h2 = _drop(p_h, train, M * D)
+            dp2 = _pos_drop_path(layer.crossattention.output, cfg, "cross", Bt, L, dev)
             ops.gemm(ctx2, sh["oc"].get(), M, D, D, bias=b_oc, dropout_p=d_h2[0], dropout_seed=d_h2[1],
-                     dropout_offset=d_h2[2], residual=x1, out_f32=s2)
+                     dropout_offset=d_h2[2], row_scale=dp2, rows_per_scale=1, residual=x1, out_f32=s2)
             xa = torch.empty(M, D, dtype=torch.float32, device=dev)
             xab = _empty_bf16(M, D, dev=dev)
             mc, rc = torch.empty(M, device=dev), torch.empty(M, device=dev)
             ops.layernorm_fwd(s2, lncw, lncb, eps, y_bf16=xab, y_f32=xa, mean=mc, rstd=rc)
             sv.update(enc2=enc2, qc=qc, kvc=kvc, ctx2=ctx2, lse2=lse2, s2=s2, mc=mc, rc=rc, d_a2=d_a2, d_h2=d_h2,
-                      dims_c=(n_kv, Nk, Dv))
+                      dims_c=(n_kv, Nk, Dv), dp2=dp2)
         else:
             xa, xab = x1, x1b
         # ---- feed-forward ----
@@ -394,14 +425,15 @@ class _BertLayerFn(torch.autograd.Function):
         ops.gemm(xab, sh["i"].get(), M, Di, D, bias=b_i, preact_out=hpre, act=ACT_GELU_SAVE_GRAD, out_bf16=act)  # hpre = GELU''
         s3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         d_h3 = _drop(p_h, train, M * D)
+        dp3 = _pos_drop_path(layer.output, cfg, "ffn", Bt, L, dev)
         ops.gemm(act, sh["out"].get(), M, D, Di, bias=b_out, dropout_p=d_h3[0], dropout_seed=d_h3[1], dropout_offset=d_h3[2],
-                 residual=xa, out_f32=s3)
+                 row_scale=dp3, rows_per_scale=1, residual=xa, out_f32=s3)
         y = torch.empty(M, D, dtype=torch.float32, device=dev)
         yb = _empty_bf16(M, D, dev=dev)
         m3, r3 = torch.empty(M, device=dev), torch.empty(M, device=dev)
         ops.layernorm_fwd(s3, ln2w, ln2b, eps, y_bf16=yb, y_f32=y, mean=m3, rstd=r3)
         sv.update(xb2=xb2, qkv=qkv, ctx1=ctx1, lse1=lse1, s1=s1, m1=m1, r1=r1, x1b=x1b, xab=xab, hpre=hpre, act=act, s3=s3,
-                  m3=m3, r3=r3, d_a1=d_a1, d_h1=d_h1, d_h3=d_h3, ln1w=ln1w, lncw=lncw, ln2w=ln2w)
+                  m3=m3, r3=r3, d_a1=d_a1, d_h1=d_h1, d_h3=d_h3, ln1w=ln1w, lncw=lncw, ln2w=ln2w, dp1=dp1, dp3=dp3)
         ctx.sv, ctx.layer, ctx.cfg, ctx.has_cross = sv, layer, cfg, has_cross
         ctx.P = (b_o, ln1w, ln1b, b_qc, b_oc, lncw, lncb, b_i, b_out, ln2w, ln2b)
         ctx.packed_bias = (b_qkv, b_kvc)
@@ -432,9 +464,7 @@ class _BertLayerFn(torch.autograd.Function):
         # LayerNorm backward, dropout mask, bf16 cast and bias-gradient column sum in ONE pass over the rows
         ds3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         g3 = _empty_bf16(M, D, dev=dev)
-        p, seed, off = sv["d_h3"]
-        ops.layernorm_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, P_ln2w.buf, P_ln2b.buf, g_bf16=g3,
-                          dbias=P_bout.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
+        _dense_bwd(dy2, sv["s3"], sv["ln2w"], sv["m3"], sv["r3"], ds3, P_ln2w, P_ln2b, g3, P_bout.buf, sv["d_h3"], sv["dp3"], M, D)
         dh = _empty_bf16(M, Di, dev=dev)
         ops.gemm(g3, sh["out"].get_nograd(), M, Di, D, b_mn=True, act=ACT_MUL_AUX, aux=sv["hpre"], out_bf16=dh)
         wg_out = _wgrad(sh["out"], g3, sv["act"], D, Di, M)
@@ -450,9 +480,8 @@ class _BertLayerFn(torch.autograd.Function):
             n_kv, Nk, Dv = sv["dims_c"]
             ds2 = torch.empty(M, D, dtype=torch.float32, device=dev)
             g2 = _empty_bf16(M, D, dev=dev)
-            p, seed, off = sv["d_h2"]
-            ops.layernorm_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, P_lncw.buf, P_lncb.buf, g_bf16=g2,
-                              dbias=P_boc.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
+            _dense_bwd((ds3, dxab), sv["s2"], sv["lncw"], sv["mc"], sv["rc"], ds2, P_lncw, P_lncb, g2, P_boc.buf, sv["d_h2"],
+                       sv["dp2"], M, D)
             dctx2 = _empty_bf16(M, D, dev=dev)
             ops.gemm(g2, sh["oc"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx2)
             wg_oc = _wgrad(sh["oc"], g2, sv["ctx2"], D, D, M)
@@ -489,9 +518,8 @@ class _BertLayerFn(torch.autograd.Function):
         # ---- self-attention ----
         ds1 = torch.empty(M, D, dtype=torch.float32, device=dev)
         g1 = _empty_bf16(M, D, dev=dev)
-        p, seed, off = sv["d_h1"]
-        ops.layernorm_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, P_ln1w.buf, P_ln1b.buf, g_bf16=g1,
-                          dbias=P_bo.buf, dropout_p=p, dropout_seed=seed, dropout_offset=off)
+        _dense_bwd((res_f32, res_bf16), sv["s1"], sv["ln1w"], sv["m1"], sv["r1"], ds1, P_ln1w, P_ln1b, g1, P_bo.buf, sv["d_h1"],
+                   sv["dp1"], M, D)
         dctx1 = _empty_bf16(M, D, dev=dev)
         ops.gemm(g1, sh["o"].get_nograd(), M, D, D, b_mn=True, out_bf16=dctx1)
         wg_o = _wgrad(sh["o"], g1, sv["ctx1"], D, D, M)

@@ -18,6 +18,8 @@ Generation paths (`history_states` of the captioning beam search, model_generati
 kernels (x2vlm_b200.functional.bert_layer_decode) and refuse to record an autograd graph.
 
 Not built (raise NotImplementedError): head pruning / head_mask, output_attentions, split_lengths.
+xbert's per-position DropPath (text_drop_path_rate / cross_drop_path_rate, refcoco_grounding_large.yaml) is folded into
+the dense GEMM epilogues as a per-row scale.
 """
 import math
 
@@ -90,10 +92,24 @@ class BertSelfAttention(nn.Module):
         self.save_attention = False
 
 
-def _check_drop_path(rate):
-    if rate > 1e-3:
-        # only configs/finetune/refcoco_grounding_large.yaml sets text/cross drop path
-        raise NotImplementedError("xbert per-position DropPath (text_drop_path_rate > 0) is not on the fused path yet")
+class DropPath(nn.Module):
+    """xbert's stochastic depth (models/xbert.py:518-548): unlike timm's per-sample version the random mask has shape
+    (1, L, 1) — one draw per sequence POSITION, shared by the whole batch.  The fused layer reads `drop_prob` and
+    folds the mask into the dense GEMM's epilogue (per-row scale); `forward` is the plain-torch definition."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if not self.drop_prob or not self.training:
+            return x
+        keep_prob = 1 - self.drop_prob
+        mask = torch.floor(keep_prob + torch.rand((1, x.shape[1], 1), dtype=x.dtype, device=x.device))
+        return x.div(keep_prob) * mask
+
+    def extra_repr(self):
+        return "p={}".format(self.drop_prob)
 
 
 class BertSelfOutput(nn.Module):
@@ -102,8 +118,7 @@ class BertSelfOutput(nn.Module):
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
         self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
-        _check_drop_path(drop_path_rate)
-        self.drop_path = nn.Identity()
+        self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 1e-3 else nn.Identity()
 
 
 class BertAttention(nn.Module):
@@ -128,8 +143,7 @@ class BertOutput(nn.Module):
         self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
         self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
-        _check_drop_path(drop_path_rate)
-        self.drop_path = nn.Identity()
+        self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 1e-3 else nn.Identity()
 
 
 class BertLayer(nn.Module):

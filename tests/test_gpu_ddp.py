@@ -48,6 +48,9 @@ def _worker(rank, world, port, q):
     want /= world
     got, order = run(True)
     err = ((got - want).norm() / want.norm()).item()
+    g0 = got.clone()
+    dist.broadcast(g0, 0)
+    assert torch.equal(g0, got), "all-reduced gradients must be bit-identical on every rank"
     # params were broadcast from rank 0: flat buffers identical across ranks
     flat0 = acc.arena.flat.clone()
     dist.broadcast(flat0, 0)
@@ -67,5 +70,7 @@ def test_bucketed_allreduce_nccl_2gpu():
     [p.join(60) for p in procs]
     for rank, err, same, n_buckets, first, nonzero in res:
         assert nonzero and same, res
-        assert err < 1e-4, res                    # fp32 sum of two ranks, then x0.5: equal up to atomics / split-K order
+        # `want` comes from a SECOND backward pass: split-K / column-sum atomics reorder fp32 sums by ~1e-7, which flips
+        # a few bf16 roundings downstream (tools/check_determinism.py: 1e-4 .. 8e-4 between identical passes on one GPU)
+        assert err < 5e-3, res
         assert n_buckets >= 15 and first > n_buckets // 2, res   # later parameters' buckets are reduced first (overlap)

@@ -163,10 +163,18 @@ def run_ours(args):
         st.record()
         last = None
         t_host = time.perf_counter()
-        for _ in range(n):
+        host_batch = {"i": ib_h, "r": rb_h} if rb_h is not None else {"i": ib_h}
+        if e2e and graphed is not None:
+            graphed.stage(host_batch)  # step 0's inputs: this copy is exposed, the later ones overlap the previous replay
+        for it in range(n):
             if e2e:
-                if graphed is not None:  # pinned host batch -> the graph's static device buffers -> replay -> loss read
-                    last = step(ib_h, rb_h, True)
+                if graphed is not None:
+                    # every step: pinned host batch -> staging buffers (copy stream, prefetched during the previous
+                    # replay like a data loader would) -> the graph's static buffers -> replay -> loss read on the host
+                    loss_t = graphed.run_staged()
+                    if it + 1 < n:
+                        graphed.stage(host_batch)
+                    last = float(loss_t)
                 else:
                     last = step(to_dev(ib_h, dev), to_dev(rb_h, dev) if rb_h is not None else None, True)
             else:

@@ -260,6 +260,32 @@ class GraphedStep:
             base.add_(self.dropout_offsets_per_step)
         self.replays = 0
 
+    # -- input prefetch: the next batch's host-to-device copy overlaps the current replay ---------------------------
+    def stage(self, inputs):
+        """Start copying `inputs` (pinned host tensors) into a second set of device buffers on a copy stream; returns
+        immediately.  `run_staged()` then moves them into the graph's static buffers (device-to-device) and replays."""
+        if getattr(self, "_staging", None) is None:
+            self._staging = self._clone_tree(self.static_in)
+            self._flat_staging = _flatten(self._staging)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staged_evt = torch.cuda.Event()
+            self._consumed_evt = None
+        if self._consumed_evt is not None:  # the previous batch has left the staging buffers
+            self._copy_stream.wait_event(self._consumed_evt)
+        with torch.cuda.stream(self._copy_stream):
+            for path, t in _flatten(inputs).items():
+                self._flat_staging[path].copy_(t, non_blocking=True)
+            self._staged_evt.record(self._copy_stream)
+
+    def run_staged(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged_evt)
+        for path, t in self._flat_staging.items():
+            self._flat_in[path].copy_(t, non_blocking=True)
+        self._consumed_evt = torch.cuda.Event()
+        self._consumed_evt.record(cur)
+        return self.__call__(None)
+
     def release(self):
         """Destroy the captured graph (NCCL will not tear a communicator down while a graph still holds its kernels)."""
         self.static_out = None

@@ -108,8 +108,11 @@ def _wgrad(shadow, dy_bf16, x_bf16, n_out, n_in, rows):
 # ----------------------------------------------------------------------------------------------
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bias, shadow, gelu, out_bf16, *weights):
-        # x: [M, K] fp32 or bf16; weights only listed so autograd tracks them
+    def forward(ctx, x, bias, shadow, gelu, out_bf16, pad_value, *weights):
+        # x: [M, K] fp32 or bf16; weights only listed so autograd tracks them.  pad_value (float or None): when the
+        # output width N is not a multiple of 8 the kernel writes rows of ld = pad8(N) elements; with pad_value the
+        # PADDED [M, ld] tensor is returned, its extra columns filled (e.g. -inf for logits that go straight into a
+        # softmax / cross entropy) — no compaction copy forward, no re-padding copy backward.
         dev = x.device
         M, K = x.shape
         N = shadow.total_rows
@@ -127,7 +130,11 @@ class _LinearFn(torch.autograd.Function):
             ops.gemm(xb, w, M, N, K, bias=bias, act=ACT_GELU_SAVE_GRAD if gelu else ACT_NONE, preact_out=pre, out_f32=y)
         ctx.shadow, ctx.gelu, ctx.dims, ctx.x_dtype = shadow, gelu, (M, N, K, ld), x.dtype
         ctx.has_bias = bias is not None
+        ctx.padded_out = pad_value is not None and ld != N
         ctx.save_for_backward(xb, pre)
+        if ctx.padded_out:
+            y[:, N:].fill_(pad_value)
+            return y
         return y[:, :N] if ld != N else y
 
     @staticmethod
@@ -137,7 +144,10 @@ class _LinearFn(torch.autograd.Function):
         dev = dy.device
         shadow = ctx.shadow
         # dy -> bf16 [M, ld] (zero padded columns)
-        if ld != N:
+        if ctx.padded_out:  # dy is already [M, ld]; its pad columns carry no gradient by construction of the caller
+            dyb = ops.to_bf16(dy.float() if dy.dtype != torch.float32 else dy)
+            dyb[:, N:].zero_()
+        elif ld != N:
             dyb = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
             dyb[:, :N].copy_(dy)
         elif dy.dtype == torch.bfloat16 and dy.is_contiguous():
@@ -163,13 +173,14 @@ class _LinearFn(torch.autograd.Function):
                 dx = torch.empty(M, K, dtype=torch.float32, device=dev)
                 ops.gemm(dyb, w, M, K, N, b_mn=True, out_f32=dx)
         wg = _wgrad(shadow, dyb, xb, N, K, M)
-        return (dx, dbias, None, None, None, *wg)
+        return (dx, dbias, None, None, None, None, *wg)
 
 
-def linear(x, shadow, bias=None, gelu=False, out_bf16=False):
-    """y[M,N] = act(x[M,K] · Wᵀ + b) on the tcgen05 GEMM; x fp32 or bf16, W given by its Shadow."""
+def linear(x, shadow, bias=None, gelu=False, out_bf16=False, pad_value=None):
+    """y[M,N] = act(x[M,K] · Wᵀ + b) on the tcgen05 GEMM; x fp32 or bf16, W given by its Shadow.  With pad_value the
+    result is [M, pad8(N)] and the extra columns hold pad_value (see _LinearFn.forward)."""
     _note_uses(shadow)
-    return _LinearFn.apply(x, bias, shadow, gelu, out_bf16, *shadow.params)
+    return _LinearFn.apply(x, bias, shadow, gelu, out_bf16, pad_value, *shadow.params)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -440,6 +451,7 @@ class _BertLayerFn(torch.autograd.Function):
         ctx.dims = (Bt, L, D, H, Di, scale)
         ctx.enc_needs_grad = has_cross and enc.requires_grad
         ctx.mark_non_differentiable(yb)
+        ctx.set_materialize_grads(False)  # no zero-filled [Bt, L, D] gradient for the non-differentiable bf16 copy
         return y.view(Bt, L, D), yb.view(Bt, L, D)
 
     @staticmethod

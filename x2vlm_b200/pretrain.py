@@ -350,11 +350,17 @@ class XVLM(nn.Module):
                 coord, rb["target_bbox"], is_image=rb["is_image"])
         # ---- MLM head once over the masked positions of both sub-batches ----
         seq = self.text_encoder.gather_seq_out_by_pos(torch.cat(mlm_seq), torch.cat(mpos))
-        logits = self.text_encoder.cls(seq)
-        V = logits.shape[-1]
-        losses["image"]["loss_mlm"] = F.cross_entropy(logits[:Bi].reshape(-1, V), mids[0].reshape(-1))
+        logits_p = self.text_encoder.cls.predictions(seq, padded=True)   # [B, n, pad8(V)], columns beyond V are -inf
+        Vp = logits_p.shape[-1]
+        logits = logits_p[..., :self.text_encoder.config.vocab_size]
+        # ONE cross entropy over all masked positions (per-row losses), then the two means: slicing the 30k-wide logits
+        # per sub-batch would make autograd materialise and add two full-size zero-padded gradients
+        tgt = torch.cat(mids).reshape(-1)
+        ce = F.cross_entropy(logits_p.reshape(-1, Vp), tgt, reduction='none')   # 0 where the target is -100
+        n_i = mids[0].numel()
+        losses["image"]["loss_mlm"] = ce[:n_i].sum() / (tgt[:n_i] != -100).sum()
         if has_r:
-            losses["region"]["loss_mlm"] = F.cross_entropy(logits[Bi:].reshape(-1, V), mids[1].reshape(-1))
+            losses["region"]["loss_mlm"] = ce[n_i:].sum() / (tgt[n_i:] != -100).sum()
         if out is not None:
             out.update(image_embeds=emb_i, text_embeds=te_i, image_feat=fi_i, text_feat=ft_i, itm_logits=itm_logits_i,
                        mlm_logits=logits[:Bi], cross=cross)

@@ -374,10 +374,14 @@ class BertLMPredictionHead(nn.Module):
             self._x2k_shadows = [self._shadow]
         return self._shadow
 
-    def forward(self, hidden_states):
+    def forward(self, hidden_states, padded=False):
+        """Logits [..., vocab_size]; with padded=True the kernel's own row layout [..., pad8(vocab_size)] whose extra
+        columns are -inf — a softmax / cross entropy over it equals the one over vocab_size classes, and neither a
+        compaction copy of the 30522-wide logits (forward) nor a re-padding copy of their gradient (backward) is
+        needed."""
         h = self.transform(hidden_states)
         shp = h.shape
-        logits = XF.linear(h.reshape(-1, shp[-1]), self._decoder_shadow(), self.bias)
+        logits = XF.linear(h.reshape(-1, shp[-1]), self._decoder_shadow(), self.bias, pad_value=float("-inf") if padded else None)
         return logits.reshape(*shp[:-1], -1)
 
 
@@ -687,12 +691,13 @@ class BertForMaskedLM(BertPreTrainedModel):
         if masked_pos is None:
             raise NotImplementedError("need check!")  # as in the reference (xbert.py:1650)
         sequence_output = self.gather_seq_out_by_pos(sequence_output, masked_pos)
-        prediction_scores = self.cls(sequence_output)
+        padded_scores = self.cls.predictions(sequence_output, padded=True)       # [B, n, pad8(V)], -inf beyond V
+        prediction_scores = padded_scores[..., :self.config.vocab_size]
         if return_logits:
             return prediction_scores
         masked_lm_loss = None
         if labels is not None:
-            masked_lm_loss = F.cross_entropy(prediction_scores.view(-1, self.config.vocab_size), labels.view(-1))
+            masked_lm_loss = F.cross_entropy(padded_scores.view(-1, padded_scores.shape[-1]), labels.view(-1))
         if not return_dict:
             output = (prediction_scores,) + outputs[2:]
             return ((masked_lm_loss,) + output) if masked_lm_loss is not None else output

@@ -393,7 +393,9 @@ def run_reference(args):
         "impl": "reference", "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": dt / n * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok; CPU sample", "sample": sample},
+        "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; random-init weights"
+                               % (args.batch, " image iteration only" if args.image_only else ""),
+                   "sample": sample, "seq_len": 40, "image_res": 224, "optimizer": "AdamW + clip 1.0 (torch)"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 

@@ -218,6 +218,27 @@ def run_ours(args):
     burst, sustained, hbm, src = peaks()
     step_tflops = flop_step_gpu * args.steps / (ms / 1e3) / 1e12  # per GPU (ms is the max over ranks)
 
+    # image-only variant (64 pairs, 14.79 TFLOP / step): one more captured graph, N = 1 only
+    image_only = None
+    if world == 1 and rb_h is not None and graphed is not None and not args.skip_image_only:
+        try:
+            g_img = acc.graph_step(lambda inp: eager_step(inp["i"], None, False), {"i": ib_d}, optimizer=opt, warmup=2)
+            for _ in range(2):
+                g_img({"i": ib_d})
+            torch.cuda.synchronize()
+            st_i, en_i = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st_i.record()
+            for _ in range(args.steps):
+                g_img({"i": ib_d})
+            en_i.record()
+            torch.cuda.synchronize()
+            ms_i = st_i.elapsed_time(en_i) / args.steps
+            image_only = {"ms_per_step": ms_i, "pairs_per_s": B / (ms_i / 1e3),
+                          "step_tflops": B * FLOP_IMAGE_PAIR / (ms_i / 1e3) / 1e12}
+            g_img.release()
+        except Exception as e:
+            sys.stderr.write("[bench] image-only variant skipped: %r\n" % (e,))
+
     roof = dominant_kernel_roofline(lambda: eager_step(ib_d, rb_d, False), sustained, src,  # every rank steps (collectives)
                                     table_path=args.kernel_table if rank == 0 else None)
     out = None
@@ -240,7 +261,8 @@ def run_ours(args):
                                       "nodes per replay x steps" if graphed is not None else "off (eager launches)"),
                        "algorithmic_tflop_per_step_per_gpu": flop_step_gpu / 1e12,
                        "step_tflops_per_gpu": step_tflops,
-                       "step_frac_of_%s_sustained_bf16_peak" % src: step_tflops / sustained},
+                       "step_frac_of_%s_sustained_bf16_peak" % src: step_tflops / sustained,
+                       "image_iteration_only": image_only},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nbytes(ib_h) + (nbytes(rb_h) if rb_h is not None else 0), "d2h_bytes_per_step": 4,
                     "loss_last_step": loss_e},
@@ -412,6 +434,7 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=48.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--skip-image-only", action="store_true", help="do not also time the image-iteration-only step (N = 1)")
     ap.add_argument("--kernel-table", default=None, help="write the per-shape GEMM / attention timing table (markdown) here")
     ap.add_argument("--profile", action="store_true", help="one step inside cudaProfilerStart/Stop, no JSON (for ncu)")
     args = ap.parse_args()

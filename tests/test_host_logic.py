@@ -197,3 +197,32 @@ def test_generation_surface_on_cpu():
     assert abs(float(got) - float(want)) < 1e-6
     out = m.prepare_inputs_for_generation(torch.ones(2, 5, dtype=torch.long), past=((None,),))
     assert out["input_ids"].shape == (2, 1) and out["is_decoder"] is True
+
+
+def _retrieval_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from x2vlm_b200 import retrieval
+    n = 7
+    full = torch.arange(n * 5, dtype=torch.float32).view(n, 5) - 10.0
+    full[2, 3] = -100.0
+    start, end, w = retrieval._rank_slice(n)          # step = 7 // 2 + 1 = 4: rank 0 rows 0-3, rank 1 rows 4-6
+    mine = torch.full((n, 5), -100.0)
+    mine[start:end] = full[start:end]
+    retrieval.combine_rank_rows(mine)
+    q.put((rank, (start, end, w), bool(torch.equal(mine, full))))
+    dist.destroy_process_group()
+
+
+def test_retrieval_rank_partition_gloo_world2():
+    """Rows split over 2 processes like Retrieval.py:120-123 and recombined on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 200
+    procs = [ctx.Process(target=_retrieval_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(30) for p in procs]
+    assert res[0][1] == (0, 4, 2) and res[1][1] == (4, 7, 2)
+    assert res[0][2] and res[1][2]

@@ -80,14 +80,25 @@ def rerank(model, image_embeds, text_embeds, text_atts, sims_matrix, k_test, row
                                      encoder_kv_index=inv.to(torch.int32))
         score_t2i[r0:r1].scatter_(1, topk_idx, itm(out).view(r1 - r0, k_t2i))
 
-    if reduce and world > 1:  # every rank filled its own rows; the others still hold -100 there (Retrieval.py:145-148)
-        for m, (s, e) in ((score_i2t, _rank_slice(n_img)[:2]), (score_t2i, _rank_slice(n_txt)[:2])):
-            mask = torch.zeros(m.shape[0], 1, device=dev)
-            mask[s:e] = 1
-            filled = torch.where(mask.bool(), m, torch.zeros_like(m))
-            dist.all_reduce(filled, op=dist.ReduceOp.SUM)
-            m.copy_(filled)
+    if reduce and world > 1:
+        combine_rank_rows(score_i2t)
+        combine_rank_rows(score_t2i)
     return score_i2t, score_t2i
+
+
+def combine_rank_rows(scores):
+    """Every process scored the rows of its _rank_slice; put the full matrix on all of them.  (The reference SUM-
+    all-reduces matrices pre-filled with -100, Retrieval.py:145-148, which shifts every entry by -100·(W-1); here the
+    rows a rank did not own contribute 0, so entries keep their single-process values, -100 included.)"""
+    start, end, world = _rank_slice(scores.shape[0])
+    if world == 1:
+        return scores
+    own = torch.zeros(scores.shape[0], 1, dtype=torch.bool, device=scores.device)
+    own[start:end] = True
+    filled = torch.where(own, scores, torch.zeros_like(scores))
+    dist.all_reduce(filled, op=dist.ReduceOp.SUM)
+    scores.copy_(filled)
+    return scores
 
 
 @torch.no_grad()

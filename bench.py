@@ -271,7 +271,7 @@ def run_ours(args):
         if cpu is not None:
             out["cpu_baseline"] = cpu
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     teardown(graphed, world)
 
 
@@ -411,7 +411,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = pairs * n / dt
     sample = "each step = mixed step on %d image + %d region pairs (bounded sample of the batch-64 workload), fp32, %d threads" % (bi, br, threads)
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": dt / n * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -419,10 +419,34 @@ def run_reference(args):
                                % (args.batch, " image iteration only" if args.image_only else ""),
                    "sample": sample, "seq_len": 40, "image_res": 224, "optimizer": "AdamW + clip 1.0 (torch)"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set, as it is on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

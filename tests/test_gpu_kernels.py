@@ -407,3 +407,26 @@ def test_flat_adamw_matches_torch(dev):
     assert torch.equal(pb, p.bfloat16())
     out = torch.zeros(1, device=dev); ops.sumsq(p, out)
     assert abs(out.item() - (p.double() ** 2).sum().item()) < 1e-4 * out.item()
+
+
+def test_attention_rejects_long_keys(dev):
+    """Maximum size: Lk <= 256 keys fit the single-pass TMEM softmax; longer sequences (384 px fine-tuning: 577 patches)
+    must fail loudly — X2K_ERR_* with a message — never fall back or truncate."""
+    from x2vlm_b200 import ops
+    from x2vlm_b200._capi import X2kError
+    B, H, L = 2, 2, 300
+    q = torch.randn(B * L, 3 * H * 64, device=dev).bfloat16()
+    o = torch.empty(B * L, H * 64, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, L, device=dev)
+    with pytest.raises(X2kError):
+        ops.attn_fwd(q[:, :H * 64], q[:, H * 64:2 * H * 64], q[:, 2 * H * 64:], B, H, L, L, 0.125, o, lse)
+    # the largest supported shape still runs: 256 queries x 256 keys
+    L = 256
+    q = torch.randn(B * L, 3 * H * 64, device=dev).bfloat16()
+    o = torch.empty(B * L, H * 64, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, L, device=dev)
+    ops.attn_fwd(q[:, :H * 64], q[:, H * 64:2 * H * 64], q[:, 2 * H * 64:], B, H, L, L, 0.125, o, lse)
+    qh, kh, vh = (_heads(q[:, i * H * 64:(i + 1) * H * 64].float(), B, L, H) for i in range(3))
+    ref, _ = _attn_ref(qh, kh, vh, 0.125)
+    got = _heads(o.float(), B, L, H)
+    assert (got - ref).abs().max() < 0.03

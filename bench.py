@@ -130,7 +130,7 @@ def run_ours(args):
         acc.backward_step(loss, opt)
         acc.optimizer_step(opt, ddp, 1.0)
         opt.step()
-        return float(loss) if read_loss else loss
+        return float(loss.detach()) if read_loss else loss
 
     host_ms = [0.0]
 
@@ -152,7 +152,7 @@ def run_ours(args):
     if graphed is not None:
         def step(ib, rb, read_loss):  # noqa: F811  (same signature; inputs are copied into the graph's static buffers)
             loss = graphed({"i": ib, "r": rb} if rb is not None else {"i": ib})
-            return float(loss) if read_loss else loss
+            return float(loss.detach()) if read_loss else loss
 
     def timed(n, e2e):
         if world > 1:
@@ -189,7 +189,7 @@ def run_ours(args):
         launched = ops.launch_count() - l0
         if graphed is not None:  # replayed kernel nodes never pass through the library's host-side launch counter
             launched = graphed.x2k_launches_per_step * n
-        return ms.item(), launched, float(last)
+        return ms.item(), launched, float(last.detach()) if torch.is_tensor(last) else float(last)
 
     ib_d, rb_d = to_dev(ib_h, dev), (to_dev(rb_h, dev) if rb_h is not None else None)
     if args.profile:

@@ -226,3 +226,53 @@ def test_retrieval_rank_partition_gloo_world2():
     [p.join(30) for p in procs]
     assert res[0][1] == (0, 4, 2) and res[1][1] == (4, 7, 2)
     assert res[0][2] and res[1][2]
+
+
+def test_beit2_checkpoint_helpers(tmp_path):
+    """load_pretrained_beit2 / interpolate_pos_embed / load_state_dict (models/beit2.py:473-754) on CPU."""
+    from functools import partial
+    from x2vlm_b200 import beit2
+    mk = lambda res: beit2.VisionTransformer(img_size=res, patch_size=16, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4,
+                                             norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), use_rel_pos_bias=True,
+                                             use_abs_pos_emb=False, init_values=0.1, qkv_bias=True)
+    src = mk(224)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    # BEiT-2 release layout: wrapped in 'model', classification head, ONE shared rel-pos table
+    ckpt = {k: v for k, v in sd.items() if "relative_position_bias_table" not in k}
+    ckpt["rel_pos_bias.relative_position_bias_table"] = sd["blocks.0.attn.relative_position_bias_table"].clone()
+    ckpt["head.weight"], ckpt["head.bias"] = torch.zeros(10, 128), torch.zeros(10)
+    path = tmp_path / "beit2.pth"
+    torch.save({"model": ckpt}, path)
+    # same resolution: every tensor arrives unchanged, the index buffer is rebuilt by the model, the head is dropped
+    dst = mk(224)
+    missing, unexpected, ignored = beit2.load_pretrained_beit2(dst, str(path))
+    assert missing == [] and unexpected == [] and all("relative_position_index" in k for k in ignored)
+    for k, v in dst.state_dict().items():
+        want = sd["blocks.0.attn.relative_position_bias_table"] if "relative_position_bias_table" in k else sd[k]
+        assert torch.equal(v, want), k
+    # 224 -> 384: 27x27 (+3) tables become 47x47 (+3)
+    big = mk(384)
+    sd2 = beit2.interpolate_pos_embed(big, {k: v.clone() for k, v in sd.items()})
+    assert not any("relative_position_index" in k for k in sd2)
+    t_src, t_dst = sd["blocks.1.attn.relative_position_bias_table"], sd2["blocks.1.attn.relative_position_bias_table"]
+    assert t_src.shape == (27 * 27 + 3, 2) and t_dst.shape == (47 * 47 + 3, 2)
+    assert torch.equal(t_dst[-3:], t_src[-3:])                       # cls rows are copied
+    # an interpolating spline reproduces the source where target offsets coincide with source offsets: 0 and +-1
+    s_img, d_img = t_src[:-3, 0].view(27, 27), t_dst[:-3, 0].view(47, 47)
+    for a in (-1, 0, 1):
+        for b in (-1, 0, 1):
+            assert abs(float(d_img[23 + a, 23 + b]) - float(s_img[13 + a, 13 + b])) < 1e-4
+    assert float(d_img.abs().max()) < 3 * float(s_img.abs().max())   # no wild overshoot
+    missing, unexpected, _ = beit2.load_state_dict(big, sd2)
+    assert missing == [] and unexpected == []
+    # absolute position embedding: bicubic resize of the patch grid, cls token kept
+    pe = mk(224)
+    pe.pos_embed = torch.nn.Parameter(torch.zeros(1, 197, 128))
+    pe_big = mk(384)
+    pe_big.pos_embed = torch.nn.Parameter(torch.zeros(1, 577, 128))
+    out = beit2.interpolate_pos_embed(pe_big, {"pos_embed": torch.randn(1, 197, 128, generator=g)})
+    assert out["pos_embed"].shape == (1, 577, 128)

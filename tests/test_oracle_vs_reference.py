@@ -143,3 +143,20 @@ def test_xbert_drop_path_matches_reference():
         got = restate.bert_layer(hidden, None, sd, "l.", 2, enc_hidden=img, cross_mask=None, train=True, p_attn=0.0, p_hidden=0.0,
                                  dp_scales=dp)
     assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+def test_interpolate_pos_embed_same_resolution_matches_reference(ref):
+    """Checkpoint adaptation helper (models/beit2.py:664-754) on the reference's own vision state_dict at its own
+    resolution: same keys dropped, every tensor untouched.  (The resizing branch of the reference cannot run here:
+    SciPy >= 1.14 removed interp2d; ours uses the documented RectBivariateSpline replacement, tests/test_host_logic.py.)"""
+    from models import beit2 as rbeit
+    from x2vlm_b200 import beit2
+    sd = {k: v.clone() for k, v in ref.vision_encoder.state_dict().items()}
+    want = rbeit.interpolate_pos_embed(ref.vision_encoder, {k: v.clone() for k, v in sd.items()})
+    ours = beit2.beit_base_patch16(img_size=224, drop_rate=0.0, drop_path_rate=0.1, attn_drop_rate=0.0, use_mean_pooling=True,
+                                   init_scale=0.001, use_rel_pos_bias=True, use_abs_pos_emb=False, init_values=0.1, qkv_bias=True)
+    got = beit2.interpolate_pos_embed(ours, {k: v.clone() for k, v in sd.items()})
+    assert sorted(got) == sorted(want) and not any("relative_position_index" in k for k in got)
+    assert all(torch.equal(got[k], want[k]) for k in want)
+    missing, unexpected, ignored = beit2.load_state_dict(ours, got)
+    assert missing == [] and unexpected == [] and len(ignored) == 12

@@ -275,3 +275,144 @@ def beit_base_patch16(img_size, **kwargs):
 def beit_large_patch16(img_size, **kwargs):
     return VisionTransformer(img_size=img_size, patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4,
                              norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------
+# checkpoint helpers (host logic; models/beit2.py:473-754)
+# ----------------------------------------------------------------------------------------------
+def _resize_rel_pos_bias_table(rel_pos_bias, src_size, dst_size, num_extra_tokens):
+    """Relative-position bias table [(2·src-1)² + extra, H] -> [(2·dst-1)² + extra, H] (models/beit2.py:514-575):
+    source offsets are placed on a geometric progression (denser near 0), every head's (2·src-1)² surface is fitted
+    with a bicubic spline and sampled on the integer offsets of the target window; the `extra` rows (cls-to-token,
+    token-to-cls, cls-to-cls) are copied.  The reference calls scipy.interpolate.interp2d(kind='cubic'), which SciPy
+    removed in 1.14; RectBivariateSpline(kx=ky=3) on the same rectilinear grid is SciPy's documented replacement
+    (interp2d(x, y, z)(xn, yn) == RectBivariateSpline(x, y, z.T)(xn, yn).T)."""
+    import numpy as np
+    from scipy import interpolate
+    extra_tokens = rel_pos_bias[-num_extra_tokens:, :]
+    table = rel_pos_bias[:-num_extra_tokens, :]
+    num_heads = table.shape[1]
+
+    def geometric_progression(a, r, n):
+        return a * (1.0 - r ** n) / (1.0 - r)
+
+    left, right = 1.01, 1.5
+    while right - left > 1e-6:
+        q = (left + right) / 2.0
+        if geometric_progression(1, q, src_size // 2) > dst_size // 2:
+            right = q
+        else:
+            left = q
+    dis, cur = [], 1
+    for i in range(src_size // 2):
+        dis.append(cur)
+        cur += q ** (i + 1)
+    x = [-d for d in reversed(dis)] + [0] + dis
+    t = dst_size // 2.0
+    dx = np.arange(-t, t + 0.1, 1.0)
+    out = []
+    for h in range(num_heads):
+        z = table[:, h].view(src_size, src_size).float().cpu().numpy()
+        spline = interpolate.RectBivariateSpline(x, x, z.T, kx=3, ky=3)
+        out.append(torch.tensor(spline(dx, dx).T, dtype=torch.float32).contiguous().view(-1, 1).to(rel_pos_bias.device))
+    return torch.cat((torch.cat(out, dim=-1).to(rel_pos_bias.dtype), extra_tokens), dim=0)
+
+
+def interpolate_pos_embed(model, checkpoint_model):
+    """Adapt a vision state_dict (no prefix) to `model`'s resolution in place (models/beit2.py:664-754): drop the
+    `relative_position_index` buffers (rebuilt by the model), resize every `relative_position_bias_table` whose window
+    differs, bicubic-resize `pos_embed` if both sides have one.  Returns the dict."""
+    for key in list(checkpoint_model.keys()):
+        if "relative_position_index" in key:
+            checkpoint_model.pop(key)
+        if "relative_position_bias_table" in key:
+            rel_pos_bias = checkpoint_model[key]
+            src_num_pos, _ = rel_pos_bias.size()
+            try:
+                dst_num_pos, _ = model.state_dict()[key].size()
+            except KeyError:
+                print("Note that vision encoder does not have: ", key)
+                continue
+            dst_patch_shape = model.patch_embed.patch_shape
+            if dst_patch_shape[0] != dst_patch_shape[1]:
+                raise NotImplementedError()
+            num_extra_tokens = dst_num_pos - (dst_patch_shape[0] * 2 - 1) * (dst_patch_shape[1] * 2 - 1)
+            src_size = int((src_num_pos - num_extra_tokens) ** 0.5)
+            dst_size = int((dst_num_pos - num_extra_tokens) ** 0.5)
+            if src_size != dst_size:
+                print("Position interpolate for %s from %dx%d to %dx%d" % (key, src_size, src_size, dst_size, dst_size))
+                checkpoint_model[key] = _resize_rel_pos_bias_table(rel_pos_bias, src_size, dst_size, num_extra_tokens)
+    if ('pos_embed' in checkpoint_model) and (model.pos_embed is not None):
+        pos_embed_checkpoint = checkpoint_model['pos_embed']
+        embedding_size = pos_embed_checkpoint.shape[-1]
+        num_patches = model.patch_embed.num_patches
+        num_extra_tokens = model.pos_embed.shape[-2] - num_patches
+        orig_size = int((pos_embed_checkpoint.shape[-2] - num_extra_tokens) ** 0.5)
+        new_size = int(num_patches ** 0.5)
+        if orig_size != new_size:
+            print("Position interpolate from %dx%d to %dx%d" % (orig_size, orig_size, new_size, new_size))
+            extra_tokens = pos_embed_checkpoint[:, :num_extra_tokens]
+            pos_tokens = pos_embed_checkpoint[:, num_extra_tokens:]
+            pos_tokens = pos_tokens.reshape(-1, orig_size, orig_size, embedding_size).permute(0, 3, 1, 2)
+            pos_tokens = torch.nn.functional.interpolate(pos_tokens, size=(new_size, new_size), mode='bicubic',
+                                                         align_corners=False)
+            pos_tokens = pos_tokens.permute(0, 2, 3, 1).flatten(1, 2)
+            checkpoint_model['pos_embed'] = torch.cat((extra_tokens, pos_tokens), dim=1)
+    return checkpoint_model
+
+
+def load_state_dict(model, state_dict, prefix='', ignore_missing="relative_position_index"):
+    """Non-strict recursive load with the reference's reporting (models/beit2.py:617-661): missing keys that contain
+    one of the `|`-separated `ignore_missing` patterns are expected.  Returns (missing, unexpected, ignored)."""
+    missing_keys, unexpected_keys, error_msgs = [], [], []
+    metadata = getattr(state_dict, '_metadata', None)
+    state_dict = state_dict.copy()
+    if metadata is not None:
+        state_dict._metadata = metadata
+
+    def load(module, prefix=''):
+        local_metadata = {} if metadata is None else metadata.get(prefix[:-1], {})
+        module._load_from_state_dict(state_dict, prefix, local_metadata, True, missing_keys, unexpected_keys, error_msgs)
+        for name, child in module._modules.items():
+            if child is not None:
+                load(child, prefix + name + '.')
+
+    load(model, prefix=prefix)
+    warn, ignored = [], []
+    for key in missing_keys:
+        (ignored if any(pat in key for pat in ignore_missing.split('|')) else warn).append(key)
+    if warn:
+        print("Weights of {} not initialized from pretrained model: {}".format(model.__class__.__name__, warn))
+    if unexpected_keys:
+        print("Weights from pretrained model not used in {}: {}".format(model.__class__.__name__, unexpected_keys))
+    if ignored:
+        print("Ignored weights of {} not initialized from pretrained model: {}".format(model.__class__.__name__, ignored))
+    if error_msgs:
+        print('\n'.join(error_msgs))
+    # (parameters are overwritten in place: their version counters change, so the bf16 shadows re-cast on next use)
+    return warn, unexpected_keys, ignored
+
+
+def load_pretrained_beit2(model, ckpt_rpath):
+    """Load a BEiT-2 checkpoint file into the vision encoder (models/beit2.py:473-614): unwrap 'model' / 'module',
+    drop the classification head, expand a shared rel-pos bias to every block, adapt tables / pos_embed to the
+    model's resolution, then load non-strictly."""
+    print("Load BEIT-V2 ckpt from %s" % ckpt_rpath)
+    checkpoint = torch.load(ckpt_rpath, map_location='cpu')
+    checkpoint_model = None
+    for model_key in 'model|module'.split('|'):
+        if model_key in checkpoint:
+            checkpoint_model = checkpoint[model_key]
+            print("Load state_dict by model_key = %s" % model_key)
+            break
+    if checkpoint_model is None:
+        checkpoint_model = checkpoint
+    for k in ['head.weight', 'head.bias']:
+        del checkpoint_model[k]
+    if getattr(model, 'use_rel_pos_bias', False) and "rel_pos_bias.relative_position_bias_table" in checkpoint_model:
+        print("Expand the shared relative position embedding to each transformer block. ")
+        rel_pos_bias = checkpoint_model.pop("rel_pos_bias.relative_position_bias_table")
+        for i in range(model.get_num_layers()):
+            checkpoint_model["blocks.%d.attn.relative_position_bias_table" % i] = rel_pos_bias.clone()
+    interpolate_pos_embed(model, checkpoint_model)
+    return load_state_dict(model, checkpoint_model, prefix='')

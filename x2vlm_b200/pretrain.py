@@ -15,7 +15,6 @@ Differences that are part of the B200-first design, none of which change results
     1 text call (clean + masked captions of both), 1 fusion call (ITM pos / ITM neg / MLM / bbox of
     both) in which sequences that look at the same image share its K/V projection (`encoder_kv_index`).
 """
-import math
 
 import torch
 import torch.distributed as dist

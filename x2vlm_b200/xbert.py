@@ -21,7 +21,6 @@ Not built (raise NotImplementedError): head pruning / head_mask, output_attentio
 xbert's per-position DropPath (text_drop_path_rate / cross_drop_path_rate, refcoco_grounding_large.yaml) is folded into
 the dense GEMM epilogues as a per-row scale.
 """
-import math
 
 import torch
 import torch.nn as nn

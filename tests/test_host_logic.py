@@ -276,3 +276,35 @@ def test_beit2_checkpoint_helpers(tmp_path):
     pe_big.pos_embed = torch.nn.Parameter(torch.zeros(1, 577, 128))
     out = beit2.interpolate_pos_embed(pe_big, {"pos_embed": torch.randn(1, 197, 128, generator=g)})
     assert out["pos_embed"].shape == (1, 577, 128)
+
+
+def test_generate_no_beam_host_loop():
+    """BertLMHeadModel.generate_no_beam (models/xbert.py:1415-1519) with the network replaced by a scripted logits
+    table: greedy path, EOS bookkeeping, padding, repetition penalty and the cache hand-over are host logic."""
+    from types import SimpleNamespace
+    from x2vlm_b200 import xbert
+    cfg = xbert.BertConfig(vocab_size=12, hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256,
+                           max_position_embeddings=32)
+    cfg.fusion_layer, cfg.encoder_width = 0, 128
+    m = xbert.BertLMHeadModel(cfg)
+    calls = []
+
+    def fake_forward(input_ids=None, past_key_values=None, use_cache=None, return_dict=None, **kw):
+        calls.append((tuple(input_ids.shape), past_key_values))
+        step = len(calls)
+        logits = torch.full((input_ids.shape[0], input_ids.shape[1], 12), -5.0)
+        # sequence 0 emits 3, 4, then EOS (= 2); sequence 1 emits 5 forever
+        plan0 = {1: 3, 2: 4}.get(step, 2)
+        logits[0, -1, plan0] = 5.0
+        logits[1, -1, 5] = 5.0
+        logits[1, -1, 6] = 4.9          # runner-up: wins once 5 is penalised
+        return SimpleNamespace(logits=logits, past_key_values=("cache", step))
+
+    m.forward = fake_forward
+    ids, lp = m.generate_no_beam(torch.tensor([[1, 7], [1, 8]]), max_length=7, eos_token_ids=(2,), pad_token_id=0)
+    assert ids.tolist() == [[1, 7, 3, 4, 2, 0, 0], [1, 8, 5, 5, 5, 5, 2]]        # finished rows are padded; EOS forced at the end
+    assert calls[0] == ((2, 2), None) and calls[1] == ((2, 1), ("cache", 1))    # prompt once, then one token per step
+    assert lp.shape == (2,) and torch.isfinite(lp).all()
+    calls.clear()
+    ids, _ = m.generate_no_beam(torch.tensor([[1, 7], [1, 8]]), max_length=5, eos_token_ids=(2,), repetition_penalty=1.5)
+    assert ids[1].tolist()[2:4] == [5, 6]                                         # 5 / 1.5 < 4.9 after its first use

@@ -160,3 +160,15 @@ def test_interpolate_pos_embed_same_resolution_matches_reference(ref):
     assert all(torch.equal(got[k], want[k]) for k in want)
     missing, unexpected, ignored = beit2.load_state_dict(ours, got)
     assert missing == [] and unexpected == [] and len(ignored) == 12
+
+
+def test_top_k_top_p_filtering_matches_reference():
+    ref_shim.install()
+    from models import xbert as rxbert
+    from x2vlm_b200 import xbert
+    g = torch.Generator().manual_seed(0)
+    for top_k, top_p, keep in ((0, 0.9, 1), (5, 1.0, 1), (7, 0.6, 3), (0, 0.3, 2), (50, 0.95, 1)):
+        logits = torch.randn(6, 40, generator=g) * 3
+        want = rxbert.top_k_top_p_filtering(logits.clone(), top_k=top_k, top_p=top_p, min_tokens_to_keep=keep)
+        got = xbert.top_k_top_p_filtering(logits.clone(), top_k=top_k, top_p=top_p, min_tokens_to_keep=keep)
+        assert torch.equal(got, want), (top_k, top_p, keep)

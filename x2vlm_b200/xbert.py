@@ -635,6 +635,55 @@ class BertLMHeadModel(BertPreTrainedModel):
         return tuple(tuple(t.index_select(0, beam_idx) for t in layer_past) for layer_past in past)
 
     @torch.no_grad()
+    def generate_no_beam(self, input_ids, max_length, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
+                         repetition_penalty=1.0, pad_token_id=0, eos_token_ids=(), **model_kwargs):
+        """The num_beams == 1 generation loop of the reference (models/xbert.py:1415-1519) on the key/value cache:
+        CTRL repetition penalty, temperature, top-k / top-p sampling or arg-max, finished sequences padded, the last
+        position forced to EOS when max_length is hit.  Returns (ids [B, max_length], mean log-prob per sequence)."""
+        batch_size = input_ids.shape[0]
+        cur_unfinished = input_ids.new_ones(batch_size)
+        logprobs, unfinished_sents = [], []
+        past, cur_len = None, input_ids.shape[1]
+        while cur_len < max_length:
+            inp = self.prepare_inputs_for_generation(input_ids, past=past, **model_kwargs)
+            out = self(**inp, use_cache=True, return_dict=True)
+            past = out.past_key_values
+            next_token_logits = out.logits[:, -1, :].float().clone()
+            if repetition_penalty != 1.0:
+                seen = torch.zeros_like(next_token_logits, dtype=torch.bool).scatter_(1, input_ids, True)
+                scaled = torch.where(next_token_logits < 0, next_token_logits * repetition_penalty,
+                                     next_token_logits / repetition_penalty)
+                next_token_logits = torch.where(seen, scaled, next_token_logits)
+            if do_sample:
+                if temperature != 1.0:
+                    next_token_logits = next_token_logits / temperature
+                next_token_logits = top_k_top_p_filtering(next_token_logits, top_k=top_k, top_p=top_p)
+                next_token = torch.multinomial(F.softmax(next_token_logits, dim=-1), num_samples=1).squeeze(1)
+            else:
+                next_token = torch.argmax(next_token_logits, dim=-1)
+            logprobs.append(torch.gather(F.log_softmax(next_token_logits, dim=-1), -1, next_token.unsqueeze(-1)))
+            unfinished_sents.append(cur_unfinished)
+            tokens_to_add = next_token * cur_unfinished + pad_token_id * (1 - cur_unfinished)
+            input_ids = torch.cat([input_ids, tokens_to_add.unsqueeze(-1)], dim=-1)
+            if "attention_mask" in model_kwargs and model_kwargs["attention_mask"] is not None:
+                am = model_kwargs["attention_mask"]
+                model_kwargs["attention_mask"] = torch.cat([am, am.new_ones((am.shape[0], 1))], dim=-1)
+            cur_len += 1
+            for eos in eos_token_ids:
+                cur_unfinished = cur_unfinished.mul(tokens_to_add.ne(eos).long())
+            if cur_unfinished.max() == 0:
+                break
+        if cur_len == max_length and len(eos_token_ids) > 0:
+            input_ids[:, -1].masked_fill_(cur_unfinished.to(dtype=torch.bool), eos_token_ids[0])
+        logprobs = torch.cat(logprobs, dim=1)
+        unfinished = torch.stack(unfinished_sents, dim=1).float()
+        mean_logprob = (logprobs * unfinished).sum(dim=1) / unfinished.sum(dim=1)
+        if max_length > input_ids.shape[1]:
+            pad = input_ids.new_full((batch_size, max_length - input_ids.shape[1]), pad_token_id)
+            input_ids = torch.cat([input_ids, pad], dim=1)
+        return input_ids, mean_logprob
+
+    @torch.no_grad()
     def greedy_decode(self, input_ids, max_length, eos_token_id=None, pad_token_id=0, **model_kwargs):
         """Cached greedy decoding (the num_beams == 1, do_sample == False case of the reference's generate loop,
         models/xbert.py:1415-1490): one prompt pass that fills the cache, then one token per step."""
@@ -652,6 +701,26 @@ class BertLMHeadModel(BertPreTrainedModel):
             if eos_token_id is not None and unfinished.max() == 0:
                 break
         return cur
+
+
+def top_k_top_p_filtering(logits, top_k=0, top_p=1.0, filter_value=-float("Inf"), min_tokens_to_keep=1):
+    """Top-k and / or nucleus filtering of a [batch, vocab] logits matrix, in place (models/xbert.py:1521-1554): keep the
+    top_k highest logits; of the rest keep the smallest prefix (by descending probability) whose cumulative probability
+    reaches top_p, always including the token that crosses the threshold and at least min_tokens_to_keep tokens."""
+    if top_k > 0:
+        k = min(max(top_k, min_tokens_to_keep), logits.size(-1))
+        kth = torch.topk(logits, k)[0][..., -1, None]
+        logits.masked_fill_(logits < kth, filter_value)
+    if top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(logits, descending=True)
+        cum = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+        drop_sorted = cum > top_p
+        if min_tokens_to_keep > 1:
+            drop_sorted[..., :min_tokens_to_keep] = False
+        drop_sorted = torch.cat([torch.zeros_like(drop_sorted[..., :1]), drop_sorted[..., :-1]], dim=-1)  # shift right
+        drop = torch.zeros_like(drop_sorted).scatter(1, sorted_idx, drop_sorted)
+        logits.masked_fill_(drop, filter_value)
+    return logits
 
 
 class BertForMaskedLM(BertPreTrainedModel):

@@ -172,3 +172,32 @@ def test_top_k_top_p_filtering_matches_reference():
         want = rxbert.top_k_top_p_filtering(logits.clone(), top_k=top_k, top_p=top_p, min_tokens_to_keep=keep)
         got = xbert.top_k_top_p_filtering(logits.clone(), top_k=top_k, top_p=top_p, min_tokens_to_keep=keep)
         assert torch.equal(got, want), (top_k, top_p, keep)
+
+
+def test_itc_idx_labels_and_negative_weights_match_reference(ref, monkeypatch):
+    """Retrieval fine-tuning passes sample ids (models/model_retrieval.py:13-24): soft ITC labels over equal ids
+    (models/xvlm.py:811-824) and hard-negative weights with every same-id pair zeroed (:838-846)."""
+    from types import SimpleNamespace
+    from x2vlm_b200 import pretrain
+    g = torch.Generator().manual_seed(2)
+    fi = torch.nn.functional.normalize(torch.randn(6, 256, generator=g), dim=-1)
+    ft = torch.nn.functional.normalize(torch.randn(6, 256, generator=g), dim=-1)
+    idx = torch.tensor([3, 7, 3, 9, 7, 1])
+    me = SimpleNamespace(temp=ref.temp.detach().clone())
+    me.hard_negative_weights = lambda *a, **k: pretrain.XVLM.hard_negative_weights(me, *a, **k)
+    with torch.no_grad():
+        for ids in (None, idx):
+            want = ref.get_contrastive_loss(fi, ft, idx=ids)
+            got = pretrain.XVLM.get_contrastive_loss(me, fi, ft, idx=ids)
+            assert abs(float(got) - float(want)) < 1e-6, ids
+    seen = []
+    real = torch.multinomial
+    monkeypatch.setattr(torch, "multinomial", lambda w, n, *a, **k: (seen.append(w.clone()), real(w, n, *a, **k))[1])
+    ref.get_hard_negatives(fi, ft, idx=idx)           # B draws from weights_t2i rows, then B from weights_i2t rows
+    monkeypatch.undo()
+    w_t2i_ref, w_i2t_ref = torch.stack(seen[:6]), torch.stack(seen[6:12])
+    w_i2t, w_t2i = pretrain.XVLM.hard_negative_weights(me, fi, ft, idx=idx)
+    assert torch.allclose(w_i2t, w_i2t_ref, atol=1e-7) and torch.allclose(w_t2i, w_t2i_ref, atol=1e-7)
+    assert float(w_i2t[0, 2]) == 0.0 and float(w_i2t[1, 4]) == 0.0 and float(w_i2t[0, 1]) > 0.0
+    ineg, tneg = pretrain.XVLM.get_hard_negatives(me, fi, ft, idx=idx)
+    assert all(int(idx[i]) != int(idx[j]) for i, j in enumerate(ineg.tolist())) and ineg.shape == (6,) and tneg.shape == (6,)

@@ -192,23 +192,45 @@ class XVLM(nn.Module):
             F.normalize(self.text_proj(text_embeds[:, 0, :]), dim=-1)
 
     def get_contrastive_loss(self, image_feat, text_feat, idx=None):
-        """models/xvlm.py:794-826 (idx=None case)."""
-        if idx is not None:
-            raise NotImplementedError("idx-grouped ITC labels")
+        """models/xvlm.py:794-826.  idx [B] (retrieval fine-tuning): samples with the same id are positives of each
+        other — soft labels = row-normalised id-equality matrix over the gathered batch."""
         image_feat_all, text_feat_all = allgather(image_feat), allgather(text_feat)
         logits = image_feat_all @ text_feat_all.t() / self.temp
-        labels = torch.arange(logits.shape[0], device=logits.device)
-        return (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
+        if idx is None:
+            labels = torch.arange(logits.shape[0], device=logits.device)
+            return (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
+        idx = idx.view(-1, 1)
+        assert idx.size(0) == image_feat.size(0)
+        idx_all = allgather(idx)
+        pos_idx = torch.eq(idx_all, idx_all.t()).float()
+        labels = pos_idx / pos_idx.sum(1, keepdim=True)
+        loss_i2t = -torch.sum(F.log_softmax(logits, dim=1) * labels, dim=1).mean()
+        loss_t2i = -torch.sum(F.log_softmax(logits.t(), dim=1) * labels, dim=1).mean()
+        return (loss_i2t + loss_t2i) / 2
 
-    def get_hard_negatives(self, image_feat, text_feat, idx=None):
-        """Same sampling law as models/xvlm.py:828-857 (multinomial over softmax(sim)+1e-5, diagonal zeroed), drawn
-        for all rows in one device call; returns index TENSORS (no host sync)."""
+    def hard_negative_weights(self, image_feat, text_feat, idx=None):
+        """Sampling weights of models/xvlm.py:828-846: softmax(sim) + 1e-5 with the positives zeroed — the diagonal, or
+        every pair that shares an id when idx is given.  Returns (weights_i2t, weights_t2i)."""
         with torch.no_grad():
             sim_i2t = image_feat @ text_feat.t() / self.temp
             w_i2t = F.softmax(sim_i2t, dim=1) + 1e-5
             w_t2i = F.softmax(sim_i2t.t(), dim=1) + 1e-5
-            w_i2t.fill_diagonal_(0)
-            w_t2i.fill_diagonal_(0)
+            if idx is None:
+                w_i2t.fill_diagonal_(0)
+                w_t2i.fill_diagonal_(0)
+            else:
+                idx = idx.view(-1, 1)
+                assert idx.size(0) == image_feat.size(0)
+                mask = torch.eq(idx, idx.t())
+                w_i2t.masked_fill_(mask, 0)
+                w_t2i.masked_fill_(mask, 0)
+        return w_i2t, w_t2i
+
+    def get_hard_negatives(self, image_feat, text_feat, idx=None):
+        """Same sampling law as models/xvlm.py:828-857, drawn for all rows in one device call; returns index TENSORS
+        (no host sync)."""
+        w_i2t, w_t2i = self.hard_negative_weights(image_feat, text_feat, idx)
+        with torch.no_grad():
             image_neg_idx = torch.multinomial(w_t2i, 1).squeeze(1)
             text_neg_idx = torch.multinomial(w_i2t, 1).squeeze(1)
         return image_neg_idx, text_neg_idx
@@ -278,6 +300,18 @@ class XVLM(nn.Module):
             coord = self.predict_bbox(image_embeds_fullatts, text_embeds, text_atts)
             loss['loss_bbox'], loss['loss_giou'] = self.get_bbox_loss(coord, target_bbox, is_image=is_image)
         return loss
+
+    def forward_retrieval(self, image, text_ids, text_atts, idx=None):
+        """Retrieval fine-tuning step (models/model_retrieval.py:13-24): ITC + ITM, sample ids `idx` mark captions of
+        the same image as mutual positives.  Returns (loss_itc, loss_itm)."""
+        image_embeds, image_atts = self.get_vision_embeds(image)
+        text_embeds = self.get_text_embeds(text_ids, text_atts)
+        with torch.no_grad():
+            self.temp.clamp_(0.001, 0.5)
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        loss_itc = self.get_contrastive_loss(image_feat, text_feat, idx=idx)
+        loss_itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=idx)
+        return loss_itc, loss_itm
 
     # ------------------------------------------------------------------ batched mixed step
     def forward_mixed(self, ib, rb=None, neg_idx_i=None, neg_idx_r=None, out=None):

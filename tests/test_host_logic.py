@@ -308,3 +308,21 @@ def test_generate_no_beam_host_loop():
     calls.clear()
     ids, _ = m.generate_no_beam(torch.tensor([[1, 7], [1, 8]]), max_length=5, eos_token_ids=(2,), repetition_penalty=1.5)
     assert ids[1].tolist()[2:4] == [5, 6]                                         # 5 / 1.5 < 4.9 after its first use
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """Contract: `bench.py --impl reference` prints exactly ONE JSON line on stdout (library chatter goes to stderr),
+    with the same metric / unit / workload as the main arm and a cpu_baseline describing the run."""
+    import json
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "image-text pairs/sec pretrain step X2VLM-base bf16"
+    assert d["config"]["workload"].startswith("X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch 64/GPU")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

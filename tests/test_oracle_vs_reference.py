@@ -201,3 +201,66 @@ def test_itc_idx_labels_and_negative_weights_match_reference(ref, monkeypatch):
     assert float(w_i2t[0, 2]) == 0.0 and float(w_i2t[1, 4]) == 0.0 and float(w_i2t[0, 1]) > 0.0
     ineg, tneg = pretrain.XVLM.get_hard_negatives(me, fi, ft, idx=idx)
     assert all(int(idx[i]) != int(idx[j]) for i, j in enumerate(ineg.tolist())) and ineg.shape == (6,) and tneg.shape == (6,)
+
+
+def test_retrieval_scores_match_reference_evaluation(ref):
+    """oracle.restate.retrieval_scores against the reference's own Retrieval.evaluation loop (Retrieval.py:71-157) run
+    on stub loader / tokenizer objects: ITC similarities, top-k candidates and ITM re-rank scores, both directions."""
+    import os
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, ref_shim.REFERENCE) if hasattr(ref_shim, "REFERENCE") else sys.path.insert(0, "/root/reference")
+    cwd = os.getcwd()
+    os.chdir(ref_shim.workdir())
+    try:
+        import Retrieval
+    finally:
+        os.chdir(cwd)
+    n_img, n_txt, k = 3, 5, 2
+    b = synth.image_text_batch(n_txt, 40, seed=7)
+    images, ids, atts = b["image"][:n_img], b["text_ids"], b["text_atts"].clone()
+    atts[1, 30:] = 0
+
+    class Tok:
+        def __call__(self, text, **kw):
+            i, a = torch.stack([ids[t] for t in text]), torch.stack([atts[t] for t in text])
+            out = SimpleNamespace(input_ids=i, attention_mask=a)
+            out.to = lambda dev: out
+            return out
+
+    class Loader:
+        dataset = SimpleNamespace(text=list(range(n_txt)), image=list(range(n_img)))
+
+        def __iter__(self):
+            for i in range(0, n_img, 2):
+                yield images[i:i + 2], torch.arange(i, min(n_img, i + 2))
+
+    Retrieval.args = SimpleNamespace(distributed=False)
+    s_i2t, s_t2i = Retrieval.evaluation(ref, Loader(), Tok(), torch.device("cpu"),
+                                        {"batch_size_test_text": 2, "max_tokens": 40, "k_test": k})
+    sd = _sd(ref)
+    with torch.no_grad():
+        ie = restate.vision_forward(images, sd, "vision_encoder.", 12, 12)
+        te = restate.bert_model(sd, "text_encoder.bert.", 12, 12, 18, input_ids=ids, attention_mask=atts, mode="text")
+        fi, ft = restate.get_features(ie, te, sd)
+        w_i2t, w_t2i = restate.retrieval_scores(sd, restate.Shapes(), ie, te, atts, fi @ ft.t(), k)
+    assert torch.equal(torch.from_numpy(s_i2t) > -99, w_i2t > -99) and torch.equal(torch.from_numpy(s_t2i) > -99, w_t2i > -99)
+    assert (w_i2t - torch.from_numpy(s_i2t)).abs().max() < 1e-4 and (w_t2i - torch.from_numpy(s_t2i)).abs().max() < 1e-4
+
+
+def test_video_avgpool_matches_reference():
+    """oracle.restate.video_forward against the reference's XVLMBase.get_vision_embeds on a 5-D input
+    (video_encoding='avgpool', learned per-frame offsets; models/xvlm.py:615-661)."""
+    m = ref_shim.build_reference_xvlm(ref_shim.base_config(video_encoding="avgpool", frame_len=3, add_frame_pos=True,
+                                                           vision_num_hidden_layers=2), seed=1)
+    m.eval()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        m.absolute_frame_pos_embed.copy_(torch.randn(m.absolute_frame_pos_embed.shape, generator=g) * 0.1)
+    frames = torch.randn(2, 3, 3, 224, 224, generator=g)
+    sd = _sd(m)
+    with torch.no_grad():
+        want, want_atts = m.get_vision_embeds(frames)
+        got = restate.video_forward(frames, sd, restate.Shapes(vision_depth=2), sd["absolute_frame_pos_embed"])
+    assert want.shape == (2, 197, 768) and want_atts.shape == (2, 197)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5)

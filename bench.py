@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps K --warmup W            # this framework
     torchrun ... bench.py --gpus N --steps K --warmup W      # one rank per GPU, NCCL
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference on the host cores (oracle/_ref)
 
 One "step" = Pretrain.py:run_mixed_iter semantics on one synthetic batch per GPU:
 zero_grad -> image iteration (64 image-text pairs: ITC+ITM+MLM) + region iteration (64 region-text samples over
@@ -242,23 +242,29 @@ def run_ours(args):
     roof = dominant_kernel_roofline(lambda: eager_step(ib_d, rb_d, False), sustained, src,  # every rank steps (collectives)
                                     table_path=args.kernel_table if rank == 0 else None)
     out = None
+    graph_on = graphed is not None
     if rank == 0:
         sys.stderr.write("[bench] timed: %.2f ms/step resident (host enqueue %.2f ms/step), %.2f ms/step e2e\n"
                          % (ms / args.steps, host_enqueue_ms, ms_e2e / args.steps))
-        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_baseline(image_only=rb_h is None) if (world == 1 and not args.no_cpu_baseline) else None
+        eager = None
+        if world == 1 and not args.no_gpu_eager:
+            try:
+                if graphed is not None:
+                    graphed.release()
+                    graphed = None
+                eager = gpu_eager_baseline(dev, B, n_img, rb_h is None)
+            except Exception as e:  # the comparator must never cost the main line
+                eager = {"unavailable": repr(e)[:300]}
         out = {
             "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; "
-                                   "random-init weights" % (B, "" if rb_h is not None else " image iteration only"),
-                       "global_batch": B * world, "pairs_per_step_per_gpu": pairs_per_step // world,
-                       "region_images_per_gpu": n_img if rb_h is not None else 0, "seq_len": 40, "image_res": 224,
-                       "parallelism": "dp%d" % world, "optimizer": "AdamW + clip 1.0 (flat fused)",
-                       "l2": "per-step working set (tens of GB of activations, 3 GB params/grads) >> 126 MB L2; no flush needed",
+            "config": workload_config(args, world),
+            "detail": {"l2": "per-step working set (tens of GB of activations, 3 GB params/grads) >> 126 MB L2; no flush needed",
                        "loss_last_step": loss_v, "host_enqueue_ms_per_step": host_enqueue_ms,
                        "cuda_graph": ("whole step (fwd+bwd+clip+AdamW) replayed as one CUDA graph; gpu_launches = x2k kernel "
-                                      "nodes per replay x steps" if graphed is not None else "off (eager launches)"),
+                                      "nodes per replay x steps" if graph_on else "off (eager launches)"),
                        "algorithmic_tflop_per_step_per_gpu": flop_step_gpu / 1e12,
                        "step_tflops_per_gpu": step_tflops,
                        "step_frac_of_%s_sustained_bf16_peak" % src: step_tflops / sustained,
@@ -268,6 +274,10 @@ def run_ours(args):
                     "loss_last_step": loss_e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
+        if eager is not None:
+            out["gpu_eager_baseline"] = eager
+            if "value" in eager:
+                out["gpu_eager_baseline"]["speedup_value_over_eager"] = value / eager["value"]
         if cpu is not None:
             out["cpu_baseline"] = cpu
     if rank == 0:
@@ -326,6 +336,84 @@ def dominant_kernel_roofline(step_fn, peak_sustained, src, table_path=None):
             "traffic": ROOFLINE_TRAFFIC, "other_kernels": other}
 
 
+def workload_config(args, world):
+    """The static description of the workload — identical in both arms' JSON lines (`config`), so the driver's
+    same-config check compares like with like; everything measured goes under `detail`."""
+    B, n_img = args.batch, (0 if args.image_only else args.region_images)
+    return {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; random-init weights"
+                        % (B, " image iteration only" if args.image_only else ""),
+            "global_batch": B * world, "pairs_per_step_per_gpu": B if args.image_only else 2 * B,
+            "region_images_per_gpu": n_img, "seq_len": 40, "image_res": 224, "parallelism": "dp%d" % world,
+            "optimizer": "AdamW(0.9, 0.98, eps 1e-8, wd 0.01) + clip 1.0"}
+
+
+def reference_step_fn(device, batch_i, batch_r, n_img_r, autocast_bf16, threads=None):
+    """One optimizer step of the UNMODIFIED reference with Pretrain.py:run_mixed_iter semantics (:189-252): the
+    reference's own models.model_pretrain.XVLM on its own encoders (byte-code of /root/reference, oracle/_ref),
+    its own optim.create_optimizer (optim.py:26-104), image iteration + region iteration summed, one backward,
+    clip_grad_norm_ 1.0, AdamW; the per-loss .item() reads are the reference's metric_logger.update calls.
+    Returns (step callable -> loss, pairs per step)."""
+    import types
+    from oracle import ref_shim
+    from x2vlm_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    model = ref_shim.build_reference_model("models.model_pretrain.XVLM", seed=0).to(device).train()
+    import optim as ref_optim  # the reference's optim.py
+    opt = ref_optim.create_optimizer(types.SimpleNamespace(lr=1e-4, weight_decay=0.01, lr_mult=2), model)
+    ib = {k: v.to(device) for k, v in synth.image_text_batch(batch_i, 40, seed=1234).items()}
+    rb = {k: v.to(device) for k, v in synth.region_batch(n_img_r, batch_r, 40, seed=4321).items()} if batch_r else None
+    dev_type = torch.device(device).type
+
+    def step():
+        opt.zero_grad()
+        with torch.no_grad():
+            model.temp.clamp_(0.001, 0.5)  # Pretrain.py:327-328
+        with torch.autocast(dev_type, dtype=torch.bfloat16, enabled=autocast_bf16):
+            li = model(ib["image"], ib["text_ids"], ib["text_atts"], text_ids_masked=ib["text_ids_masked"],
+                       masked_pos=ib["masked_pos"], masked_ids=ib["masked_ids"])
+            loss = li["loss_itc"] + li["loss_itm"] + li["loss_mlm"]
+            logged = [li[k].item() for k in ("loss_itc", "loss_itm", "loss_mlm")]
+            if rb is not None:
+                lr_ = model(rb["image"], rb["text_ids"], rb["text_atts"], text_ids_masked=rb["text_ids_masked"],
+                            masked_pos=rb["masked_pos"], masked_ids=rb["masked_ids"], image_atts=rb["image_atts"],
+                            idx_to_group_img=rb["idx_to_group_img"], target_bbox=rb["target_bbox"], is_image=rb["is_image"],
+                            ret_bbox_loss=True)
+                loss = loss + lr_["loss_itc"] + lr_["loss_itm"] + lr_["loss_mlm"] + lr_["loss_bbox"] + lr_["loss_giou"]
+                logged += [lr_[k].item() for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou")]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return sum(logged)
+
+    return step, batch_i + batch_r
+
+
+def gpu_eager_baseline(dev, batch, n_img, image_only, steps=5, warmup=3):
+    """The >= 6x comparator of BASELINE.md §4.4: the reference's own modules, PyTorch eager under
+    torch.autocast('cuda', bfloat16) (apex O1 is not installable offline; bf16 needs no loss scaler), same GPU, same
+    batch (64 + 64 over 26 images), inputs resident on the device, CUDA-event timed after warm-up."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return {"unavailable": "oracle/_ref (compiled reference) not present"}
+    step, pairs = reference_step_fn(dev, batch, 0 if image_only else batch, n_img, autocast_bf16=True)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    for _ in range(steps):
+        loss = step()
+    en.record()
+    torch.cuda.synchronize()
+    ms = st.elapsed_time(en) / steps
+    return {"value": pairs / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "what": "UNMODIFIED reference (models.model_pretrain.XVLM on models.beit2/models.xbert, optim.create_optimizer), "
+                    "PyTorch eager, torch.autocast(cuda, bfloat16), run_mixed_iter semantics, batch %d%s, resident inputs, "
+                    "same GPU as `value`" % (batch, "" if image_only else " + %d regions / %d images" % (batch, n_img)),
+            "loss_last_step": loss, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+
+
 def host_threads():
     """CPU threads this process may really use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -375,10 +463,32 @@ def oracle_step_fn(batch_i, batch_r, threads):
     return step, batch_i + batch_r
 
 
-def cpu_baseline(budget_s=25.0, batch_i=4, batch_r=4):
-    """Bounded sample: one warm-up step, then timed steps until ~budget_s of CPU work (at least one)."""
+CPU_SAMPLE_I, CPU_SAMPLE_R, CPU_SAMPLE_IMGS = 8, 8, 3  # bounded sample of the 64 + 64 / 26-image step (same 26/64 image ratio)
+
+
+def cpu_step_fn(image_only):
+    """(step, pairs per step, kind, cores, sample text) of the CPU arm: the UNMODIFIED reference (oracle/_ref byte-code of
+    /root/reference, fp32, all host threads — BASELINE.md §4.3: B = 8 image iteration, here together with the region
+    iteration of the mixed step) or, only if that copy is missing, the oracle port."""
+    from oracle import ref_shim
     threads = host_threads()
-    step, pairs = oracle_step_fn(batch_i, batch_r, threads)
+    bi, br = CPU_SAMPLE_I, (0 if image_only else CPU_SAMPLE_R)
+    if ref_shim.available():
+        step, pairs = reference_step_fn("cpu", bi, br, CPU_SAMPLE_IMGS, autocast_bf16=False, threads=threads)
+        kind = "reference"
+        what = "UNMODIFIED reference (models.model_pretrain.XVLM + optim.create_optimizer, run_mixed_iter semantics)"
+    else:
+        step, pairs = oracle_step_fn(bi, br, threads)
+        kind, what = "port", "oracle/restate.py port (oracle/_ref missing)"
+    sample = ("each step = one optimizer step on %d image-text pairs%s — a bounded sample of the batch-64 workload; %s, fp32, "
+              "torch CPU, %d threads" % (bi, "" if image_only else " + %d region samples over %d images" % (br, CPU_SAMPLE_IMGS),
+                                         what, threads))
+    return step, pairs, kind, threads, sample
+
+
+def cpu_baseline(budget_s=25.0, image_only=False):
+    """Bounded sample: one warm-up step, then timed steps until ~budget_s of CPU work (at least one)."""
+    step, pairs, kind, threads, sample = cpu_step_fn(image_only)
     step()  # warm-up (the first step pays allocator / lazy-init costs)
     n, t0 = 0, time.perf_counter()
     while True:
@@ -387,38 +497,34 @@ def cpu_baseline(budget_s=25.0, batch_i=4, batch_r=4):
         dt = time.perf_counter() - t0
         if dt >= budget_s or n >= 8:
             break
-    return {"value": pairs * n / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": "%d step(s), %.1f s, of the mixed step at batch %d image + %d region pairs (fp32, torch CPU, "
-                      "oracle/restate.py: the reference is Python and cannot travel to the GPU box)" % (n, dt, batch_i, batch_r)}
+    return {"value": pairs * n / dt, "unit": "pairs/s", "cores": threads, "kind": kind,
+            "sample": "%d timed step(s) in %.1f s after 1 warm-up; %s" % (n, dt, sample)}
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's own CPU path on this box's host cores.  /root/reference is a Python
-    tree that does not exist on the GPU box, so the timed code is the oracle port (oracle/restate.py), which
-    tests/test_oracle_vs_reference.py pins against the unmodified reference."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores — the unmodified
+    reference itself (byte-code compiled from /root/reference by oracle/build_ref.py; it travels to the GPU box in
+    oracle/_ref/), same metric / unit / config as the main arm, every step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = host_threads()
-    bi, br = 2, (0 if args.image_only else 2)
-    step, pairs = oracle_step_fn(bi, br, threads)
-    for _ in range(min(args.warmup, 2)):
+    step, pairs, kind, threads, sample = cpu_step_fn(args.image_only)
+    warm = max(args.warmup, 0)
+    for _ in range(warm):
         step()
     n = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(n):
-        step()
+        loss = step()
     dt = time.perf_counter() - t0
     v = pairs * n / dt
-    sample = "each step = mixed step on %d image + %d region pairs (bounded sample of the batch-64 workload), fp32, %d threads" % (bi, br, threads)
     emit_json({
         "impl": "reference", "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": v, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": dt / n * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": dt / n * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; random-init weights"
-                               % (args.batch, " image iteration only" if args.image_only else ""),
-                   "sample": sample, "seq_len": 40, "image_res": 224, "optimizer": "AdamW + clip 1.0 (torch)"},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.gpus),
+        "detail": {"loss_last_step": loss, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
@@ -457,6 +563,7 @@ def main():
     ap.add_argument("--image-only", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=48.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager comparator (N = 1 leg)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the step graph")
     ap.add_argument("--skip-image-only", action="store_true", help="do not also time the image-iteration-only step (N = 1)")
     ap.add_argument("--kernel-table", default=None, help="write the per-shape GEMM / attention timing table (markdown) here")

@@ -15,14 +15,35 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("X2VLM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The reference's sources (build container) or, where they do not exist (GPU box), the byte-code-only copy that
+    oracle/build_ref.py compiled from them into oracle/_ref/."""
+    env = os.environ.get("X2VLM_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and (os.path.exists(os.path.join(cand, "models", "__init__.py")) or
+                     os.path.exists(os.path.join(cand, "models", "__init__.pyc"))):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
+COMPILED_ONLY = not os.path.exists(os.path.join(REFERENCE_ROOT, "models", "__init__.py"))
 
 _installed = False
 _workdir = None
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+    return (os.path.exists(os.path.join(REFERENCE_ROOT, "models", "__init__.py")) or
+            os.path.exists(os.path.join(REFERENCE_ROOT, "models", "__init__.pyc")))
+
+
+def sources_available():
+    """True only in the build container (tests that read reference .py files / yaml configs)."""
+    return os.path.exists(os.path.join(REFERENCE_ROOT, "models", "__init__.py"))
 
 
 def _fake_module(name, **attrs):
@@ -127,6 +148,9 @@ def install():
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    repo = os.path.dirname(_HERE)
+    if repo not in sys.path:  # workdir() changes the cwd while models are built: keep the repo importable
+        sys.path.insert(1, repo)
     _installed = True
 
 
@@ -137,6 +161,9 @@ BERT_BASE_CONFIG = {
     "num_hidden_layers": 12, "pad_token_id": 0, "type_vocab_size": 2, "vocab_size": 30522,
 }
 
+# data/bert-large-uncased-12l of configs/pretrain/x2vlm_large_*.yaml: BERT-large width, 12 layers
+BERT_LARGE_12L_CONFIG = dict(BERT_BASE_CONFIG, hidden_size=1024, intermediate_size=4096, num_attention_heads=16)
+
 
 def workdir():
     """Scratch cwd holding configs/config_beit2_*.json (copied) and a synthesised data/bert-base-uncased."""
@@ -144,19 +171,20 @@ def workdir():
     if _workdir is None:
         d = tempfile.mkdtemp(prefix="x2vlm_oracle_")
         os.makedirs(os.path.join(d, "configs"))
-        for n in ("config_beit2_base.json", "config_beit2_large.json"):
-            src = os.path.join(REFERENCE_ROOT, "configs", n)
-            if os.path.exists(src):
-                with open(src) as fi, open(os.path.join(d, "configs", n), "w") as fo:
-                    fo.write(fi.read())
-        bd = os.path.join(d, "data", "bert-base-uncased")
-        os.makedirs(bd)
-        with open(os.path.join(bd, "config.json"), "w") as f:
-            json.dump(BERT_BASE_CONFIG, f)
+        # configs/config_beit2_{base,large}.json hold three values each (checkpoint path, width, patch size); written
+        # here rather than copied so the GPU box (byte-code-only reference) has them too
+        for n, width in (("base", 768), ("large", 1024)):
+            with open(os.path.join(d, "configs", "config_beit2_%s.json" % n), "w") as fo:
+                json.dump({"ckpt": "data/beitv2_%s_patch16_224_pt1k_ft21k.pth" % n, "vision_width": width, "patch_size": 16}, fo)
         vocab = ["[unused%d]" % i for i in range(30522)]
         vocab[0], vocab[100], vocab[101], vocab[102], vocab[103] = "[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"
-        with open(os.path.join(bd, "vocab.txt"), "w") as f:
-            f.write("\n".join(vocab) + "\n")
+        for name, cfg in (("bert-base-uncased", BERT_BASE_CONFIG), ("bert-large-uncased-12l", BERT_LARGE_12L_CONFIG)):
+            bd = os.path.join(d, "data", name)
+            os.makedirs(bd)
+            with open(os.path.join(bd, "config.json"), "w") as f:
+                json.dump(cfg, f)
+            with open(os.path.join(bd, "vocab.txt"), "w") as f:
+                f.write("\n".join(vocab) + "\n")
         _workdir = d
     return _workdir
 
@@ -170,11 +198,15 @@ def base_config(**over):
 
 
 def init_dist():
+    """1-rank process group: the reference's losses call dist.get_rank() / all_gather unconditionally
+    (models/xvlm.py:805-806).  gloo serves CPU tensors, NCCL the CUDA ones when a GPU is present."""
+    import torch
     import torch.distributed as dist
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29577")
-        dist.init_process_group("gloo", rank=0, world_size=1)
+        backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend, rank=0, world_size=1)
 
 
 def build_reference_xvlm(config=None, seed=0):
@@ -188,6 +220,63 @@ def build_reference_xvlm(config=None, seed=0):
         from models.model_pretrain import XVLM
         torch.manual_seed(seed)
         m = XVLM(config or base_config(), load_vision_params=False, load_text_params=False, pretraining=False)
+    finally:
+        os.chdir(cwd)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's UNMODIFIED callers on the B200-native modules (SURVEY.md §7.1 patch point (ii))
+# ---------------------------------------------------------------------------------------------------------------
+class x2k_patched:
+    """Context manager: while active, the reference's model factories resolve to x2vlm_b200's drop-in modules —
+    `models.beit2.{beit_base_patch16, beit_large_patch16, interpolate_pos_embed, load_pretrained_beit2}`,
+    `models.xvlm.{BertModel, BertForMaskedLM}`, `models.model_generation.BertLMHeadModel`,
+    `models.xbert.BertOnlyMLMHead` — so `XVLMBase.__init__` (models/xvlm.py:246-316) builds its encoders from them.
+    No reference file is touched; on exit the reference's own classes are back, so one process can hold the same
+    reference class twice: once on its own encoders, once on the x2k ones."""
+
+    TARGETS = (("models.beit2", ("beit_base_patch16", "beit_large_patch16", "interpolate_pos_embed", "load_pretrained_beit2"), "beit2"),
+               ("models.xvlm", ("BertModel", "BertForMaskedLM"), "xbert"),
+               ("models.model_generation", ("BertLMHeadModel",), "xbert"),
+               ("models.xbert", ("BertOnlyMLMHead",), "xbert"))
+
+    def __enter__(self):
+        import importlib
+        install()
+        from x2vlm_b200 import beit2, xbert
+        mine = {"beit2": beit2, "xbert": xbert}
+        self._saved = []
+        for modname, names, src in self.TARGETS:
+            mod = importlib.import_module(modname)
+            for n in names:
+                self._saved.append((mod, n, getattr(mod, n)))
+                setattr(mod, n, getattr(mine[src], n))
+        return self
+
+    def __exit__(self, *exc):
+        for mod, n, v in self._saved:
+            setattr(mod, n, v)
+
+
+def build_reference_model(cls_path="models.model_pretrain.XVLM", config=None, seed=0, x2k=False, **ctor_kw):
+    """Construct a reference model class (by dotted path) — on the reference's own encoders, or with x2k=True on the
+    B200-native drop-in modules (the class itself and everything it calls stay the reference's code)."""
+    import contextlib
+    import importlib
+    import torch
+    install()
+    init_dist()
+    cwd = os.getcwd()
+    os.chdir(workdir())
+    try:
+        modname, clsname = cls_path.rsplit(".", 1)
+        with (x2k_patched() if x2k else contextlib.nullcontext()):
+            cls = getattr(importlib.import_module(modname), clsname)
+            torch.manual_seed(seed)
+            if not ctor_kw and clsname in ("XVLM",):
+                ctor_kw = dict(load_vision_params=False, load_text_params=False, pretraining=False)
+            m = cls(config or base_config(), **ctor_kw)
     finally:
         os.chdir(cwd)
     return m

@@ -324,5 +324,11 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"] == "image-text pairs/sec pretrain step X2VLM-base bf16"
     assert d["config"]["workload"].startswith("X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch 64/GPU")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference itself (oracle/_ref byte-code, built by __graft_entry__.build()), not the port
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert "UNMODIFIED reference" in d["cpu_baseline"]["sample"]
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    assert d["config"] == bench.workload_config(argparse.Namespace(batch=64, region_images=26, image_only=False), 1)
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

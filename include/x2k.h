@@ -173,7 +173,9 @@ int x2k_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream)
  * the packed QKV projection output in place ([B·L, 3D] for BEiT/BERT self-attention, separate
  * Q and KV buffers for cross-attention) and several query sequences may share one K/V sequence
  * (the image K/V cache across the ITM/MLM passes, models/xvlm.py:859-899).
- * Let Lk_pad = Lk rounded up to 16 (Lk <= 256) and Lk_32 = Lk rounded up to 32.
+ * Any Lq / Lk: up to 256 keys the whole key range of a (sequence, head) stays in TMEM (attn.cu); longer sequences
+ * (384 px / 768 px fine-tuning: N = 577 / 2305) run key-blocked kernels with an online softmax (attn_long.cu).
+ * Let Lk_pad = Lk rounded up to 16 and Lk_32 = Lk rounded up to 32.
  * bias: fp32, element (h,i,j) at bias[h*bias_h_stride + i*bias_q_stride + j] (BEiT relative
  *   position bias already gathered), or NULL.  Strides are multiples of 4, q stride >= Lk_32
  *   (the kernels stage it in coalesced 32-row x 32-column blocks).
@@ -221,10 +223,16 @@ typedef struct X2kAttnArgs {
    * writes delta[b,h,i] = sum_d O[b,i,h,d] * dO[b,i,h,d] there, and the attention kernels read one float per row
    * instead of fetching the row's O and dO at their start (a DRAM round trip on every CTA's critical path). */
   float* delta_ws;
+  /* backward, workspace of the key-blocked kernels (Lq > 256 or Lk > 256): x2k_attn_bwd_workspace_bytes(args) bytes,
+   * 16-byte aligned; fp32 [B*Lq, H*64] into which the key-block CTAs reduce their dQ contributions.  The call zeroes
+   * it on the stream.  NULL is fine whenever the query says 0 bytes. */
+  float* dq_ws;
 } X2kAttnArgs;
 
 int x2k_attn_fwd(const X2kAttnArgs* args, void* stream);
 int x2k_attn_bwd(const X2kAttnArgs* args, void* stream);
+/* Bytes of X2kAttnArgs.dq_ws that x2k_attn_bwd needs for these shapes (B, H, Lq, Lk of *args; 0 = none). */
+int64_t x2k_attn_bwd_workspace_bytes(const X2kAttnArgs* args);
 
 /* Short query sequences (Lq rounded up to 8 <= 64, no bias): several sequences share one 128-row MMA
  * tile.  Self-attention (kv_index == NULL, Lq == Lk-sized segments) is packed automatically inside

@@ -276,7 +276,7 @@ def build_reference_model(cls_path="models.model_pretrain.XVLM", config=None, se
             torch.manual_seed(seed)
             if not ctor_kw and clsname in ("XVLM",):
                 ctor_kw = dict(load_vision_params=False, load_text_params=False, pretraining=False)
-            m = cls(config or base_config(), **ctor_kw)
+            m = cls(config=config or base_config(), **ctor_kw)
     finally:
         os.chdir(cwd)
     return m

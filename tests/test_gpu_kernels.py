@@ -176,7 +176,9 @@ def _heads(x, B, L, H):
     return x.view(B, L, H, 64).permute(0, 2, 1, 3)
 
 
-@pytest.mark.parametrize("case", ["beit", "text", "text3d", "cross_shared", "text_dropout", "n256"])
+@pytest.mark.parametrize("case", ["beit", "text", "text3d", "cross_shared", "text_dropout", "n256",
+                                  # key-blocked online-softmax kernels (attn_long.cu): 384 px / 768 px fine-tuning shapes
+                                  "beit577", "beit2305", "cross577_shared_dropout", "causal300", "cross2305"])
 def test_attention_fwd_bwd(dev, case):
     from x2vlm_b200 import ops
     from oracle import philox
@@ -191,6 +193,18 @@ def test_attention_fwd_bwd(dev, case):
     elif case == "cross_shared":
         B, Lq, Lk, n_kv = 7, 40, 197, 3
         kv_index = torch.tensor([0, 2, 1, 1, 0, 2, 2], device=dev, dtype=torch.int32)
+    elif case == "beit577":      # 384 px: 24 x 24 patches + cls, dense rel-pos bias streamed per key block
+        B, Lq, Lk, n_kv, H = 2, 577, 577, 2, 2
+    elif case == "beit2305":     # 768 px: 48 x 48 patches + cls (configs/finetune/vqa2_base.yaml)
+        B, Lq, Lk, n_kv, H = 1, 2305, 2305, 1, 2
+    elif case == "cross577_shared_dropout":  # captions over 384 px image tokens, shared K/V, key mask, prob. dropout
+        B, Lq, Lk, n_kv, H = 7, 40, 577, 3, 4
+        kv_index = torch.tensor([0, 2, 1, 1, 0, 2, 2], device=dev, dtype=torch.int32)
+        p_drop = 0.1
+    elif case == "cross2305":
+        B, Lq, Lk, n_kv, H = 2, 40, 2305, 2, 2
+    elif case == "causal300":    # more than two query tiles with a per-query (3-D) mask
+        B, Lq, Lk, n_kv, H = 2, 300, 300, 2, 2
     else:
         B, Lq, Lk, n_kv = 5, 40, 40, 5
     if case == "text_dropout":
@@ -207,12 +221,12 @@ def test_attention_fwd_bwd(dev, case):
         qv, kv_, vv = qkv[:, :D], kvbuf[:, :D], kvbuf[:, D:]
     bias = mask = None
     per_query = False
-    if case in ("beit", "n256"):
+    if case in ("beit", "n256", "beit577", "beit2305"):
         bias = torch.zeros(H, Lq, ld, device=dev); bias[:, :, :Lk] = torch.randn(H, Lq, Lk, device=dev, generator=g)
-    if case in ("text", "text_dropout", "cross_shared"):
+    if case in ("text", "text_dropout", "cross_shared", "cross577_shared_dropout", "cross2305"):
         m01 = (torch.rand(B, Lk, device=dev, generator=g) > 0.3).float(); m01[:, 0] = 1
         mask = torch.zeros(B, ld, device=dev); mask[:, :Lk] = (1 - m01) * -10000.0
-    if case == "text3d":
+    if case in ("text3d", "causal300"):
         m01 = torch.tril(torch.ones(Lq, Lk, device=dev)).expand(B, -1, -1)
         mask = torch.zeros(B, Lq, ld, device=dev); mask[:, :, :Lk] = (1 - m01) * -10000.0
         per_query = True
@@ -409,24 +423,29 @@ def test_flat_adamw_matches_torch(dev):
     assert abs(out.item() - (p.double() ** 2).sum().item()) < 1e-4 * out.item()
 
 
-def test_attention_rejects_long_keys(dev):
-    """Maximum size: Lk <= 256 keys fit the single-pass TMEM softmax; longer sequences (384 px fine-tuning: 577 patches)
-    must fail loudly — X2K_ERR_* with a message — never fall back or truncate."""
-    from x2vlm_b200 import ops
-    from x2vlm_b200._capi import X2kError
-    B, H, L = 2, 2, 300
-    q = torch.randn(B * L, 3 * H * 64, device=dev).bfloat16()
+def test_attention_workspace_query_and_loud_failure(dev):
+    """x2k_attn_bwd_workspace_bytes: 0 for the whole-range kernels (Lq, Lk <= 256), B*Lq*H*64 fp32 for the key-blocked ones;
+    a long backward without the workspace fails loudly (X2K_ERR_ARG) instead of truncating or falling back."""
+    import ctypes
+    from x2vlm_b200 import _capi as C
+    a = C.X2kAttnArgs()
+    a.B, a.H, a.Lq, a.Lk = 3, 12, 197, 197
+    assert C.lib().x2k_attn_bwd_workspace_bytes(ctypes.byref(a)) == 0
+    a.Lq, a.Lk = 40, 577
+    assert C.lib().x2k_attn_bwd_workspace_bytes(ctypes.byref(a)) == 3 * 40 * 12 * 64 * 4
+    a.Lq, a.Lk = 577, 577
+    assert C.lib().x2k_attn_bwd_workspace_bytes(ctypes.byref(a)) == 3 * 577 * 12 * 64 * 4
+    B, H, L = 1, 2, 300
+    t = torch.randn(B * L, 3 * H * 64, device=dev).bfloat16()
     o = torch.empty(B * L, H * 64, device=dev, dtype=torch.bfloat16)
-    lse = torch.empty(B, H, L, device=dev)
-    with pytest.raises(X2kError):
-        ops.attn_fwd(q[:, :H * 64], q[:, H * 64:2 * H * 64], q[:, 2 * H * 64:], B, H, L, L, 0.125, o, lse)
-    # the largest supported shape still runs: 256 queries x 256 keys
-    L = 256
-    q = torch.randn(B * L, 3 * H * 64, device=dev).bfloat16()
-    o = torch.empty(B * L, H * 64, device=dev, dtype=torch.bfloat16)
-    lse = torch.empty(B, H, L, device=dev)
-    ops.attn_fwd(q[:, :H * 64], q[:, H * 64:2 * H * 64], q[:, 2 * H * 64:], B, H, L, L, 0.125, o, lse)
-    qh, kh, vh = (_heads(q[:, i * H * 64:(i + 1) * H * 64].float(), B, L, H) for i in range(3))
-    ref, _ = _attn_ref(qh, kh, vh, 0.125)
-    got = _heads(o.float(), B, L, H)
-    assert (got - ref).abs().max() < 0.03
+    lse = torch.empty(B, H, L, device=dev); delta = torch.empty(B, H, L, device=dev)
+    dqkv = torch.empty_like(t)
+    a = C.X2kAttnArgs()
+    a.q, a.k, a.v = t.data_ptr(), t.data_ptr() + 2 * H * 64, t.data_ptr() + 4 * H * 64
+    a.ld_q = a.ld_k = a.ld_v = a.ld_dq = a.ld_dk = a.ld_dv = 3 * H * 64
+    a.B, a.H, a.Lq, a.Lk, a.scale = B, H, L, L, 0.125
+    a.o, a.ld_o, a.lse, a.d_o, a.ld_do = o.data_ptr(), H * 64, lse.data_ptr(), o.data_ptr(), H * 64
+    a.dq, a.dk, a.dv = dqkv.data_ptr(), dqkv.data_ptr() + 2 * H * 64, dqkv.data_ptr() + 4 * H * 64
+    a.delta_ws = delta.data_ptr()
+    rc = C.lib().x2k_attn_bwd(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == -1 and b"dq_ws" in C.lib().x2k_last_error()

@@ -177,3 +177,87 @@ def test_unmodified_forward_losses_and_backward(models):
     finally:
         ours.zero_grad(set_to_none=True)
         ours.eval()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fine-tuning heads at their own configurations (key-blocked attention: N = 577 / 2305 image tokens)
+# ---------------------------------------------------------------------------------------------------------------
+def _pair(cls_path, config, **kw):
+    """The same reference class twice — on its own encoders and on the x2k ones — with identical weights."""
+    ref = ref_shim.build_reference_model(cls_path, config=config, x2k=False, **kw)
+    _perturb(ref)
+    ours = ref_shim.build_reference_model(cls_path, config=config, x2k=True, **kw)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    return ref.cuda().eval(), ours.cuda().eval()
+
+
+def test_vqa_768px_unmodified_head():
+    """configs/finetune/vqa2_base.yaml: 768 px images (48 x 48 patches + cls = 2305 tokens through every BEiT block, and
+    as the keys of the question encoder's cross-attention), 6-layer BertLMHeadModel answer decoder.  The reference's
+    XVLMForVQA.forward(train=True) (models/model_generation.py:514-549) is called unchanged on the x2k modules."""
+    import types
+    cfg = ref_shim.base_config(image_res=768, pad_token_id=0, num_dec_layers=6, large_lr_for_dec=True)
+    ref, ours = _pair("models.model_generation.XVLMForVQA", cfg)
+    assert type(ours.text_decoder).__module__ == "x2vlm_b200.xbert"
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    image = torch.randn(B, 3, 768, 768, generator=g).cuda()
+    q_ids = torch.randint(1000, 30000, (B, 20), generator=g); q_ids[:, 0] = 101
+    q_att = torch.ones(B, 20, dtype=torch.long); q_att[1, 14:] = 0; q_ids[1, 14:] = 0
+    k = [2, 3]
+    a_ids = torch.randint(1000, 30000, (5, 6), generator=g); a_ids[:, 0] = 101
+    a_att = torch.ones(5, 6, dtype=torch.long); a_att[0, 4:] = 0; a_ids[0, 4:] = 0; a_att[3, 3:] = 0; a_ids[3, 3:] = 0
+    weights = torch.tensor([0.6, 0.4, 0.5, 0.3, 0.2]).cuda()
+    question = types.SimpleNamespace(input_ids=q_ids.cuda(), attention_mask=q_att.cuda())
+    answer = types.SimpleNamespace(input_ids=a_ids.cuda(), attention_mask=a_att.cuda())
+
+    def loss(m, autocast=False):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return float(m(image, question, answer, k=k, weights=weights, train=True))
+
+    want, auto, got = loss(ref), loss(ref, True), loss(ours)
+    print("\nVQA 768px loss: fp32 %.5f  ref-bf16 %.5f  ours %.5f" % (want, auto, got))
+    assert abs(got - want) <= max(RATIO * abs(auto - want), 2e-3 * abs(want)), (want, auto, got)
+    with torch.no_grad():
+        e_ref, _ = ref.get_vision_embeds(image)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e_auto, _ = ref.get_vision_embeds(image)
+        e_ours, _ = ours.get_vision_embeds(image)
+    assert e_ours.shape == (B, 2305, 768)
+    assert _rel(e_ours.float(), e_ref) <= RATIO * _rel(e_auto.float(), e_ref), (_rel(e_ours.float(), e_ref), _rel(e_auto.float(), e_ref))
+    # one training step's backward through 12 BEiT blocks at N = 2305 (key-blocked backward, dQ workspace, dS export)
+    ours.train()
+    torch.manual_seed(0)
+    l = ours(image, question, answer, k=k, weights=weights, train=True)
+    l.backward()
+    for n in ("vision_encoder.blocks.0.attn.relative_position_bias_table", "vision_encoder.blocks.11.attn.qkv.weight",
+              "text_encoder.encoder.layer.12.crossattention.self.key.weight", "text_decoder.bert.encoder.layer.0.crossattention.self.value.weight"):
+        p = dict(ours.named_parameters())[n]
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
+
+
+def test_retrieval_384px_unmodified_head():
+    """XVLMForRetrieval.forward (models/model_retrieval.py:14-26) at 384 px (N = 577): ITC against the reference, then a
+    train-mode ITC + ITM backward with sample ids (captions of one image are mutual positives)."""
+    cfg = ref_shim.base_config(image_res=384)
+    ref, ours = _pair("models.model_retrieval.XVLMForRetrieval", cfg)
+    b = _dev(synth.image_text_batch(6, 40, image_res=384, seed=21))
+    idx = torch.tensor([0, 1, 1, 2, 3, 3]).cuda()
+
+    def itc(m, autocast=False):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            ie, _ = m.get_vision_embeds(b["image"])
+            te = m.get_text_embeds(b["text_ids"], b["text_atts"])
+            fi, ft = m.get_features(ie, te)
+            return ie.float(), float(m.get_contrastive_loss(fi, ft, idx=idx))
+
+    (e_ref, want), (e_auto, auto), (e_ours, got) = itc(ref), itc(ref, True), itc(ours)
+    assert e_ours.shape == (6, 577, 768)
+    assert _rel(e_ours, e_ref) <= RATIO * _rel(e_auto, e_ref)
+    assert abs(got - want) <= max(RATIO * abs(auto - want), 2e-3 * abs(want)), (want, auto, got)
+    ours.train()
+    torch.manual_seed(0)
+    loss_itc, loss_itm = ours(b["image"], b["text_ids"], b["text_atts"], idx=idx)
+    (loss_itc + loss_itm).backward()
+    g = ours.vision_encoder.blocks[3].attn.relative_position_bias_table.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0

@@ -40,6 +40,11 @@ int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint
 int attn_pack_fwd(const X2kAttnArgs& a, cudaStream_t stream);
 int attn_pack_bwd(const X2kAttnArgs& a, cudaStream_t stream);
 
+// attn_long.cu: key-blocked (online softmax) attention for Lk > 256 / Lq > 256.
+int attn_long_fwd(const X2kAttnArgs& a, cudaStream_t stream);
+int attn_long_bwd(const X2kAttnArgs& a, cudaStream_t stream);
+int64_t attn_long_bwd_ws_bytes(const X2kAttnArgs& a);
+
 #define X2K_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

@@ -277,6 +277,10 @@ def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None,
     a.ld_dq, a.ld_dk, a.ld_dv = dq.stride(0), dk.stride(0), dv.stride(0)
     delta_ws = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)  # rowsum(dO * O), filled by a pre-kernel
     a.delta_ws = delta_ws.data_ptr()
+    ws_bytes = int(C.lib().x2k_attn_bwd_workspace_bytes(ctypes.byref(a)))
+    if ws_bytes:  # key-blocked kernels (Lq or Lk > 256): fp32 dQ accumulator shared by the key-block CTAs
+        dq_ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=q.device)
+        a.dq_ws = dq_ws.data_ptr()
     if ds_out is not None:  # [B, H, Lq, ld]
         a.ds_out = ds_out.data_ptr()
         a.ds_b_stride, a.ds_h_stride, a.ds_q_stride = ds_out.stride(0), ds_out.stride(1), ds_out.stride(2)

@@ -33,6 +33,33 @@ FLOP_REGION_SAMPLE = 3 * 48.92e9     # region iteration, per region-text sample 
 FLOP_VISION_IMAGE = 3 * 35.13e9      # + vision once per unique region image
 
 
+# --config: the BASELINE.json workloads.  FLOPs per unit are the reference-algorithm closed forms of SURVEY.md §8(d)
+# (fwd + bwd = 3 x fwd): image-iteration pair, region sample (2 text + 5 fusion + head), vision once per unique region image.
+CONFIGS = {
+    "base": dict(model="base", name="X2VLM-base", batch=64, region_images=26, flop_pair=231.4e9, flop_region=3 * 48.92e9,
+                 flop_image=3 * 35.13e9, what="pretrain step (ITC+ITM+MLM+bbox)"),
+    "large": dict(model="large", name="X2VLM-large (6 fusion layers)", batch=32, region_images=14, flop_pair=591.4e9,
+                  flop_region=3 * 86.30e9, flop_image=3 * 123.11e9, what="pretrain step (ITC+ITM+MLM+bbox)"),
+    "large12": dict(model="large12", name="X2VLM-large (12 fusion layers)", batch=32, region_images=14, flop_pair=738.3e9,
+                    flop_region=3 * 147.45e9, flop_image=3 * 123.11e9, what="pretrain step (ITC+ITM+MLM+bbox)"),
+    "video": dict(model="video", name="X2VLM-base video-text (8 frames)", batch=16, region_images=0, flop_pair=969.0e9,
+                  flop_region=0.0, flop_image=0.0, what="video pretrain step (ITC+ITM+MLM), 8 frames avgpool"),
+}
+
+
+def model_config(kind):
+    from x2vlm_b200 import pretrain
+    if kind == "base":
+        return pretrain.base_config()
+    if kind == "large":    # configs/pretrain/x2vlm_large_1b_stage2.yaml: beit2-large + bert-large 12 text / 6 fusion layers
+        return pretrain.large_config()
+    if kind == "large12":  # BASELINE.json's literal "12 fusion layers"
+        return pretrain.large_config(text_num_hidden_layers=24, text_fusion_start_at=12)
+    if kind == "video":    # MSRVTT shape: 8 frames x 224 px, learned frame offsets, mean over time
+        return pretrain.base_config(video_encoding="avgpool", frame_len=8, add_frame_pos=True)
+    raise ValueError(kind)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -80,13 +107,15 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_batches(batch, n_img, rank, pin):
+def make_batches(batch, n_img, rank, pin, frames=0):
     from x2vlm_b200 import synth
     ib = synth.image_text_batch(batch, 40, seed=1234 + rank)
-    rb = synth.region_batch(n_img, batch, 40, seed=4321 + rank)
+    if frames:
+        ib["image"] = torch.randn(batch, frames, 3, 224, 224, generator=torch.Generator().manual_seed(99 + rank))
+    rb = synth.region_batch(n_img, batch, 40, seed=4321 + rank) if n_img else None
     if pin:
         ib = {k: v.pin_memory() for k, v in ib.items()}
-        rb = {k: v.pin_memory() for k, v in rb.items()}
+        rb = {k: v.pin_memory() for k, v in rb.items()} if rb is not None else None
     return ib, rb
 
 
@@ -111,15 +140,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = pretrain.XVLM(pretrain.base_config())
+    C = CONFIGS[args.config]
+    FLOP_IMAGE_PAIR, FLOP_REGION_SAMPLE, FLOP_VISION_IMAGE = C["flop_pair"], C["flop_region"], C["flop_image"]
+    model = pretrain.XVLM(model_config(C["model"]))
     acc = accelerator.X2kDDPAccelerator({"lr": 1e-4, "weight_decay": 0.01, "bucket_mb": args.bucket_mb})
     ddp, opt, _ = acc.set_up(model, None, None, local, world, rank)
     ddp.train()
     XF.manual_seed(1234 + rank)
     B, n_img = args.batch, args.region_images
-    ib_h, rb_h = make_batches(B, n_img, rank, pin=True)
-    if args.image_only:
-        rb_h = None
+    ib_h, rb_h = make_batches(B, 0 if args.image_only else n_img, rank, pin=True, frames=8 if C["model"] == "video" else 0)
 
     def step(ib, rb, read_loss):
         with torch.no_grad():
@@ -220,7 +249,7 @@ def run_ours(args):
 
     # image-only variant (64 pairs, 14.79 TFLOP / step): one more captured graph, N = 1 only
     image_only = None
-    if world == 1 and rb_h is not None and graphed is not None and not args.skip_image_only:
+    if world == 1 and rb_h is not None and graphed is not None and not args.skip_image_only and args.config == "base":
         try:
             g_img = acc.graph_step(lambda inp: eager_step(inp["i"], None, False), {"i": ib_d}, optimizer=opt, warmup=2)
             for _ in range(2):
@@ -246,9 +275,10 @@ def run_ours(args):
     if rank == 0:
         sys.stderr.write("[bench] timed: %.2f ms/step resident (host enqueue %.2f ms/step), %.2f ms/step e2e\n"
                          % (ms / args.steps, host_enqueue_ms, ms_e2e / args.steps))
-        cpu = cpu_baseline(image_only=rb_h is None) if (world == 1 and not args.no_cpu_baseline) else None
+        base_cfg = args.config == "base"
+        cpu = cpu_baseline(image_only=rb_h is None) if (world == 1 and not args.no_cpu_baseline and base_cfg) else None
         eager = None
-        if world == 1 and not args.no_gpu_eager:
+        if world == 1 and not args.no_gpu_eager and base_cfg:
             try:
                 if graphed is not None:
                     graphed.release()
@@ -257,7 +287,7 @@ def run_ours(args):
             except Exception as e:  # the comparator must never cost the main line
                 eager = {"unavailable": repr(e)[:300]}
         out = {
-            "metric": "image-text pairs/sec pretrain step X2VLM-base bf16", "value": value, "unit": "pairs/s",
+            "metric": metric_name(args), "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
@@ -336,13 +366,19 @@ def dominant_kernel_roofline(step_fn, peak_sustained, src, table_path=None):
             "traffic": ROOFLINE_TRAFFIC, "other_kernels": other}
 
 
+def metric_name(args):
+    name = CONFIGS[getattr(args, "config", "base")]["name"].split(" (")[0].replace(" video-text", "")
+    return "image-text pairs/sec pretrain step %s bf16" % name
+
+
 def workload_config(args, world):
     """The static description of the workload — identical in both arms' JSON lines (`config`), so the driver's
     same-config check compares like with like; everything measured goes under `detail`."""
+    C = CONFIGS[getattr(args, "config", "base")]
     B, n_img = args.batch, (0 if args.image_only else args.region_images)
-    return {"workload": "X2VLM-base pretrain step (ITC+ITM+MLM+bbox), 224px, 40 tok, batch %d/GPU%s; random-init weights"
-                        % (B, " image iteration only" if args.image_only else ""),
-            "global_batch": B * world, "pairs_per_step_per_gpu": B if args.image_only else 2 * B,
+    return {"workload": "%s %s, 224px, 40 tok, batch %d/GPU%s; random-init weights"
+                        % (C["name"], C["what"], B, " image iteration only" if (args.image_only and C["region_images"]) else ""),
+            "global_batch": B * world, "pairs_per_step_per_gpu": B if not n_img else 2 * B,
             "region_images_per_gpu": n_img, "seq_len": 40, "image_res": 224, "parallelism": "dp%d" % world,
             "optimizer": "AdamW(0.9, 0.98, eps 1e-8, wd 0.01) + clip 1.0"}
 
@@ -528,6 +564,89 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
+def run_retrieval(args):
+    """--config retrieval (BASELINE config 4): 1 000 images x 5 000 captions, ITC all-pairs + top-128 ITM re-rank in both
+    directions (Retrieval.py:71-157) on one GPU.  A "step" is one whole evaluation; value = re-ranked (image, caption)
+    pairs per second.  Reference-algorithm FLOPs: 35.1 T vision + 34.3 T text + 768 000 x 6.93 G rerank."""
+    from x2vlm_b200 import ops, pretrain, retrieval, synth
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n_img, n_txt, k = args.retrieval_images, args.retrieval_texts, args.k_test
+    torch.manual_seed(0)
+    model = pretrain.XVLM(pretrain.base_config()).to(dev).eval()
+    b = synth.image_text_batch(n_txt, 40, seed=1234)
+    g = torch.Generator().manual_seed(5)
+    images = torch.randn(n_img, 3, 224, 224, generator=g).pin_memory()
+    ids, atts = b["text_ids"].pin_memory(), b["text_atts"].pin_memory()
+
+    def one(resident):
+        im, ti, ta = (images.to(dev, non_blocking=True), ids.to(dev, non_blocking=True), atts.to(dev, non_blocking=True)) \
+            if not resident else resident
+        s_i2t, s_t2i, sims = retrieval.evaluation(model, im, ti, ta, k_test=k, image_bs=100, text_bs=500,
+                                                  rows_per_call=args.rows_per_call)
+        return s_i2t, s_t2i
+
+    res = (images.to(dev), ids.to(dev), atts.to(dev))
+    for _ in range(max(1, min(args.warmup, 1))):
+        one(res)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    l0 = ops.launch_count()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(1, args.steps)
+    st.record()
+    for _ in range(n):
+        s_i2t, s_t2i = one(res)
+    en.record()
+    torch.cuda.synchronize()
+    ms = st.elapsed_time(en) / n
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop()
+    st.record()
+    for _ in range(n):   # end to end: pinned host images / token ids -> device, both score matrices back on the host
+        s_i2t, s_t2i = one(None)
+        h1, h2 = s_i2t.cpu(), s_t2i.cpu()
+    en.record()
+    torch.cuda.synchronize()
+    ms_e2e = st.elapsed_time(en) / n
+    pairs = n_img * min(k, n_txt) + n_txt * min(k, n_img)
+    flop_ref = n_img * 35.13e9 + n_txt * 6.85e9 + pairs * 6.93e9            # reference algorithm (K/V re-projected per pair)
+    flop_exec = n_img * 35.13e9 + n_txt * 6.85e9 + pairs * (6.93e9 - 2.79e9) + n_img * 2.79e9  # i2t: K/V once per image
+    _, sustained, _, src = peaks()
+    out = {"metric": "image-text pairs/sec retrieval rerank X2VLM-base bf16", "value": pairs / (ms / 1e3), "unit": "pairs/s",
+           "n_gpus": 1, "steps": n, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "retrieval inference: %d x 224px images vs %d 40-token captions, ITC all-pairs + top-%d ITM "
+                                  "cross-attention rerank both ways; random-init weights" % (n_img, n_txt, k),
+                      "reranked_pairs": pairs, "rows_per_call": args.rows_per_call},
+           "detail": {"reference_algorithm_tflop": flop_ref / 1e12, "executed_tflop_lower_bound": flop_exec / 1e12,
+                      "redundant_kv_tflop_removed_i2t": (n_img * min(k, n_txt) - n_img) * 2.79e9 / 1e12,
+                      "tflops_reference_algorithm": flop_ref / (ms / 1e3) / 1e12,
+                      "frac_of_%s_sustained_bf16_peak" % src: flop_ref / (ms / 1e3) / 1e12 / sustained,
+                      "note": "t2i candidates are de-duplicated per call: each distinct image's K/V is projected once per call"},
+           "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": images.numel() * 4 + ids.numel() * 8 + atts.numel() * 8,
+                   "d2h_bytes_per_step": 2 * n_img * n_txt * 4},
+           "gpu_launches": launches, "clocks": clocks}
+    if args.retrieval_eager:
+        try:
+            from oracle import ref_shim
+            ref = ref_shim.build_reference_model().to(dev).eval()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ref_shim.run_reference_retrieval(ref, res[0], res[1], res[2], k, "cuda", image_bs=100, text_bs=500)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["gpu_eager_baseline"] = {"value": pairs / dt, "unit": "pairs/s", "ms_per_step": dt * 1e3,
+                                         "what": "UNMODIFIED reference Retrieval.evaluation loop on the reference's modules, "
+                                                 "PyTorch eager, torch.autocast(cuda, bfloat16), same GPU, resident inputs",
+                                         "speedup_value_over_eager": (pairs / (ms / 1e3)) / (pairs / dt)}
+        except Exception as e:
+            out["gpu_eager_baseline"] = {"unavailable": repr(e)[:300]}
+    emit_json(out)
+
+
 _JSON_FD = None
 
 
@@ -558,8 +677,15 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--region-images", type=int, default=26)
+    ap.add_argument("--config", default="base", choices=sorted(CONFIGS) + ["retrieval"],
+                    help="BASELINE.json workload: base (headline), large / large12, video, retrieval (1k x 5k, k = 128)")
+    ap.add_argument("--retrieval-images", type=int, default=1000)
+    ap.add_argument("--retrieval-texts", type=int, default=5000)
+    ap.add_argument("--k-test", type=int, default=128)
+    ap.add_argument("--rows-per-call", type=int, default=8)
+    ap.add_argument("--retrieval-eager", action="store_true", help="also time the reference's own evaluation loop (eager, bf16)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--region-images", type=int, default=None)
     ap.add_argument("--image-only", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=48.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -569,6 +695,14 @@ def main():
     ap.add_argument("--kernel-table", default=None, help="write the per-shape GEMM / attention timing table (markdown) here")
     ap.add_argument("--profile", action="store_true", help="one step inside cudaProfilerStart/Stop, no JSON (for ncu)")
     args = ap.parse_args()
+    if args.config == "retrieval":
+        return run_retrieval(args)
+    if args.batch is None:
+        args.batch = CONFIGS[args.config]["batch"]
+    if args.region_images is None:
+        args.region_images = CONFIGS[args.config]["region_images"]
+    if not args.region_images:
+        args.image_only = True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -203,10 +203,12 @@ def init_dist():
     import torch
     import torch.distributed as dist
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29577")
+        import socket
+        with socket.socket() as sk:  # a free port of our own: never the inherited MASTER_PORT (a parent may hold it)
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
         backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
-        dist.init_process_group(backend, rank=0, world_size=1)
+        dist.init_process_group(backend, init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
 
 
 def build_reference_xvlm(config=None, seed=0):
@@ -280,3 +282,38 @@ def build_reference_model(cls_path="models.model_pretrain.XVLM", config=None, se
     finally:
         os.chdir(cwd)
     return m
+
+
+def run_reference_retrieval(model, images, text_ids, text_atts, k_test, device, image_bs=64, text_bs=256):
+    """The reference's own Retrieval.evaluation loop (Retrieval.py:71-157) on pre-tokenised tensors: the data loader and
+    the tokenizer are stand-ins that hand out slices of `images` / `text_ids` / `text_atts`; everything that computes is
+    the reference's code.  Returns (score_matrix_i2t, score_matrix_t2i) as numpy arrays, like the reference."""
+    import importlib
+    import torch
+    from types import SimpleNamespace
+    install()
+    cwd = os.getcwd()
+    os.chdir(workdir())
+    try:
+        Retrieval = importlib.import_module("Retrieval")
+    finally:
+        os.chdir(cwd)
+    n_img, n_txt = images.shape[0], text_ids.shape[0]
+
+    class Tok:
+        def __call__(self, text, **kw):
+            sel = torch.as_tensor(list(text), device=text_ids.device)
+            out = SimpleNamespace(input_ids=text_ids[sel], attention_mask=text_atts[sel])
+            out.to = lambda dev: SimpleNamespace(input_ids=out.input_ids.to(dev), attention_mask=out.attention_mask.to(dev))
+            return out
+
+    class Loader:
+        dataset = SimpleNamespace(text=list(range(n_txt)), image=list(range(n_img)))
+
+        def __iter__(self):
+            for i in range(0, n_img, image_bs):
+                yield images[i:i + image_bs], torch.arange(i, min(n_img, i + image_bs))
+
+    Retrieval.args = SimpleNamespace(distributed=False)
+    return Retrieval.evaluation(model, Loader(), Tok(), torch.device(device),
+                                {"batch_size_test_text": text_bs, "max_tokens": text_ids.shape[1], "k_test": k_test})

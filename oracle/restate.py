@@ -68,16 +68,18 @@ def beit_mlp(x, sd, pfx):
     return F.linear(h, sd[pfx + "mlp.fc2.weight"], sd[pfx + "mlp.fc2.bias"])
 
 
-def beit_block(x, sd, pfx, num_heads, drop_path_scale=None):
-    """Pre-LN block with LayerScale; drop_path_scale = per-sample keep/(1-p) [B] or None
-    (models/beit2.py:191-209; timm drop_path is per sample)."""
+def beit_block(x, sd, pfx, num_heads, drop_path_scale=None, drop_path_scale2=None):
+    """Pre-LN block with LayerScale; drop_path_scale / drop_path_scale2 = per-sample keep/(1-p) [B] (or None) of the
+    attention / MLP branch — the reference draws them independently (models/beit2.py:204-207; timm drop_path is per
+    sample).  Passing only the first applies it to both branches."""
     dp = 1.0 if drop_path_scale is None else drop_path_scale.view(-1, 1, 1)
+    dp2 = dp if drop_path_scale2 is None else drop_path_scale2.view(-1, 1, 1)
     C = x.shape[-1]
     y, prob = beit_attention(F.layer_norm(x, (C,), sd[pfx + "norm1.weight"], sd[pfx + "norm1.bias"], 1e-6), sd, pfx,
                              num_heads)
     x = x + dp * (sd[pfx + "gamma_1"] * y)
     y = beit_mlp(F.layer_norm(x, (C,), sd[pfx + "norm2.weight"], sd[pfx + "norm2.bias"], 1e-6), sd, pfx)
-    x = x + dp * (sd[pfx + "gamma_2"] * y)
+    x = x + dp2 * (sd[pfx + "gamma_2"] * y)
     return x, prob
 
 

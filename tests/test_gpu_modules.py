@@ -104,13 +104,14 @@ def test_beit_block_backward_vs_oracle(dev):
     x = torch.randn(3, 197, 128, generator=gen)
     dy = torch.randn(3, 197, 128, generator=gen)
     dp = torch.tensor([1.0, 0.0, 1.0 / 0.9])
+    dp2 = torch.tensor([0.0, 1.0 / 0.9, 1.0 / 0.9])  # independent draw of the MLP branch (beit2.py:204-207)
     sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state_dict"].items()}
     xr = x.clone().requires_grad_(True)
-    yr, _ = restate.beit_block(xr, sd, "blocks.1.", 2, dp)
+    yr, _ = restate.beit_block(xr, sd, "blocks.1.", 2, dp, dp2)
     yr.backward(dy)
     xg = x.to(dev).requires_grad_(True)
     from x2vlm_b200 import functional as XF
-    y = XF.beit_block(xg, blk, dp.to(dev))
+    y = XF.beit_block(xg, blk, dp.to(dev), dp2.to(dev))
     y.backward(dy.to(dev))
     assert rel_l2(y.detach().cpu(), yr.detach()) < 1e-2
     assert rel_l2(xg.grad.cpu(), xr.grad) < 3e-2

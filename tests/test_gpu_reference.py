@@ -261,3 +261,44 @@ def test_retrieval_384px_unmodified_head():
     (loss_itc + loss_itm).backward()
     g = ours.vision_encoder.blocks[3].attn.relative_position_bias_table.grad
     assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_retrieval_k128_vs_reference_evaluation_loop(models):
+    """BASELINE config 4's algorithm at its own k: ITC all-pairs + top-128 ITM re-rank, both directions.  The batched
+    x2k engine (x2vlm_b200.retrieval, shared image K/V) against the reference's unmodified Retrieval.evaluation loop
+    (Retrieval.py:71-157) on the reference's fp32 modules, 160 images x 640 captions on the same GPU: identical candidate
+    sets wherever the similarity margin allows, ITM scores within the bf16 budget, identical recall bookkeeping."""
+    import numpy as np
+    from x2vlm_b200 import pretrain, retrieval
+    ref, _ = models
+    mine = pretrain.XVLM(pretrain.base_config())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.cuda().eval()
+    n_img, n_txt, k = 160, 640, 128
+    b = synth.image_text_batch(n_txt, 40, seed=99)
+    images, ids, atts = b["image"][:n_img].cuda(), b["text_ids"].cuda(), b["text_atts"].clone().cuda()
+    atts[5, 22:] = 0
+    atts[77, 31:] = 0
+    w_i2t, w_t2i = ref_shim.run_reference_retrieval(ref, images, ids, atts, k, "cuda", image_bs=32, text_bs=128)
+    w_i2t, w_t2i = torch.from_numpy(w_i2t), torch.from_numpy(w_t2i)
+    s_i2t, s_t2i, sims = retrieval.evaluation(mine, images, ids, atts, k_test=k, image_bs=32, text_bs=128, rows_per_call=8)
+    s_i2t, s_t2i = s_i2t.cpu(), s_t2i.cpu()
+    assert s_i2t.shape == (n_img, n_txt) and s_t2i.shape == (n_txt, n_img)
+    assert int((s_i2t > -99).sum()) == n_img * k and int((s_t2i > -99).sum()) == n_txt * k
+    # candidate sets: bf16 similarities may swap candidates that are tied at the rank-k boundary; everything else is equal
+    both_i = (s_i2t > -99) & (w_i2t > -99)
+    both_t = (s_t2i > -99) & (w_t2i > -99)
+    assert int(both_i.sum()) >= 0.97 * n_img * k and int(both_t.sum()) >= 0.97 * n_txt * k, (int(both_i.sum()), int(both_t.sum()))
+    scale = max(1.0, float(w_i2t[both_i].abs().max()))
+    e_i = (s_i2t[both_i] - w_i2t[both_i]).abs()
+    e_t = (s_t2i[both_t] - w_t2i[both_t]).abs()
+    print("\nretrieval k=128: i2t max|d| %.3e mean %.3e, t2i max|d| %.3e mean %.3e (score scale %.2f)"
+          % (e_i.max(), e_i.mean(), e_t.max(), e_t.mean(), scale))
+    assert float(e_i.max()) < 4e-2 * scale and float(e_t.max()) < 4e-2 * scale
+    assert float(e_i.mean()) < 6e-3 * scale and float(e_t.mean()) < 6e-3 * scale
+    # recall bookkeeping on a synthetic ground truth: same numbers from both score matrices up to near-ties
+    txt2img = {j: j % n_img for j in range(n_txt)}
+    img2txt = {i: [j for j in range(n_txt) if j % n_img == i] for i in range(n_img)}
+    r_mine = retrieval.itm_eval(s_i2t, s_t2i, txt2img, img2txt)
+    r_ref = retrieval.itm_eval(w_i2t, w_t2i, txt2img, img2txt)
+    assert abs(r_mine["r_mean"] - r_ref["r_mean"]) <= 1.0, (r_mine, r_ref)

@@ -211,7 +211,8 @@ def _retrieval_worker(rank, world, port, q):
     mine = torch.full((n, 5), -100.0)
     mine[start:end] = full[start:end]
     retrieval.combine_rank_rows(mine)
-    q.put((rank, (start, end, w), bool(torch.equal(mine, full))))
+    # the reference's SUM of -100-filled matrices (Retrieval.py:145-148): every entry shifted by -100 * (W - 1)
+    q.put((rank, (start, end, w), bool(torch.equal(mine, full - 100.0 * (w - 1)))))
     dist.destroy_process_group()
 
 
@@ -332,3 +333,63 @@ def test_bench_reference_arm_prints_one_json_line():
     import bench
     assert d["config"] == bench.workload_config(argparse.Namespace(batch=64, region_images=26, image_only=False), 1)
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.reference
+def test_set_up_takes_over_reference_optimizer_and_scheduler(xvlm):
+    """The drop-in flow of Pretrain.py:560-579: optim.create_optimizer -> scheduler.create_scheduler -> accelerator.set_up
+    -> reinit_scheduler_properties_mysched.  The flat optimizer takes over the reference AdamW's groups one to one, is a
+    real torch Optimizer (LambdaLR accepts it), follows the scheduler, and round-trips its state."""
+    import copy
+    import types
+    from oracle import ref_shim
+    from x2vlm_b200.accelerator import FlatAdamW, rebind_scheduler
+    from x2vlm_b200.params import ParamArena
+    ref_shim.install()
+    import optim as ref_optim
+    import scheduler as ref_sched
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    m = torch.nn.Module()
+    m.vision_encoder = copy.deepcopy(xvlm.vision_encoder.blocks[0])
+    m.text_encoder = copy.deepcopy(xvlm.text_encoder.bert.encoder.layer[12])
+    m.head = torch.nn.Linear(8, 8)
+    m.text_encoder.intermediate.dense.weight.requires_grad_(False)      # a frozen weight (fine-tuning)
+    args = types.SimpleNamespace(lr=1e-4, weight_decay=0.01, lr_mult=2, vision_lr=2e-5, text_lr=4e-5)
+    opt = ref_optim.create_optimizer(args, m)                           # the reference's own grouping (optim.py:26-104)
+    sch = ref_sched.create_scheduler(AttrDict(sched="linear", epochs=1, step_per_epoch=100, num_warmup_steps=10), opt)
+    arena = ParamArena(m)
+    flat = FlatAdamW.from_optimizer(m, arena, opt)
+    assert isinstance(flat, torch.optim.Optimizer) and len(flat.param_groups) == len(opt.param_groups) == 10
+    for g0, g1 in zip(opt.param_groups, flat.param_groups):
+        assert [id(p) for p in g0["params"]] == [id(p) for p in g1["params"]]
+        assert g1["weight_decay"] == g0["weight_decay"] and tuple(g1["betas"]) == (0.9, 0.98) and g1["eps"] == 1e-8
+    sch2 = rebind_scheduler(sch, flat)
+    assert sch2.optimizer is flat
+    # Pretrain.py:33-51 re-initialises the scheduler on the optimizer set_up returned
+    assert sch2.optimizer == flat
+    sch2.__init__(flat, sch2.lr_lambdas[0], last_epoch=-1)
+    assert all(g["lr"] == 0.0 for g in flat.param_groups)               # warm-up starts at 0
+    for _ in range(5):
+        sch2.step()
+    lrs = [g["lr"] for g in flat.param_groups]
+    assert abs(lrs[0] - 0.5e-4) < 1e-12 and abs(lrs[4] - 1e-5) < 1e-12 and abs(lrs[6] - 2e-5) < 1e-12
+    flat._upload_hparams()
+    names = {id(p): n for n, p in m.named_parameters()}
+    for i, p in enumerate(arena.params):
+        want = 0.0 if not p.requires_grad else (1e-5 if names[id(p)].startswith("vision_encoder") else
+                                                2e-5 if names[id(p)].startswith("text_encoder") else 0.5e-4)
+        assert abs(float(flat.seg_lr[i]) - want) < 1e-10, names[id(p)]
+    # checkpoint round trip (training_states, Pretrain.py:603)
+    flat.exp_avg.normal_(); flat.exp_avg_sq.uniform_(); flat.step_dev.fill_(7)
+    sd = flat.state_dict()
+    other = FlatAdamW.from_optimizer(m, arena, ref_optim.create_optimizer(args, m))
+    other.load_state_dict(sd)
+    assert torch.equal(other.exp_avg, flat.exp_avg) and int(other.step_dev) == 7
+    assert [g["lr"] for g in other.param_groups] == lrs
+    # anything that is not AdamW is rejected loudly
+    with pytest.raises(TypeError):
+        FlatAdamW.from_optimizer(m, arena, torch.optim.SGD(m.parameters(), lr=0.1))

@@ -206,38 +206,11 @@ def test_itc_idx_labels_and_negative_weights_match_reference(ref, monkeypatch):
 def test_retrieval_scores_match_reference_evaluation(ref):
     """oracle.restate.retrieval_scores against the reference's own Retrieval.evaluation loop (Retrieval.py:71-157) run
     on stub loader / tokenizer objects: ITC similarities, top-k candidates and ITM re-rank scores, both directions."""
-    import os
-    import sys
-    from types import SimpleNamespace
-    sys.path.insert(0, ref_shim.REFERENCE) if hasattr(ref_shim, "REFERENCE") else sys.path.insert(0, "/root/reference")
-    cwd = os.getcwd()
-    os.chdir(ref_shim.workdir())
-    try:
-        import Retrieval
-    finally:
-        os.chdir(cwd)
     n_img, n_txt, k = 3, 5, 2
     b = synth.image_text_batch(n_txt, 40, seed=7)
     images, ids, atts = b["image"][:n_img], b["text_ids"], b["text_atts"].clone()
     atts[1, 30:] = 0
-
-    class Tok:
-        def __call__(self, text, **kw):
-            i, a = torch.stack([ids[t] for t in text]), torch.stack([atts[t] for t in text])
-            out = SimpleNamespace(input_ids=i, attention_mask=a)
-            out.to = lambda dev: out
-            return out
-
-    class Loader:
-        dataset = SimpleNamespace(text=list(range(n_txt)), image=list(range(n_img)))
-
-        def __iter__(self):
-            for i in range(0, n_img, 2):
-                yield images[i:i + 2], torch.arange(i, min(n_img, i + 2))
-
-    Retrieval.args = SimpleNamespace(distributed=False)
-    s_i2t, s_t2i = Retrieval.evaluation(ref, Loader(), Tok(), torch.device("cpu"),
-                                        {"batch_size_test_text": 2, "max_tokens": 40, "k_test": k})
+    s_i2t, s_t2i = ref_shim.run_reference_retrieval(ref, images, ids, atts, k, "cpu", image_bs=2, text_bs=2)
     sd = _sd(ref)
     with torch.no_grad():
         ie = restate.vision_forward(images, sd, "vision_encoder.", 12, 12)
@@ -264,3 +237,28 @@ def test_video_avgpool_matches_reference():
         got = restate.video_forward(frames, sd, restate.Shapes(vision_depth=2), sd["absolute_frame_pos_embed"])
     assert want.shape == (2, 197, 768) and want_atts.shape == (2, 197)
     assert torch.allclose(got, want, atol=2e-5, rtol=1e-5)
+
+
+def test_beit_drop_path_two_independent_draws(ref):
+    """The reference calls self.drop_path twice per block (models/beit2.py:204-207): the attention and the MLP branch get
+    independent per-sample masks.  Replaying the two torch.rand draws of timm's drop_path through the oracle reproduces
+    the reference's train-mode block output — the contract the fused block's (dp_scale, dp_scale2) pair implements."""
+    sd = _sd(ref)
+    blk = ref.vision_encoder.blocks[7]
+    p = blk.drop_path.drop_prob
+    assert p > 0
+    x = torch.randn(6, 197, 768, generator=torch.Generator().manual_seed(11))
+    blk.train()
+    try:
+        torch.manual_seed(123)
+        with torch.no_grad():
+            y_ref, _ = blk(x)
+    finally:
+        blk.eval()
+    torch.manual_seed(123)
+    keep = 1 - p
+    dp1 = torch.floor(keep + torch.rand(6, 1, 1)).view(-1) / keep
+    dp2 = torch.floor(keep + torch.rand(6, 1, 1)).view(-1) / keep
+    with torch.no_grad():
+        y, _ = restate.beit_block(x, sd, "vision_encoder.blocks.7.", 12, dp1, dp2)
+    assert torch.allclose(y, y_ref, atol=1e-5, rtol=1e-5)

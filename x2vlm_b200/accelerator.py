@@ -28,56 +28,78 @@ NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.wei
             "norm2.bias", "norm2.weight")
 
 
-class FlatAdamW:
-    """AdamW(eps=1e-8, betas=(0.9, 0.98)) over the arena's flat buffers with the reference's name-based
-    parameter groups (optim.py:26-104: decay / no-decay x {default, init_params·lr_mult, vision, text, cross})."""
+def name_based_groups(model, params, lr=1e-4, weight_decay=0.01, lr_mult=1.0, vision_lr=None, text_lr=None, cross_lr=None):
+    """The reference's parameter groups (optim.py:26-104): decay / no-decay x {default, init_params * lr_mult, vision, text,
+    cross}, in the reference's group order; frozen parameters are left out."""
+    names = {id(p): n for n, p in model.named_parameters()}
+    init_params = set(getattr(model, "init_params", []) or [])
+    if cross_lr is None:
+        cross_lr = text_lr
+    groups = [{"params": [], "weight_decay": weight_decay, "lr": lr}, {"params": [], "weight_decay": 0.0, "lr": lr},
+              {"params": [], "weight_decay": weight_decay, "lr": lr * lr_mult}, {"params": [], "weight_decay": 0.0, "lr": lr * lr_mult}]
+    if vision_lr is not None:
+        for lr_ in (vision_lr, text_lr, cross_lr):
+            groups += [{"params": [], "weight_decay": weight_decay, "lr": lr_}, {"params": [], "weight_decay": 0.0, "lr": lr_}]
+    for p in params:
+        n = names.get(id(p), "")
+        if not p.requires_grad:
+            continue
+        nd = int(any(k in n for k in NO_DECAY))
+        if vision_lr is not None and n.startswith("vision_encoder"):
+            gi = 4
+        elif vision_lr is not None and n.startswith("text_encoder"):
+            gi = 6
+        elif vision_lr is not None and n.startswith("cross_encoder"):
+            gi = 8
+        elif n in init_params:
+            gi = 2
+        else:
+            gi = 0
+        groups[gi + nd]["params"].append(p)
+    return groups
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """AdamW over the arena's flat buffers — one fused kernel (x2k_adamw_flat) for every parameter.
+
+    A real `torch.optim.Optimizer`: `param_groups` hold per-group lr / weight_decay / betas / eps (so LambdaLR and the
+    reference's `reinit_scheduler_properties_mysched`, Pretrain.py:33-51, drive it like any optimizer), `state_dict` /
+    `load_state_dict` carry the flat moments and the step count (checkpoint `training_states`, Pretrain.py:603).
+    Built either from the reference's name-based rules (optim.py:26-104) or from the param_groups of an existing torch
+    AdamW (`from_optimizer`): the groups, their order and their hyper-parameters are taken over one to one."""
 
     def __init__(self, model, arena, lr=1e-4, weight_decay=0.01, lr_mult=1.0, vision_lr=None, text_lr=None, cross_lr=None,
-                 betas=(0.9, 0.98), eps=1e-8):
+                 betas=(0.9, 0.98), eps=1e-8, param_groups=None):
         self.arena = arena
-        self.betas, self.eps = betas, eps
-        names = {id(p): n for n, p in model.named_parameters()}
-        init_params = set(getattr(model, "init_params", []) or [])
-        if cross_lr is None:
-            cross_lr = text_lr
-        self.param_groups = []
-        group_of = {}
-
-        def group(lr_, wd_):
-            key = (lr_, wd_)
-            if key not in group_of:
-                group_of[key] = len(self.param_groups)
-                self.param_groups.append({"params": [], "lr": lr_, "weight_decay": wd_, "initial_lr": lr_})
-            return self.param_groups[group_of[key]]
-
-        for p in arena.params:
-            n = names.get(id(p), "")
-            if not p.requires_grad:
-                continue
-            wd_ = 0.0 if any(nd in n for nd in NO_DECAY) else weight_decay
-            if vision_lr is not None and n.startswith("vision_encoder"):
-                lr_ = vision_lr
-            elif text_lr is not None and n.startswith("text_encoder"):
-                lr_ = text_lr
-            elif cross_lr is not None and n.startswith("cross_encoder"):
-                lr_ = cross_lr
-            elif n in init_params:
-                lr_ = lr * lr_mult
-            else:
-                lr_ = lr
-            group(lr_, wd_)["params"].append(p)
+        if param_groups is None:
+            param_groups = name_based_groups(model, arena.params, lr, weight_decay, lr_mult, vision_lr, text_lr, cross_lr)
+        known = {id(p) for p in arena.params}
+        for g in param_groups:
+            for p in g["params"]:
+                if id(p) not in known:
+                    raise ValueError("FlatAdamW: optimizer parameter is not part of the model's arena")
+        if not any(g["params"] for g in param_groups):
+            raise ValueError("FlatAdamW: no trainable parameters")
+        super().__init__(param_groups, dict(lr=lr, weight_decay=weight_decay, betas=tuple(betas), eps=eps))
+        b, e = self.param_groups[0]["betas"], self.param_groups[0]["eps"]
+        if any(tuple(g["betas"]) != tuple(b) or g["eps"] != e for g in self.param_groups):
+            raise NotImplementedError("FlatAdamW: betas / eps must be the same in every group (they are kernel constants)")
+        self.betas, self.eps = tuple(b), e
+        for g in self.param_groups:
+            g.setdefault("initial_lr", g["lr"])
         dev = arena.flat.device
-        # one segment per parameter (arena order == ascending offsets)
-        seg_end, self._seg_group = [], []
+        # one segment per parameter (arena order == ascending offsets); parameters outside every group are frozen
+        seg_end, seg_group = [], []
         gid = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
         for p in arena.params:
             seg_end.append(arena.span(p)[1])
-            self._seg_group.append(gid.get(id(p), -1))
+            seg_group.append(gid.get(id(p), -1))
         seg_end[-1] = arena.numel
+        n_groups = len(self.param_groups)
         self.seg_end = torch.tensor(seg_end, dtype=torch.int64, device=dev)
         self.seg_lr = torch.zeros(len(seg_end), dtype=torch.float32, device=dev)
         self.seg_wd = torch.zeros(len(seg_end), dtype=torch.float32, device=dev)
-        self._seg_group_t = torch.tensor([g if g >= 0 else len(self.param_groups) for g in self._seg_group], device=dev)
+        self._seg_group_t = torch.tensor([g if g >= 0 else n_groups for g in seg_group], device=dev)
         self.exp_avg = torch.zeros_like(arena.flat)
         self.exp_avg_sq = torch.zeros_like(arena.flat)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -85,9 +107,29 @@ class FlatAdamW:
         self._lr_host = None
         self._upload_hparams()
 
+    @classmethod
+    def from_optimizer(cls, model, arena, optimizer):
+        """Take over a torch AdamW (e.g. the reference's optim.create_optimizer result): same groups, lr, weight decay,
+        betas, eps.  Anything that is not a decoupled-weight-decay Adam is rejected loudly."""
+        if isinstance(optimizer, FlatAdamW):
+            return optimizer
+        if not isinstance(optimizer, torch.optim.AdamW):
+            raise TypeError("X2kDDPAccelerator needs a torch.optim.AdamW (the reference's optim.create_optimizer) or None, got %s"
+                            % type(optimizer).__name__)
+        if any(g.get("amsgrad", False) or g.get("maximize", False) for g in optimizer.param_groups):
+            raise NotImplementedError("FlatAdamW: amsgrad / maximize are not implemented")
+        if any(len(st) for st in optimizer.state.values()):
+            raise NotImplementedError("FlatAdamW.from_optimizer: the incoming optimizer already has state; load it with "
+                                      "FlatAdamW.load_state_dict instead")
+        groups = [{"params": list(g["params"]), "lr": g["lr"], "weight_decay": g["weight_decay"], "betas": tuple(g["betas"]),
+                   "eps": g["eps"], **({"initial_lr": g["initial_lr"]} if "initial_lr" in g else {})}
+                  for g in optimizer.param_groups]
+        d = optimizer.defaults
+        return cls(model, arena, lr=d["lr"], weight_decay=d["weight_decay"], betas=d["betas"], eps=d["eps"], param_groups=groups)
+
     def _upload_hparams(self):
-        lrs = [g["lr"] for g in self.param_groups] + [0.0]   # frozen parameters: lr 0, wd 0
-        wds = [g["weight_decay"] for g in self.param_groups] + [0.0]
+        lrs = [float(g["lr"]) for g in self.param_groups] + [0.0]   # frozen parameters: lr 0, wd 0
+        wds = [float(g["weight_decay"]) for g in self.param_groups] + [0.0]
         if self._lr_host == (lrs, wds):
             return
         self._lr_host = (list(lrs), list(wds))
@@ -96,9 +138,12 @@ class FlatAdamW:
         self.seg_wd.copy_(torch.tensor(wds, dtype=torch.float32, device=dev)[self._seg_group_t])
 
     def zero_grad(self, set_to_none=False):
-        self.arena.zero_grad()
+        self.arena.zero_grad()  # the gradients are views of one flat buffer: one fill, never set to None
 
-    def step(self):
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FlatAdamW.step: closures are not supported")
         self._upload_hparams()  # picks up LambdaLR-style mutations of param_groups[i]['lr']
         self.step_dev += 1
         a = self.arena
@@ -107,8 +152,43 @@ class FlatAdamW:
         self.grad_scale.fill_(1.0)
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_dev,
+        return {"flat": True, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": int(self.step_dev.item()),
+                "numel": self.arena.numel,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        """Resume from `state_dict()` (the checkpoint's `training_states`): flat moments, step count, group hyper-parameters."""
+        if not sd.get("flat") or sd["numel"] != self.arena.numel or len(sd["param_groups"]) != len(self.param_groups):
+            raise ValueError("FlatAdamW.load_state_dict: not a FlatAdamW state of this model (numel %s vs %d, %d vs %d groups)"
+                             % (sd.get("numel"), self.arena.numel, len(sd.get("param_groups", ())), len(self.param_groups)))
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_dev.fill_(int(sd["step"]))
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in saved.items() if k != "params"})
+        self._lr_host = None
+        self._upload_hparams()
+
+
+def rebind_scheduler(lr_scheduler, optimizer):
+    """The scheduler the caller built on its torch optimizer, re-created on `optimizer` (same lambdas, same progress).
+    Only LambdaLR — the one scheduler the reference creates (scheduler.py:4-33) — is supported."""
+    if lr_scheduler is None or getattr(lr_scheduler, "optimizer", None) is optimizer:
+        return lr_scheduler
+    from torch.optim.lr_scheduler import LambdaLR
+    if not isinstance(lr_scheduler, LambdaLR):
+        raise TypeError("X2kDDPAccelerator.set_up: only LambdaLR schedulers can be re-bound to the flat optimizer, got %s"
+                        % type(lr_scheduler).__name__)
+    lambdas = list(lr_scheduler.lr_lambdas)
+    if len(lambdas) != len(optimizer.param_groups):
+        raise ValueError("scheduler has %d lr_lambdas, optimizer %d groups" % (len(lambdas), len(optimizer.param_groups)))
+    done = lr_scheduler.last_epoch
+    for g in optimizer.param_groups:  # LambdaLR multiplies the groups' initial_lr
+        g["lr"] = g.get("initial_lr", g["lr"])
+    new = LambdaLR(optimizer, lambdas, last_epoch=-1)
+    for _ in range(max(0, done)):  # replay the progress already made (0 for a fresh run)
+        new.step()
+    return new
 
 
 class DDPModel(torch.nn.Module):
@@ -182,8 +262,8 @@ class GradBucketer:
         if self.is_cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
-                view.mul_(1.0 / self.world_size)
+                # NCCL averages inside the collective (apex gradient_average): no second pass over the bucket
+                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.pg)
         else:  # gloo (CPU tests of the bucket logic)
             dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
             view.mul_(1.0 / self.world_size)
@@ -325,9 +405,15 @@ class X2kDDPAccelerator:
         self.norm_sq = None
 
     def set_up(self, model, optimizer, lr_scheduler, local_rank, world_size, rank):
-        """Move the model to cuda:local_rank, join the NCCL group, flatten parameters, broadcast rank 0's weights and
-        arm the bucketed all-reduce.  `optimizer` may be None: a FlatAdamW over the arena is then created from
-        self.cfg (lr, weight_decay, ...)."""
+        """Same call as ApexDDPAccelerator.set_up (accelerators/apex_ddp_accelerator.py:42-72; Pretrain.py:578): move the
+        model to cuda:local_rank, join the NCCL group, flatten parameters, broadcast rank 0's weights, arm the bucketed
+        all-reduce — and return (wrapped model, optimizer, lr_scheduler).
+
+        The returned optimizer is always the flat fused AdamW: built from the incoming torch AdamW's param_groups (the
+        reference's optim.create_optimizer result: groups, lr, weight decay, betas, eps are taken over one to one), or
+        from self.cfg when `optimizer` is None; any other optimizer type is rejected.  The returned scheduler is the
+        incoming LambdaLR re-created on that optimizer, so `reinit_scheduler_properties_mysched(optimizer, scheduler, ...)`
+        and `scheduler.step()` keep working on what set_up returns."""
         torch.cuda.set_device(local_rank)
         model = model.cuda()
         if world_size > 1 and not dist.is_initialized():
@@ -344,7 +430,12 @@ class X2kDDPAccelerator:
             optimizer = FlatAdamW(model, self.arena, **{k: v for k, v in self.cfg.items()
                                                         if k in ("lr", "weight_decay", "lr_mult", "vision_lr", "text_lr",
                                                                  "cross_lr")})
+        else:
+            optimizer = FlatAdamW.from_optimizer(model, self.arena, optimizer)
+        lr_scheduler = rebind_scheduler(lr_scheduler, optimizer)
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=self.arena.flat.device)
+        # spans of frozen parameters: kept at zero gradient so they never enter the clip norm (torch.clip_grad_norm_ skips them)
+        self._frozen_spans = [self.arena.span(p) for p in self.arena.params if not p.requires_grad]
         return DDPModel(model), optimizer, lr_scheduler
 
     def broadcast(self, model, src=0):
@@ -365,6 +456,10 @@ class X2kDDPAccelerator:
     def optimizer_step(self, optimizer, model, grad_norm):
         """Global-norm clip (torch.nn.utils.clip_grad_norm_ semantics) folded into the optimizer's gradient scale.
         Returns the total norm as a 0-dim device tensor."""
+        if not isinstance(optimizer, FlatAdamW):
+            raise TypeError("optimizer_step needs the optimizer that set_up returned")
+        for s0, e0 in getattr(self, "_frozen_spans", ()):  # a packed group with one frozen member still receives a wgrad
+            self.arena.grad[s0:e0].zero_()
         self.norm_sq.zero_()
         ops.sumsq(self.arena.grad, self.norm_sq, self.arena.numel)
         total_norm = self.norm_sq.sqrt()

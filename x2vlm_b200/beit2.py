@@ -135,8 +135,11 @@ class Block(nn.Module):
             # the reference never passes these on the hot path (VisionTransformer.forward, beit2.py:401-407)
             raise NotImplementedError("x2k Block: return_attention/return_qkv/rel_pos_bias/image_atts/output_attentions "
                                       "are outside the fused hot path")
-        dp = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
-        return XF.beit_block(x, self, dp), None
+        dp1 = dp2 = None
+        if isinstance(self.drop_path, DropPath):  # two independent per-sample draws per block (beit2.py:204-207)
+            dp1 = self.drop_path.sample_scale(x.shape[0], x.device)
+            dp2 = self.drop_path.sample_scale(x.shape[0], x.device)
+        return XF.beit_block(x, self, dp1, dp2), None
 
 
 class PatchEmbed(nn.Module):

@@ -22,16 +22,33 @@ from ._capi import ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE
 # dropout bookkeeping: every dropout site gets a unique Philox (seed, offset) range
 # ----------------------------------------------------------------------------------------------
 class _DropoutState:
+    """Philox key + running offset of the in-kernel dropout masks.  Unless `manual_seed` pins it, the key is derived on
+    first use from torch's seed and the data-parallel rank — the reference flow `torch.manual_seed(args.seed + rank)`
+    (Pretrain.py:437-441) therefore gives every rank, and every --seed, its own masks."""
+
     def __init__(self):
-        self.seed = 0x5EED5EED
+        self.seed = None
         self.offset = 0
         self.lock = threading.Lock()
 
     def manual_seed(self, seed):
         self.seed, self.offset = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
 
+    def _default_seed(self):
+        import os
+        rank = int(os.environ.get("RANK", "0"))
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:
+            pass
+        return ((torch.initial_seed() * 0x9E3779B97F4A7C15) ^ ((rank + 1) * 0xD1B54A32D192ED03) ^ 0x5EED5EED) & 0xFFFFFFFFFFFFFFFF
+
     def take(self, n_elems):
         with self.lock:
+            if self.seed is None:
+                self.seed = self._default_seed()
             off = self.offset
             self.offset += (int(n_elems) + 3) // 4 + 1
         return self.seed, off
@@ -61,15 +78,16 @@ class _G:
 
     def __init__(self, param, dev):
         self.param = param
+        self.frozen = param is not None and not param.requires_grad
         g = getattr(param, "_x2k_grad", None) if param is not None else None
-        if g is not None:
+        if g is not None and not self.frozen:
             self.buf, self.direct = g.view(-1), True
-        else:
+        else:  # frozen parameters (fine-tuning with frozen layers): the kernels still need a target, nothing keeps it
             self.direct = False
             self.buf = torch.zeros(param.numel(), dtype=torch.float32, device=dev) if param is not None else None
 
     def ret(self):
-        if self.param is None:
+        if self.param is None or self.frozen:
             return None
         if self.direct:
             self.param._x2k_arena.note_grad_written(self.param, [self.param])
@@ -93,6 +111,8 @@ def _note_uses(*objs):
 def _wgrad(shadow, dy_bf16, x_bf16, n_out, n_in, rows):
     """dW[n_out, n_in] = dyᵀ · x over `rows`; into the arena's flat gradient (accumulating) or a new tensor.
     Returns the list of per-parameter grads to hand to autograd (None when the sink took them)."""
+    if not any(q.requires_grad for q in shadow.params):  # frozen weights: no wgrad GEMM, nothing enters the clip norm
+        return [None] * len(shadow.params)
     sink = shadow.grad_sink()
     if sink is not None:
         ops.gemm(dy_bf16, x_bf16, n_out, n_in, rows, a_mn=True, b_mn=True, out_f32=sink, accumulate=True)
@@ -221,7 +241,7 @@ class _BeitBlockFn(torch.autograd.Function):
     """x += dp·γ1·proj(attn(LN1(x)));  x += dp·γ2·fc2(GELU(fc1(LN2(x))))."""
 
     @staticmethod
-    def forward(ctx, x, dp_scale, blk, n1w, n1b, qkv_bias, table, projb, g1, n2w, n2b, fc1b, fc2b, g2, *weights):
+    def forward(ctx, x, dp_scale, dp_scale2, blk, n1w, n1b, qkv_bias, table, projb, g1, n2w, n2b, fc1b, fc2b, g2, *weights):
         B, N, D = x.shape
         H = blk.attn.num_heads
         M = B * N
@@ -256,18 +276,18 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.gemm(ln2, sh["fc1"].get(), M, Dh, D, bias=fc1b, preact_out=hpre, act=ACT_GELU_SAVE_GRAD, out_bf16=act)
         y2 = _empty_bf16(M, D, dev=dev)
         out = torch.empty(M, D, dtype=torch.float32, device=dev)
-        ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale,
+        ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale2,
                  rows_per_scale=N, residual=x1, out_f32=out)
         ctx.blk, ctx.dims, ctx.scale = blk, (B, N, D, H, Dh, ldb), scale
         ctx.P = (n1w, n1b, table, projb, g1, n2w, n2b, fc1b, fc2b, g2)
-        ctx.save_for_backward(x2, dp_scale, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1,
+        ctx.save_for_backward(x2, dp_scale, dp_scale2, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1,
                               mean2, rstd2, ln2, hpre, act, y2)
         return out.view(B, N, D)
 
     @staticmethod
     def backward(ctx, dout):
-        (x2, dp_scale, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1, mean2, rstd2, ln2, hpre,
-         act, y2) = ctx.saved_tensors
+        (x2, dp_scale, dp_scale2, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1, mean2, rstd2, ln2,
+         hpre, act, y2) = ctx.saved_tensors
         blk = ctx.blk
         sh = blk._x2k
         B, N, D, H, Dh, ldb = ctx.dims
@@ -277,7 +297,7 @@ class _BeitBlockFn(torch.autograd.Function):
         dx2 = dout.contiguous().view(M, D)
         # ---- MLP branch ----
         g2b = _empty_bf16(M, D, dev=dev)
-        ops.scale_cast_colsum(dx2, M, D, g_bf16=g2b, gamma=g2, row_scale=dp_scale, rows_per_scale=N,
+        ops.scale_cast_colsum(dx2, M, D, g_bf16=g2b, gamma=g2, row_scale=dp_scale2, rows_per_scale=N,
                               y_bf16=y2 if g2 is not None else None, dbias=P_fc2b.buf, dgamma=P_g2.buf)
         dh = _empty_bf16(M, Dh, dev=dev)
         ops.gemm(g2b, sh["fc2"].get_nograd(), M, Dh, D, b_mn=True, act=ACT_MUL_AUX, aux=hpre, out_bf16=dh)
@@ -312,13 +332,14 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.layernorm_bwd(dln1, x2, n1w, mean1, rstd1, dx, P_n1w.buf, P_n1b.buf, dx_residual=dx1)
         # weights were passed in the order qkv, proj, fc1, fc2
         nig = ctx.needs_input_grad
-        return (dx.view(B, N, D), None, None, P_n1w.ret(), P_n1b.ret(), d_qkvb if nig[5] else None, P_table.ret(),
+        return (dx.view(B, N, D), None, None, None, P_n1w.ret(), P_n1b.ret(), d_qkvb if nig[6] else None, P_table.ret(),
                 P_projb.ret(), P_g1.ret(), P_n2w.ret(), P_n2b.ret(), P_fc1b.ret(), P_fc2b.ret(), P_g2.ret(), *wg_qkv, *wg_proj,
                 *wg_fc1, *wg_fc2)
 
 
-def beit_block(x, blk, dp_scale=None):
-    """x: [B, N, D] fp32.  dp_scale: per-sample DropPath keep/(1-p) [B] fp32 or None."""
+def beit_block(x, blk, dp_scale=None, dp_scale2=None):
+    """x: [B, N, D] fp32.  dp_scale / dp_scale2: per-sample DropPath keep/(1-p) [B] fp32 (or None) of the attention and of
+    the MLP branch — two independent draws, as the reference calls self.drop_path twice per block (beit2.py:204-207)."""
     a = blk.attn
     # K has no bias (beit2.py:129)
     qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)) if a.q_bias is not None else None
@@ -326,7 +347,7 @@ def beit_block(x, blk, dp_scale=None):
     weights = (*sh["qkv"].params, *sh["proj"].params, *sh["fc1"].params, *sh["fc2"].params)
     _note_uses(sh["qkv"], sh["proj"], sh["fc1"], sh["fc2"], blk.norm1.weight, blk.norm1.bias, a.relative_position_bias_table,
                a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias, blk.mlp.fc2.bias, blk.gamma_2)
-    return _BeitBlockFn.apply(x, dp_scale, blk, blk.norm1.weight, blk.norm1.bias, qkv_bias, a.relative_position_bias_table,
+    return _BeitBlockFn.apply(x, dp_scale, dp_scale2, blk, blk.norm1.weight, blk.norm1.bias, qkv_bias, a.relative_position_bias_table,
                               a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias,
                               blk.mlp.fc2.bias, blk.gamma_2, *weights)
 

@@ -7,7 +7,7 @@ keyword arguments — so reference checkpoints load and the reference's callers 
 (In the build container the reference's own XVLMBase is also constructed on top of these encoders,
 tests/test_dropin_reference.py; the reference tree does not exist on the GPU box, hence this mirror.)
 
-Differences that are part of the B200-first design, none of which change results:
+Differences that are part of the B200-first design, none of which change the training semantics:
   * hard negatives are drawn on the device (`torch.multinomial` over all rows at once) instead of
     2·B host-synchronising `.item()` calls (models/xvlm.py:847-855; SURVEY.md §8f rank 1);
   * `forward_mixed` runs one image iteration + one region iteration (Pretrain.py:run_mixed_iter) with
@@ -325,9 +325,14 @@ class XVLM(nn.Module):
         Br = rb["text_ids"].shape[0] if has_r else 0
         n_img_r = rb["image"].shape[0] if has_r else 0
         # ---- vision: all images once ----
-        images = torch.cat([ib["image"], rb["image"]]) if has_r else ib["image"]
-        patches, x_cls, _ = self.vision_encoder.forward_features(images)
-        full = torch.cat([x_cls, patches], dim=1)  # [Bi + n_img_r, N, D]
+        if ib["image"].dim() == 5:  # video iteration (Pretrain.py:run_video_iter): frames -> per-frame encoding -> avgpool
+            assert not has_r, "video batches carry no region sub-batch"
+            full, _ = self.get_frame_embeds(ib["image"])
+            patches = x_cls = None
+        else:
+            images = torch.cat([ib["image"], rb["image"]]) if has_r else ib["image"]
+            patches, x_cls, _ = self.vision_encoder.forward_features(images)
+            full = torch.cat([x_cls, patches], dim=1)  # [Bi + n_img_r, N, D]
         emb_i = full[:Bi]
         N = full.shape[1]
         atts_i = torch.ones(Bi, N, dtype=torch.long, device=dev)
@@ -402,9 +407,13 @@ class XVLM(nn.Module):
         return losses
 
     @staticmethod
-    def total_loss(losses):
-        """Sum of the image- and region-iteration losses (Pretrain.py:204-232, iter_perc = 1)."""
-        tot = sum(losses["image"].values())
+    def total_loss(losses, image_w=1.0, region_w=1.0, regions_use_bbox_only=False):
+        """Pretrain.py:204-232: images.iter_perc * (itc + itm + mlm) + regions.iter_perc * (itc + itm + mlm + bbox + giou),
+        or only the two box losses of the region iteration with config['regions_use_bbox_only'].  iter_perc defaults to 1
+        (x2vlm_base_1b.yaml / x2vlm_large_1b.yaml set regions.iter_perc = 0.5)."""
+        tot = image_w * sum(losses["image"].values())
         if losses["region"]:
-            tot = tot + sum(losses["region"].values())
+            r = losses["region"]
+            keys = ("loss_bbox", "loss_giou") if regions_use_bbox_only else tuple(r.keys())
+            tot = tot + region_w * sum(r[k] for k in keys)
         return tot

@@ -87,17 +87,13 @@ def rerank(model, image_embeds, text_embeds, text_atts, sims_matrix, k_test, row
 
 
 def combine_rank_rows(scores):
-    """Every process scored the rows of its _rank_slice; put the full matrix on all of them.  (The reference SUM-
-    all-reduces matrices pre-filled with -100, Retrieval.py:145-148, which shifts every entry by -100·(W-1); here the
-    rows a rank did not own contribute 0, so entries keep their single-process values, -100 included.)"""
-    start, end, world = _rank_slice(scores.shape[0])
-    if world == 1:
-        return scores
-    own = torch.zeros(scores.shape[0], 1, dtype=torch.bool, device=scores.device)
-    own[start:end] = True
-    filled = torch.where(own, scores, torch.zeros_like(scores))
-    dist.all_reduce(filled, op=dist.ReduceOp.SUM)
-    scores.copy_(filled)
+    """Every process scored the rows of its _rank_slice into a matrix pre-filled with -100; the reference SUM-all-reduces
+    those matrices as they are (Retrieval.py:145-148), so with W processes every entry carries an extra -100·(W-1)
+    (a constant shift per matrix: rankings are unchanged).  Same call here — the score matrices are the reference's,
+    entry for entry, at any world size."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world > 1:
+        dist.all_reduce(scores, op=dist.ReduceOp.SUM)
     return scores
 
 

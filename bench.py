@@ -632,6 +632,8 @@ def run_retrieval(args):
         try:
             from oracle import ref_shim
             ref = ref_shim.build_reference_model().to(dev).eval()
+            # the loop writes ITM scores into an fp32 matrix (Retrieval.py:133): hand it fp32 scores under autocast
+            ref.itm_head.register_forward_hook(lambda mod, inp, out: out.float())
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -234,6 +234,15 @@ int x2k_attn_bwd(const X2kAttnArgs* args, void* stream);
 /* Bytes of X2kAttnArgs.dq_ws that x2k_attn_bwd needs for these shapes (B, H, Lq, Lk of *args; 0 = none). */
 int64_t x2k_attn_bwd_workspace_bytes(const X2kAttnArgs* args);
 
+/* Attention maps on request (the fused kernels never materialise them):
+ *   mode 0: out[b,h,i,j] = softmax_j(scale·q_i·k_j + bias + mask)  — the PRE-dropout probabilities the reference returns as
+ *           `attn_prob` / `attention_probs` with output_attentions (models/beit2.py:152,166; models/xbert.py:392,410) and
+ *           stores with save_attention (models/xbert.py:394-396); needs q, k, lse (from x2k_attn_fwd), bias / mask;
+ *   mode 1: out[b,h,i,j] = (dO_i·v_j) * keepscale(b,h,i,j) — dL/d(attention_probs), what the reference's
+ *           register_hook(save_attn_gradients) receives; needs d_o, v and the forward's dropout parameters.
+ * out: fp32 [B, H, Lq, Lk] contiguous.  HBM-bound on the output. */
+int x2k_attn_probs(const X2kAttnArgs* args, int32_t mode, float* out, void* stream);
+
 /* Short query sequences (Lq rounded up to 8 <= 64, no bias): several sequences share one 128-row MMA
  * tile.  Self-attention (kv_index == NULL, Lq == Lk-sized segments) is packed automatically inside
  * x2k_attn_fwd/bwd.  Cross-attention over shared K/V needs the sequences grouped by K/V source:

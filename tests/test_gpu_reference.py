@@ -302,3 +302,74 @@ def test_retrieval_k128_vs_reference_evaluation_loop(models):
     r_mine = retrieval.itm_eval(s_i2t, s_t2i, txt2img, img2txt)
     r_ref = retrieval.itm_eval(w_i2t, w_t2i, txt2img, img2txt)
     assert abs(r_mine["r_mean"] - r_ref["r_mean"]) <= 1.0, (r_mine, r_ref)
+
+
+def test_attention_maps_on_request(models):
+    """output_attentions (knowledge distillation: models/beit2.py:418-421, models/xbert.py:392-410) and save_attention
+    (Grad-CAM hooks, models/xbert.py:248-260,394-396): the fused kernels never hold [B,H,L,L]; the maps are rebuilt by
+    x2k_attn_probs and must equal the reference's, as must the hooked gradient of a cross-attention map."""
+    ref, ours = models
+    ib = _dev(synth.image_text_batch(3, 30, seed=31))
+    atts = ib["text_atts"].clone(); atts[1, 21:] = 0
+    with torch.no_grad():
+        vr = ref.vision_encoder(ib["image"], output_attentions=True, output_hidden_states=True)
+        vo = ours.vision_encoder(ib["image"], output_attentions=True, output_hidden_states=True)
+    assert len(vo["attentions"]) == len(vr["attentions"]) == 12 and len(vo["hidden_states"]) == 13
+    for i in (0, 5, 11):
+        assert vo["attentions"][i].shape == (3, 12, 197, 197)
+        assert _rel(vo["attentions"][i], vr["attentions"][i]) < 2e-2, i
+        assert (vo["attentions"][i].sum(-1) - 1).abs().max() < 2e-3
+    assert _rel(vo["last_hidden_state"], vr["last_hidden_state"]) < 1e-2
+    with torch.no_grad():
+        kw = dict(attention_mask=atts, encoder_hidden_states=vr["last_hidden_state"], return_dict=True, output_attentions=True)
+        tr = ref.text_encoder.bert(ib["text_ids"], **kw)
+        to = ours.text_encoder.bert(ib["text_ids"], **kw)
+    assert len(to.attentions) == 18 and len(to.cross_attentions) == 6
+    for a, b in ((to.attentions[0], tr.attentions[0]), (to.attentions[17], tr.attentions[17]),
+                 (to.cross_attentions[0], tr.cross_attentions[0]), (to.cross_attentions[5], tr.cross_attentions[5])):
+        assert a.shape == b.shape and _rel(a, b) < 3e-2, (a.shape, _rel(a, b))
+    # Grad-CAM: map + gradient of the first fusion layer's cross-attention
+    enc = vr["last_hidden_state"].detach()
+    res = []
+    for m in (ref, ours):
+        att = m.text_encoder.bert.encoder.layer[12].crossattention.self
+        att.save_attention = True
+        try:
+            x = m.text_encoder.bert(ib["text_ids"], attention_mask=atts, encoder_hidden_states=enc, return_dict=True).last_hidden_state
+            m.itm_head(x[:, 0])[:, 1].sum().backward()
+            res.append((att.get_attention_map().detach().float(), att.get_attn_gradients().detach().float()))
+        finally:
+            att.save_attention = False
+            m.zero_grad(set_to_none=True)
+    (pm, pg), (om, og) = res
+    assert om.shape == pm.shape == (3, 12, 30, 197) and og.shape == pg.shape
+    assert _rel(om, pm) < 3e-2 and _rel(og, pg) < 6e-2, (_rel(om, pm), _rel(og, pg))
+
+
+def test_per_query_cross_attention_mask(models):
+    """A 3-D encoder_attention_mask [B, L, Nk] (every text position sees its own subset of image tokens) through the
+    fusion layers: the reference accepts it (xbert.py:1165-1170), so must the fused layer — forward and backward."""
+    ref, ours = models
+    ib = _dev(synth.image_text_batch(4, 24, seed=41))
+    g = torch.Generator().manual_seed(2)
+    m3 = (torch.rand(4, 24, 197, generator=g) > 0.4).long().cuda()
+    m3[:, :, 0] = 1
+    with torch.no_grad():
+        enc, _ = ref.get_vision_embeds(ib["image"])
+        te = ref.get_text_embeds(ib["text_ids"], ib["text_atts"])
+        kw = dict(encoder_embeds=te, attention_mask=ib["text_atts"], encoder_hidden_states=enc, encoder_attention_mask=m3,
+                  return_dict=True, mode="fusion")
+        want = ref.text_encoder.bert(**kw).last_hidden_state
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            auto = ref.text_encoder.bert(**kw).last_hidden_state.float()
+        got = ours.text_encoder.bert(**kw).last_hidden_state
+    assert _rel(got, want) <= RATIO * _rel(auto, want), (_rel(got, want), _rel(auto, want))
+    ours.train()
+    try:
+        out = ours.text_encoder.bert(**kw).last_hidden_state
+        out.square().mean().backward()
+        gk = ours.text_encoder.bert.encoder.layer[13].crossattention.self.key.weight.grad
+        assert gk is not None and torch.isfinite(gk).all() and float(gk.abs().sum()) > 0
+    finally:
+        ours.zero_grad(set_to_none=True)
+        ours.eval()

@@ -91,6 +91,7 @@ SYMBOLS = {
     "x2k_cast_f32_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "x2k_attn_fwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
     "x2k_attn_bwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
+    "x2k_attn_probs": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_int32, c_void_p, c_void_p]),
     "x2k_attn_bwd_workspace_bytes": (c_int64, [ctypes.POINTER(X2kAttnArgs)]),
     "x2k_attn_group_slots": (c_int32, [c_int32]),
     "x2k_attn_group_table_ints": (c_int64, [c_int32, c_int32, c_int32]),

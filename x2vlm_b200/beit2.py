@@ -131,15 +131,17 @@ class Block(nn.Module):
 
     def forward(self, x, rel_pos_bias=None, return_attention=False, return_qkv=False, image_atts=None,
                 output_attentions=None):
-        if return_attention or return_qkv or rel_pos_bias is not None or image_atts is not None or output_attentions:
+        if return_attention or return_qkv or rel_pos_bias is not None or image_atts is not None:
             # the reference never passes these on the hot path (VisionTransformer.forward, beit2.py:401-407)
-            raise NotImplementedError("x2k Block: return_attention/return_qkv/rel_pos_bias/image_atts/output_attentions "
+            raise NotImplementedError("x2k Block: return_attention / return_qkv / rel_pos_bias / image_atts "
                                       "are outside the fused hot path")
+        # attention maps are rebuilt on request only (knowledge distillation): the fused block never materialises them
+        attn_prob = XF.beit_attention_map(x, self) if output_attentions else None
         dp1 = dp2 = None
         if isinstance(self.drop_path, DropPath):  # two independent per-sample draws per block (beit2.py:204-207)
             dp1 = self.drop_path.sample_scale(x.shape[0], x.device)
             dp2 = self.drop_path.sample_scale(x.shape[0], x.device)
-        return XF.beit_block(x, self, dp1, dp2), None
+        return XF.beit_block(x, self, dp1, dp2), attn_prob
 
 
 class PatchEmbed(nn.Module):
@@ -228,9 +230,9 @@ class VisionTransformer(nn.Module):
     def no_weight_decay(self):
         return {'pos_embed', 'cls_token'}
 
-    def forward_features(self, x, all_states=None):
+    def forward_features(self, x, all_states=None, all_attentions=None):
         """patch embed -> cls cat -> blocks -> drop cls -> fc_norm.  Returns (patch tokens [B,P,D], their mean
-        [B,1,D], hidden states tuple or None)."""
+        [B,1,D], hidden states tuple or None); with all_attentions (a list) the per-block attention maps are appended."""
         x = self.patch_embed(x)
         batch_size = x.shape[0]
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), x), dim=1)
@@ -241,7 +243,9 @@ class VisionTransformer(nn.Module):
         for blk in self.blocks:
             if all_states is not None:
                 all_states = all_states + (x,)
-            x, _ = blk(x)
+            x, attn = blk(x, output_attentions=all_attentions is not None)
+            if all_attentions is not None:
+                all_attentions.append(attn)
         x = x[:, 1:]  # the cls output is dropped (beit2.py:409)
         x = XF.layer_norm(x, self.fc_norm.weight, self.fc_norm.bias, self.fc_norm.eps)
         return x, x.mean(dim=1, keepdim=True), all_states
@@ -256,14 +260,14 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x, idx_to_group_img=None, image_atts=None, output_attentions=None, output_hidden_states=None):
         assert output_attentions == output_hidden_states
-        if output_attentions:
-            raise NotImplementedError("attention probabilities are never materialised by the fused kernels")
-        x, x_cls, all_states = self.forward_features(x, () if output_hidden_states else None)
+        attns = [] if output_attentions else None
+        x, x_cls, all_states = self.forward_features(x, () if output_hidden_states else None, attns)
         if idx_to_group_img is None:
             x = torch.cat([x_cls, x], dim=1)
             if output_hidden_states:
                 all_states = all_states + (x,)
-                return {'last_hidden_state': x, 'hidden_states': all_states, 'attentions': ()}
+                assert len(all_states) == len(attns) + 1
+                return {'last_hidden_state': x, 'hidden_states': all_states, 'attentions': tuple(attns)}
             return x
         if output_hidden_states:
             raise NotImplementedError("not implemented KD for BBox Loss")

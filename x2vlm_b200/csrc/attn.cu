@@ -480,6 +480,82 @@ __global__ void relpos_scatter_kernel(const __nv_bfloat16* __restrict__ ds, int 
   atomicAdd(dtable + __ldg(index + static_cast<int64_t>(i) * N + j) * H + h, s);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Attention maps for the callers that ask for them (output_attentions: knowledge distillation; save_attention: Grad-CAM).
+// The fused kernels never materialise [B,H,Lq,Lk]; this streaming kernel rebuilds it from Q, K and the forward's
+// log-sum-exp:  mode 0: P = softmax(scale·QKᵀ + bias + mask) (pre-dropout, what the reference returns, models/beit2.py:152,
+// models/xbert.py:392-410);  mode 1: dL/dP = (dO·Vᵀ) ∘ dropout keep-scale (the gradient models/xbert.py:394-396 hooks).
+// Block = 32 query rows x 64 keys of one (b, h); thread = one row x 8 keys; HBM-bound on the fp32 output.
+// ---------------------------------------------------------------------------------------------
+constexpr int PB_ROWS = 32, PB_KEYS = 64, PB_LD = 66;  // smem rows padded to 33 words: 2-way conflicts at worst
+
+__global__ void __launch_bounds__(256)
+attn_probs_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld_a, const __nv_bfloat16* __restrict__ bm, int64_t ld_b,
+                  const AttnParams p, int mode, float* __restrict__ out) {
+  __shared__ __nv_bfloat16 sA[PB_ROWS * PB_LD];
+  __shared__ __nv_bfloat16 sB[PB_KEYS * PB_LD];
+  const int bh = blockIdx.z, b = bh / p.H, h = bh - b * p.H;
+  const int q0 = blockIdx.y * PB_ROWS, k0 = blockIdx.x * PB_KEYS;
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+  for (int i = threadIdx.x; i < PB_ROWS * 32; i += 256) {  // 32 rows x 32 bf16-pairs
+    const int r = i >> 5, c = (i & 31) * 2;
+    uint32_t v = 0u;
+    if (q0 + r < p.Lq) v = *reinterpret_cast<const uint32_t*>(a + (static_cast<int64_t>(b) * p.Lq + q0 + r) * ld_a + h * 64 + c);
+    *reinterpret_cast<uint32_t*>(sA + r * PB_LD + c) = v;
+  }
+  for (int i = threadIdx.x; i < PB_KEYS * 32; i += 256) {
+    const int r = i >> 5, c = (i & 31) * 2;
+    uint32_t v = 0u;
+    if (k0 + r < p.Lk) v = *reinterpret_cast<const uint32_t*>(bm + (static_cast<int64_t>(kvb) * p.Lk + k0 + r) * ld_b + h * 64 + c);
+    *reinterpret_cast<uint32_t*>(sB + r * PB_LD + c) = v;
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 8;
+  const int q = q0 + r;
+  if (q >= p.Lq) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int d = 0; d < 64; d += 2) {
+    const uint32_t av = *reinterpret_cast<const uint32_t*>(sA + r * PB_LD + d);
+    const float a0 = bf16_lo(av), a1 = bf16_hi(av);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t bv = *reinterpret_cast<const uint32_t*>(sB + (c0 + j) * PB_LD + d);
+      acc[j] = fmaf(a0, bf16_lo(bv), fmaf(a1, bf16_hi(bv), acc[j]));
+    }
+  }
+  float* dst = out + ((static_cast<int64_t>(bh) * p.Lq + q) * p.Lk);
+  if (mode == 0) {
+    const float lse = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q];
+    const float* bias_row = p.bias ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(q) * p.bias_q_stride : nullptr;
+    const float* mask_row = p.mask ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + c0 + j;
+      if (k < p.Lk) {
+        float add = 0.f;
+        if (bias_row) add += __ldg(bias_row + k);
+        if (mask_row) add += __ldg(mask_row + k);
+        dst[k] = fast_exp2(fmaf(acc[j], p.scale_log2, add * kLog2e) - lse);
+      }
+    }
+  } else {
+    float keep[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (p.dropout_p > 0.f) {
+      const DropCfg dc = make_drop(p.dropout_p);
+      const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
+      const uint64_t base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad + k0 + c0;  // multiple of 8
+      drop8(p.seed, doff, base >> 3, dc, keep);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + c0 + j;
+      if (k < p.Lk) dst[k] = acc[j] * keep[j];
+    }
+  }
+}
+
 }  // namespace
 }  // namespace x2k
 
@@ -601,6 +677,33 @@ extern "C" int64_t x2k_attn_bwd_workspace_bytes(const X2kAttnArgs* args) {
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0 || a.Lk <= 0) return 0;
   // the packed short-sequence kernels (Lq <= 64 and Lk <= 256) and the whole-range kernels (both <= 256) need none
   return (a.Lq > 256 || a.Lk > 256) ? attn_long_bwd_ws_bytes(a) : 0;
+}
+
+extern "C" int x2k_attn_probs(const X2kAttnArgs* args, int32_t mode, float* out, void* stream_) {
+  X2K_REQUIRE(args != nullptr && out != nullptr, "x2k_attn_probs: NULL argument");
+  const X2kAttnArgs& a = *args;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(mode == 0 || mode == 1, "x2k_attn_probs: mode must be 0 (probabilities) or 1 (their gradient)");
+  X2K_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "x2k_attn_probs: bad shape");
+  X2K_REQUIRE(static_cast<int64_t>(a.B) * a.H <= 65535, "x2k_attn_probs: B*H > 65535");
+  AttnParams p;
+  fill_params(a, p);
+  const void *pa, *pb;
+  int64_t lda, ldb;
+  if (mode == 0) {
+    X2K_REQUIRE(a.q && a.k && a.lse, "x2k_attn_probs: mode 0 needs q, k and the forward's lse");
+    pa = a.q; lda = a.ld_q; pb = a.k; ldb = a.ld_k;
+  } else {
+    X2K_REQUIRE(a.d_o && a.v, "x2k_attn_probs: mode 1 needs d_o and v");
+    pa = a.d_o; lda = a.ld_do; pb = a.v; ldb = a.ld_v;
+  }
+  X2K_REQUIRE(lda % 2 == 0 && ldb % 2 == 0, "x2k_attn_probs: leading dimensions must be even");
+  dim3 grid((a.Lk + PB_KEYS - 1) / PB_KEYS, (a.Lq + PB_ROWS - 1) / PB_ROWS, a.B * a.H);
+  attn_probs_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(pa), lda, static_cast<const __nv_bfloat16*>(pb), ldb,
+                                              p, mode, out);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
 }
 
 extern "C" int x2k_relpos_bias_gather(const float* table, const int64_t* index, int32_t N, int32_t H, float* out,

@@ -74,7 +74,7 @@ class _G:
     """Gradient slot of a small parameter (bias / LayerNorm / LayerScale / rel-pos table) inside a fused backward:
     the arena's flat-gradient view — the kernel accumulates in place and autograd receives None — or, without an
     arena, a fresh zero buffer that is returned to autograd."""
-    __slots__ = ("param", "buf", "direct")
+    __slots__ = ("param", "buf", "direct", "frozen")
 
     def __init__(self, param, dev):
         self.param = param
@@ -436,7 +436,13 @@ class _BertLayerFn(torch.autograd.Function):
             lse2 = torch.empty(Bt, H, L, dtype=torch.float32, device=dev)
             d_a2 = _drop(p_a, train, Bt * H * L * ops.pad16(Nk))
             ops.attn_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, ctx2, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
-                         kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"], dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
+                         kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"], mask_per_query=cfg.get("cross_mask_3d", False),
+                         dropout_p=d_a2[0], dropout_seed=d_a2[1], dropout_offset=d_a2[2])
+            if getattr(layer.crossattention.self, "save_attention", False):
+                # Grad-CAM hooks of models/xbert.py:394-396: the (pre-dropout) map now, its gradient in backward
+                layer.crossattention.self.save_attention_map(
+                    ops.attn_probs(qc, kvc[:, :D], Bt, H, L, Nk, scale, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
+                                   mask=cfg["cross_mask"], mask_per_query=cfg.get("cross_mask_3d", False)))
             s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
             d_h2 = _drop(p_h, train, M * D)
             dp2 = _pos_drop_path(layer.crossattention.output, cfg, "cross", Bt, L, dev)
@@ -525,7 +531,12 @@ class _BertLayerFn(torch.autograd.Function):
             kvc = sv["kvc"]
             ops.attn_bwd(sv["qc"], kvc[:, :D], kvc[:, D:], Bt, H, L, Nk, scale, sv["ctx2"], sv["lse2"], dctx2, dqc,
                          dkv_seq[:, :D], dkv_seq[:, D:], kv_index=cfg["kv_index"], n_kv=n_kv, kv_groups=cfg.get("kv_groups"),
-                         mask=cfg["cross_mask"], dropout_p=p, dropout_seed=seed, dropout_offset=off)
+                         mask=cfg["cross_mask"], mask_per_query=cfg.get("cross_mask_3d", False), dropout_p=p, dropout_seed=seed,
+                         dropout_offset=off)
+            if getattr(layer.crossattention.self, "save_attention", False):
+                layer.crossattention.self.save_attn_gradients(
+                    ops.attn_probs_grad(dctx2, kvc[:, D:], Bt, H, L, Nk, kv_index=cfg["kv_index"], n_kv=n_kv, dropout_p=p,
+                                        dropout_seed=seed, dropout_offset=off))
             if cfg["kv_index"] is not None and not grouped:
                 dkv = _empty_bf16(n_kv * Nk, 2 * D, dev=dev)
                 ops.segment_sum_bf16(dkv_seq.view(Bt, Nk * 2 * D), cfg["kv_index"], n_kv, dkv.view(n_kv, Nk * 2 * D))
@@ -627,14 +638,16 @@ def _kv_heads(rows, B, H):
 
 
 @torch.no_grad()
-def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=None):
+def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=None, return_probs=False):
     """One BertLayer forward for the generation paths of models/xbert.py:322-415 (no autograd graph):
 
     * `history` [B, Lh, D] — the layer's cached INPUT states (model_generation.py:180-188): keys/values are projected
       from cat(history, x) while queries come from x only (xbert.py:349-353);
     * `past_kv` (K, V) each [B, H, Lp, 64] — HF-style cache: new keys/values are appended (xbert.py:355-359).
 
-    cfg['self_mask'] covers all Lk = Lh|Lp + Lq keys.  Returns (y fp32 [B,Lq,D], (K, V) in the cache layout)."""
+    cfg['self_mask'] covers all Lk = Lh|Lp + Lq keys.  Returns (y fp32 [B,Lq,D], (K, V) in the cache layout); with
+    return_probs also (self-attention map, cross-attention map or None), fp32 [B,H,Lq,Lk], pre-dropout — the tensors the
+    reference returns under output_attentions (xbert.py:392,410)."""
     if history is not None and past_kv is not None:
         raise ValueError("history_states and past_key_value are mutually exclusive (xbert.py:350)")
     B, Lq, D = x.shape
@@ -677,6 +690,10 @@ def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=
     lse1 = torch.empty(B, H, Lq, dtype=torch.float32, device=dev)
     ops.attn_fwd(q, k_rows, v_rows, B, H, Lq, Lk, scale, ctx1, lse1, n_kv=B, mask=cfg["self_mask"],
                  mask_per_query=cfg["self_mask_3d"])
+    p_self = p_cross = None
+    if return_probs:
+        p_self = ops.attn_probs(q, k_rows, B, H, Lq, Lk, scale, lse1, n_kv=B, mask=cfg["self_mask"],
+                                mask_per_query=cfg["self_mask_3d"])
     s1 = torch.empty(M, D, dtype=torch.float32, device=dev)
     ops.gemm(ctx1, sh["o"].get(), M, D, D, bias=so.dense.bias, residual=x2, out_f32=s1)
     x1 = torch.empty(M, D, dtype=torch.float32, device=dev)
@@ -694,7 +711,10 @@ def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=
         ctx2 = _empty_bf16(M, D, dev=dev)
         lse2 = torch.empty(B, H, Lq, dtype=torch.float32, device=dev)
         ops.attn_fwd(qc, kvc[:, :D], kvc[:, D:], B, H, Lq, Nk, scale, ctx2, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
-                     kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"])
+                     kv_groups=cfg.get("kv_groups"), mask=cfg["cross_mask"], mask_per_query=cfg.get("cross_mask_3d", False))
+        if return_probs:
+            p_cross = ops.attn_probs(qc, kvc[:, :D], B, H, Lq, Nk, scale, lse2, kv_index=cfg["kv_index"], n_kv=n_kv,
+                                     mask=cfg["cross_mask"], mask_per_query=cfg.get("cross_mask_3d", False))
         s2 = torch.empty(M, D, dtype=torch.float32, device=dev)
         ops.gemm(ctx2, sh["oc"].get(), M, D, D, bias=co.dense.bias, residual=x1, out_f32=s2)
         xa = torch.empty(M, D, dtype=torch.float32, device=dev)
@@ -709,4 +729,29 @@ def bert_layer_decode(x, layer, cfg, enc=None, encb=None, history=None, past_kv=
     ops.gemm(act, sh["out"].get(), M, D, Di, bias=layer.output.dense.bias, residual=xa, out_f32=s3)
     y = torch.empty(M, D, dtype=torch.float32, device=dev)
     ops.layernorm_fwd(s3, layer.output.LayerNorm.weight, layer.output.LayerNorm.bias, eps, y_f32=y)
+    if return_probs:
+        return y.view(B, Lq, D), present, (p_self, p_cross)
     return y.view(B, Lq, D), present
+
+
+@torch.no_grad()
+def beit_attention_map(x, blk):
+    """Pre-dropout attention probabilities [B,H,N,N] of one BEiT block for input x (the `attn_prob` the reference's
+    Attention.forward returns, models/beit2.py:152,166): LN1 -> QKV -> lse by the fused forward -> streaming map kernel."""
+    B, N, D = x.shape
+    M, dev = B * N, x.device
+    a = blk.attn
+    H = a.num_heads
+    ln1 = _empty_bf16(M, D, dev=dev)
+    ops.layernorm_fwd(x.contiguous().view(M, D).float(), blk.norm1.weight, blk.norm1.bias, 1e-6, y_bf16=ln1)
+    qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)) if a.q_bias is not None else None
+    qkv = _empty_bf16(M, 3 * D, dev=dev)
+    ops.gemm(ln1, blk._x2k["qkv"].get_nograd(), M, 3 * D, D, bias=qkv_bias, out_bf16=qkv)
+    bias_g = None
+    if a.relative_position_bias_table is not None:
+        bias_g = torch.empty(H, N, ops.pad32(N), dtype=torch.float32, device=dev)
+        ops.relpos_bias_gather(a.relative_position_bias_table, a.relative_position_index, N, H, bias_g)
+    o = _empty_bf16(M, D, dev=dev)
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=dev)
+    ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, a.scale, o, lse, bias=bias_g)
+    return ops.attn_probs(qkv[:, :D], qkv[:, D:2 * D], B, H, N, N, a.scale, lse, bias=bias_g)

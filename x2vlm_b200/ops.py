@@ -288,6 +288,24 @@ def attn_bwd(q, k, v, B, H, Lq, Lk, scale, o, lse, d_o, dq, dk, dv, ds_out=None,
            lambda: C.check(C.lib().x2k_attn_bwd(ctypes.byref(a), _stream()), "x2k_attn_bwd"), "B%d Lq%d Lk%d" % (B, Lq, Lk))
 
 
+def attn_probs(q, k, B, H, Lq, Lk, scale, lse, **kw):
+    """fp32 [B, H, Lq, Lk]: the pre-dropout attention probabilities rebuilt from Q, K and the forward's lse."""
+    o_dummy = q  # not read in this mode
+    a = _attn_args(q, k, k, B, H, Lq, Lk, scale, o_dummy, lse, **kw)
+    out = torch.empty(B, H, Lq, Lk, dtype=torch.float32, device=q.device)
+    C.check(C.lib().x2k_attn_probs(ctypes.byref(a), 0, _p(out), _stream()), "x2k_attn_probs")
+    return out
+
+
+def attn_probs_grad(d_o, v, B, H, Lq, Lk, **kw):
+    """fp32 [B, H, Lq, Lk]: dL/d(attention probabilities) = (dO · Vᵀ) * dropout keep-scale."""
+    a = _attn_args(d_o, v, v, B, H, Lq, Lk, 1.0, d_o, torch.empty(0, device=d_o.device), **kw)
+    a.d_o, a.ld_do = d_o.data_ptr(), d_o.stride(0)
+    out = torch.empty(B, H, Lq, Lk, dtype=torch.float32, device=d_o.device)
+    C.check(C.lib().x2k_attn_probs(ctypes.byref(a), 1, _p(out), _stream()), "x2k_attn_probs")
+    return out
+
+
 def relpos_bias_gather(table, index, N, H, out):
     _req(table, torch.float32, "table"); _req(index, torch.int64, "index"); _req(out, torch.float32, "out")
     C.check(C.lib().x2k_relpos_bias_gather(_p(table), _p(index), N, H, _p(out), out.stride(1), _stream()),

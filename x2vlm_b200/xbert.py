@@ -17,7 +17,9 @@ Generation paths (`history_states` of the captioning beam search, model_generati
 `past_key_values` / `use_cache` of `BertLMHeadModel`, xbert.py:355-359) run forward-only on the same
 kernels (x2vlm_b200.functional.bert_layer_decode) and refuse to record an autograd graph.
 
-Not built (raise NotImplementedError): head pruning / head_mask, output_attentions, split_lengths.
+`output_attentions` / `save_attention` are served on request: a streaming kernel (x2k_attn_probs) rebuilds the
+pre-dropout maps (and, for save_attention, their gradients) from Q, K and the fused forward's log-sum-exp.
+Not built (raise NotImplementedError): head pruning / head_mask, split_lengths.
 xbert's per-position DropPath (text_drop_path_rate / cross_drop_path_rate, refcoco_grounding_large.yaml) is folded into
 the dense GEMM epilogues as a per-row scale.
 """
@@ -89,6 +91,20 @@ class BertSelfAttention(nn.Module):
         if self.position_embedding_type != "absolute":
             raise NotImplementedError("relative position embeddings (the reference raises too, xbert.py:381-382)")
         self.save_attention = False
+
+    # Grad-CAM hooks (models/xbert.py:248-260): with save_attention = True on a cross-attention module the fused layer
+    # stores the pre-dropout map [B, H, L, Nk] after forward and its gradient after backward
+    def save_attn_gradients(self, attn_gradients):
+        self.attn_gradients = attn_gradients
+
+    def get_attn_gradients(self):
+        return self.attn_gradients
+
+    def save_attention_map(self, attention_map):
+        self.attention_map = attention_map
+
+    def get_attention_map(self):
+        return self.attention_map
 
 
 class DropPath(nn.Module):
@@ -181,8 +197,8 @@ class BertLayer(nn.Module):
                 encoder_attention_mask=None, past_key_value=None, output_attentions=False, split_lengths=None,
                 history_states=None):
         """Reference-shaped entry point: extended additive masks in, tuple out (layer output, present key/value)."""
-        if head_mask is not None or output_attentions or split_lengths:
-            raise NotImplementedError("x2k BertLayer: head_mask / output_attentions / split_lengths")
+        if head_mask is not None or split_lengths:
+            raise NotImplementedError("x2k BertLayer: head_mask / split_lengths")
         B, L = hidden_states.shape[:2]
         decode = past_key_value is not None or history_states is not None
         n_past = (past_key_value[0].shape[2] if past_key_value is not None else 0) + \
@@ -195,10 +211,13 @@ class BertLayer(nn.Module):
             _group_cross(cfg, B, L, encoder_hidden_states.shape[1], hidden_states.device)
         if decode:
             _no_grad_only("past_key_value / history_states")
-            y, present = XF.bert_layer_decode(hidden_states, self, cfg, encoder_hidden_states,
-                                              history=history_states, past_kv=past_key_value[:2] if past_key_value else None)
-            return (y, present)
+            out = XF.bert_layer_decode(hidden_states, self, cfg, encoder_hidden_states, history=history_states,
+                                       past_kv=past_key_value[:2] if past_key_value else None, return_probs=bool(output_attentions))
+            return (out[0], *[p for p in out[2] if p is not None], out[1]) if output_attentions else (out[0], out[1])
         y, _ = self.fused(hidden_states, None, cfg, encoder_hidden_states)
+        if output_attentions:  # (layer output, self map, [cross map], present) like models/xbert.py:576-625
+            maps = XF.bert_layer_decode(hidden_states.detach(), self, dict(cfg, train=False), encoder_hidden_states, return_probs=True)[2]
+            return (y, *[p for p in maps if p is not None], None)
         return (y, None)
 
 
@@ -228,9 +247,8 @@ def _pad_mask(ext_mask, B, Lq, Lk, device):
 def _layer_cfg(config, training, ext_self_mask, ext_cross_mask, kv_index, B, L, Nk, device, Lk_self=None):
     self_mask, self_3d = _pad_mask(ext_self_mask, B, L, Lk_self if Lk_self is not None else L, device)
     cross_mask, cross_3d = _pad_mask(ext_cross_mask, B, L, Nk, device) if Nk else (None, False)
-    if cross_3d:
-        raise NotImplementedError("per-query cross-attention masks")
-    return dict(self_mask=self_mask, self_mask_3d=self_3d, cross_mask=cross_mask, kv_index=kv_index, n_kv=0, kv_groups=None,
+    return dict(self_mask=self_mask, self_mask_3d=self_3d, cross_mask=cross_mask, cross_mask_3d=cross_3d, kv_index=kv_index,
+                n_kv=0, kv_groups=None,
                 train=bool(training), p_hidden=float(config.hidden_dropout_prob),
                 p_attn=float(config.attention_probs_dropout_prob), eps=float(config.layer_norm_eps))
 
@@ -262,8 +280,8 @@ class BertEncoder(nn.Module):
                 encoder_attention_mask=None, past_key_values=None, use_cache=None, output_attentions=False,
                 output_hidden_states=False, return_dict=True, mode='multi_modal', split_lengths=None, history_states=None,
                 encoder_kv_index=None):
-        if output_attentions or split_lengths:
-            raise NotImplementedError("x2k BertEncoder: output_attentions / split_lengths")
+        if split_lengths:
+            raise NotImplementedError("x2k BertEncoder: split_lengths")
         if head_mask is not None and any(h is not None for h in head_mask):
             raise NotImplementedError("x2k BertEncoder: head_mask")
         if mode == 'text':
@@ -298,6 +316,9 @@ class BertEncoder(nn.Module):
             if output_layer > self.config.fusion_layer:
                 encb = ops.to_bf16(enc)  # one bf16 copy feeds the K/V projection of every fusion layer
         all_hidden_states = () if output_hidden_states else None
+        # attention maps are rebuilt on request by a forward-only pass of the layer (the fused layer never holds them)
+        all_self_attentions = () if output_attentions else None
+        all_cross_attentions = () if (output_attentions and enc is not None) else None
         next_decoder_cache = () if use_cache else None
         x, xb = hidden_states.float().contiguous(), None
         if decode:
@@ -306,21 +327,30 @@ class BertEncoder(nn.Module):
             if output_hidden_states:
                 all_hidden_states = all_hidden_states + (x,)
             if decode:
-                x, present = XF.bert_layer_decode(
+                out = XF.bert_layer_decode(
                     x, self.layer[i], cfg, enc, encb,
                     history=history_states[i - start_layer] if history_states is not None else None,
-                    past_kv=past_key_values[i][:2] if past_key_values is not None else None)
+                    past_kv=past_key_values[i][:2] if past_key_values is not None else None, return_probs=bool(output_attentions))
+                x, present = out[0], out[1]
+                maps = out[2] if output_attentions else None
                 if use_cache:
                     next_decoder_cache += (present,)
             else:
+                maps = XF.bert_layer_decode(x.detach(), self.layer[i], dict(cfg, train=False), enc, encb, return_probs=True)[2] \
+                    if output_attentions else None
                 x, xb = self.layer[i].fused(x, xb, cfg, enc, encb)
+            if output_attentions:
+                all_self_attentions = all_self_attentions + (maps[0],)
+                if maps[1] is not None:
+                    all_cross_attentions = all_cross_attentions + (maps[1],)
         if output_hidden_states:
             all_hidden_states = all_hidden_states + (x,)
         if not return_dict:
-            return tuple(v for v in [x, next_decoder_cache, all_hidden_states] if v is not None)
+            return tuple(v for v in [x, next_decoder_cache, all_hidden_states, all_self_attentions, all_cross_attentions]
+                         if v is not None)
         return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=x, past_key_values=next_decoder_cache,
-                                                         hidden_states=all_hidden_states, attentions=None,
-                                                         cross_attentions=None)
+                                                         hidden_states=all_hidden_states, attentions=all_self_attentions,
+                                                         cross_attentions=all_cross_attentions)
 
 
 class BertPooler(nn.Module):
@@ -539,7 +569,8 @@ class BertModel(BertPreTrainedModel):
             return (sequence_output, pooled_output) + encoder_outputs[1:]
         return BaseModelOutputWithPoolingAndCrossAttentions(
             last_hidden_state=sequence_output, pooler_output=pooled_output, past_key_values=encoder_outputs.past_key_values,
-            hidden_states=encoder_outputs.hidden_states, attentions=None, cross_attentions=None)
+            hidden_states=encoder_outputs.hidden_states, attentions=encoder_outputs.attentions,
+            cross_attentions=encoder_outputs.cross_attentions)
 
 
 class LabelSmoothSoftmaxCEV1(nn.Module):
@@ -619,7 +650,8 @@ class BertLMHeadModel(BertPreTrainedModel):
             output = (prediction_scores,) + outputs[2:]
             return ((lm_loss,) + output) if lm_loss is not None else output
         return CausalLMOutputWithCrossAttentions(loss=lm_loss, logits=prediction_scores, past_key_values=outputs.past_key_values,
-                                                 hidden_states=outputs.hidden_states, attentions=None, cross_attentions=None)
+                                                 hidden_states=outputs.hidden_states, attentions=outputs.attentions,
+                                                 cross_attentions=outputs.cross_attentions)
 
     def prepare_inputs_for_generation(self, input_ids, past=None, attention_mask=None, **model_kwargs):
         """Cut the prompt to its last token once a cache exists (models/xbert.py:1390-1407)."""
@@ -770,4 +802,4 @@ class BertForMaskedLM(BertPreTrainedModel):
             output = (prediction_scores,) + outputs[2:]
             return ((masked_lm_loss,) + output) if masked_lm_loss is not None else output
         return MaskedLMOutput(loss=masked_lm_loss, logits=prediction_scores, hidden_states=outputs.hidden_states,
-                              attentions=None)
+                              attentions=outputs.attentions)

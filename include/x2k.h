@@ -107,9 +107,27 @@ typedef struct X2kGemmArgs {
                               accumulated with atomics), 1 = never, n = force n slices */
   const uint64_t* dropout_offset_dev; /* optional device counter ADDED to dropout_offset at run time: a captured
                               CUDA graph advances it between replays so every step draws fresh masks */
+  /* Fused cross entropy over N (the vocabulary GEMM of the MLM / LM heads, models/xbert.py:805-834 + :1653-1661):
+   *   ce_mode 1: no logits are stored; after the bias add every 16-column group of row m writes its online-softmax
+   *              statistics (max, sum exp(v - max)) to ce_partials[m, n/16, 0..1] and the label's logit to
+   *              ce_target_logit[m]; x2k_ce_finalize turns them into the row's log-sum-exp and loss;
+   *   ce_mode 2: (backward) the logits are recomputed and out_bf16[m,n] = ce_row_grad[m] * (exp(v - ce_lse[m]) - [n == label]).
+   * ce_labels: int64 [M], negative = ignored row (loss 0, no target logit). */
+  int32_t ce_mode;
+  const int64_t* ce_labels;
+  float* ce_partials;
+  float* ce_target_logit;
+  const float* ce_lse;
+  const float* ce_row_grad;
 } X2kGemmArgs;
 
 int x2k_gemm(const X2kGemmArgs* args, void* stream);
+
+/* Second half of the fused cross entropy: per row m reduce the ceil(N/16) partial statistics of x2k_gemm(ce_mode 1) into
+ * lse[m] = log sum_n exp(logit[m,n]) and loss[m] = labels[m] >= 0 ? lse[m] - target_logit[m] : 0 (CrossEntropyLoss with
+ * ignore_index, reduction 'none').  Streaming, one warp per row. */
+int x2k_ce_finalize(const float* partials, const float* target_logit, const int64_t* labels, int32_t M, int32_t N,
+                    float* lse, float* loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound): LayerNorm forward / backward.
@@ -265,6 +283,42 @@ int x2k_relpos_bias_gather(const float* table, const int64_t* index, int32_t N, 
 int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H, int32_t N, int64_t ds_b_stride,
                             int64_t ds_h_stride, int64_t ds_q_stride, const int64_t* index,
                             float* dtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The two small HBM-bound ends of the encoders.  D must be a multiple of 128, <= 1024.
+ *
+ * x2k_embed_ln_fwd: y[m] = dropout(LayerNorm(word[ids[m]] + pos[p(m)] + type[t(m)])), t(m) = type_ids ? type_ids[m] : 0,
+ *   p(m) = pos_ids ? pos_ids[m] : pos_offset + m % L.  Writes y_f32 (and y_bf16 if given) and the LayerNorm statistics
+ *   mean / rstd [M] for backward.  Dropout element index m*D + n of the Philox stream described at x2k_gemm.
+ *   Replaces BertEmbeddings.forward (models/xbert.py:189-216): three gathers, two adds, LayerNorm, dropout.
+ * x2k_embed_ln_bwd: recomputes the summed row, applies dropout' and LayerNorm' and ACCUMULATES (+=, vector reductions)
+ *   the row gradient into dword[ids[m]], dpos[p(m)], dtype[t(m)]; dw / db (LayerNorm weight / bias) are accumulated too.
+ * ------------------------------------------------------------------------------------------ */
+int x2k_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int32_t M, int32_t D,
+                     int32_t L, int32_t pos_offset, const float* word, const float* pos, const float* type,
+                     const float* ln_w, const float* ln_b, float eps, float dropout_p, uint64_t dropout_seed,
+                     uint64_t dropout_offset, const uint64_t* dropout_offset_dev, float* y_f32, void* y_bf16,
+                     float* mean, float* rstd, void* stream);
+int x2k_embed_ln_bwd(const float* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int32_t M,
+                     int32_t D, int32_t L, int32_t pos_offset, const float* word, const float* pos, const float* type,
+                     const float* ln_w, const float* ln_b, const float* mean, const float* rstd, float dropout_p,
+                     uint64_t dropout_seed, uint64_t dropout_offset, const uint64_t* dropout_offset_dev, float* dword,
+                     float* dpos, float* dtype, float* dw, float* db, void* stream);
+
+/* x2k_pool_tail_fwd: the tail of VisionTransformer.forward (models/beit2.py:409-436).  x [n_img, N, D] is the output of
+ *   the last block (token 0 = cls, dropped).  For every output sequence s (image g = group ? group[s] : s):
+ *     out[s, r] = fc_norm(x[g, r]) for r = 1..N-1,   out[s, 0] = sum_r a[s,r] * out[s, r] / sum_r a[s,r]
+ *   with a = atts ? atts[s, r] (int64 0/1 region masks, column 0 ignored) : 1 — i.e. the plain mean of the normalised
+ *   patch tokens (full-image embeddings) or the mask-weighted mean of region mode (idx_to_group_img + image_atts[:, 1:]).
+ *   mean / rstd [n_out, N] (optional, both or none) keep the LayerNorm statistics for backward.
+ * x2k_pool_tail_bwd: dx[g, r] += LN'(d_out[s, r] + a[s,r] / sum a * d_out[s, 0]) by vector reductions (dx is zeroed first
+ *   unless accumulate != 0), dw / db of fc_norm accumulated. */
+int x2k_pool_tail_fwd(const float* x, int32_t n_img, int32_t n_out, int32_t N, int32_t D, const int64_t* group,
+                      const int64_t* atts, const float* w, const float* b, float eps, float* out, float* mean,
+                      float* rstd, void* stream);
+int x2k_pool_tail_bwd(const float* d_out, const float* x, int32_t n_img, int32_t n_out, int32_t N, int32_t D,
+                      const int64_t* group, const int64_t* atts, const float* w, const float* mean,
+                      const float* rstd, float* dx, int32_t accumulate, float* dw, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flat-buffer optimizer step (replaces optim.py:26-104 AdamW +

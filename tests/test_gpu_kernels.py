@@ -449,3 +449,104 @@ def test_attention_workspace_query_and_loud_failure(dev):
     a.delta_ws = delta.data_ptr()
     rc = C.lib().x2k_attn_bwd(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == -1 and b"dq_ws" in C.lib().x2k_last_error()
+
+
+@pytest.mark.parametrize("M,N", [(300, 30522), (77, 1000), (1536, 30522)])
+def test_fused_vocab_cross_entropy(dev, M, N):
+    """Vocabulary GEMM fused with the online-softmax cross entropy (x2k_gemm ce_mode 1/2 + x2k_ce_finalize; models/xbert.py
+    :805-834,1653-1661) against F.cross_entropy on fp32 logits of the same bf16 operands: per-row losses (ignored rows 0),
+    and the gradients w.r.t. the hidden states, the tied decoder weight and the bias — no [M, vocab] logits in between."""
+    import torch.nn.functional as F
+    from x2vlm_b200 import functional as XF
+    from x2vlm_b200.params import Shadow
+    g = torch.Generator(device=dev).manual_seed(5)
+    K = 768
+    w = torch.nn.Parameter(_bf(torch.randn(N, K, device=dev, generator=g) * 0.05).float())
+    bias = torch.nn.Parameter(torch.randn(N, device=dev, generator=g) * 0.1)
+    h = _bf(torch.randn(M, K, device=dev, generator=g)).float().requires_grad_(True)
+    labels = torch.randint(0, N, (M,), device=dev, generator=g)
+    labels[::7] = -100
+    labels[1] = N - 1          # label inside the ragged last 16-column group
+    labels[2] = 0
+    up = torch.rand(M, device=dev, generator=g) / M
+    rows = XF.vocab_cross_entropy(h, Shadow(w), bias, labels)
+    (rows * up).sum().backward()
+    got = (rows.detach(), h.grad.clone(), w.grad.clone(), bias.grad.clone())
+    h.grad = w.grad = bias.grad = None
+    logits = h @ w.t() + bias
+    ref = F.cross_entropy(logits, labels, reduction="none", ignore_index=-100)
+    (ref * up).sum().backward()
+    assert (got[0] - ref).abs().max().item() < 2e-3, (got[0] - ref).abs().max().item()
+    assert float(got[0][::7].abs().max()) == 0.0
+    for name, a, b in (("dh", got[1], h.grad), ("dW", got[2], w.grad), ("dbias", got[3], bias.grad)):
+        err = ((a - b).norm() / b.norm()).item()
+        assert err < 1e-2, (name, err)
+
+
+@pytest.mark.parametrize("D,p_drop", [(768, 0.0), (1024, 0.1), (128, 0.0)])
+def test_embed_ln_fused(dev, D, p_drop):
+    """x2k_embed_ln_{fwd,bwd} against word + position + token-type gathers -> LayerNorm(1e-12) -> dropout in torch
+    (models/xbert.py:189-216), the dropout mask taken from the Philox oracle."""
+    import torch.nn.functional as F
+    from oracle import philox
+    from x2vlm_b200 import functional as XF
+    g = torch.Generator(device=dev).manual_seed(3)
+    B, L, V, P, T = 5, 37, 1000, 64, 2
+    word = torch.nn.Parameter(torch.randn(V, D, device=dev, generator=g))
+    pos = torch.nn.Parameter(torch.randn(P, D, device=dev, generator=g))
+    typ = torch.nn.Parameter(torch.randn(T, D, device=dev, generator=g))
+    lw = torch.nn.Parameter(1 + 0.1 * torch.randn(D, device=dev, generator=g))
+    lb = torch.nn.Parameter(0.1 * torch.randn(D, device=dev, generator=g))
+    ids = torch.randint(0, V, (B, L), device=dev, generator=g)
+    ids[0, :5] = ids[1, :5]                      # repeated ids: the word-table scatter must accumulate
+    tt = torch.randint(0, T, (B, L), device=dev, generator=g)
+    dy = torch.randn(B, L, D, device=dev, generator=g)
+    XF.manual_seed(77)
+    y = XF.embed_ln(ids, tt, None, 3, word, pos, typ, lw, lb, 1e-12, p_drop, True)
+    y.backward(dy)
+    got = [y.detach()] + [q.grad.clone() for q in (word, pos, typ, lw, lb)]
+    for q in (word, pos, typ, lw, lb):
+        q.grad = None
+    keep = 1.0
+    if p_drop > 0:
+        keep = torch.from_numpy(philox.keep_scale(77, 0, B * L * D, p_drop)).view(B, L, D).to(dev)
+    x = word[ids] + pos[3 + torch.arange(L, device=dev)][None] + typ[tt]
+    ref = F.layer_norm(x, (D,), lw, lb, 1e-12) * keep
+    ref.backward(dy)
+    want = [ref.detach()] + [q.grad for q in (word, pos, typ, lw, lb)]
+    for name, a, b in zip(("y", "dword", "dpos", "dtype", "dln_w", "dln_b"), got, want):
+        err = ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+        assert err < 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("D", [768, 1024])
+def test_pool_tail_fused(dev, D):
+    """x2k_pool_tail_{fwd,bwd} against drop-cls -> fc_norm -> mean (models/beit2.py:409-425) and the region-mode gather +
+    mask-weighted mean (:430-434), forward and backward (shared images accumulate)."""
+    import torch.nn.functional as F
+    from x2vlm_b200 import functional as XF, synth
+    g = torch.Generator(device=dev).manual_seed(9)
+    n_img, N = 3, 197
+    x = torch.randn(n_img, N, D, device=dev, generator=g).requires_grad_(True)
+    w = torch.nn.Parameter(1 + 0.1 * torch.randn(D, device=dev, generator=g))
+    b = torch.nn.Parameter(0.1 * torch.randn(D, device=dev, generator=g))
+    rb = synth.region_batch(n_img, 7, 24, seed=2)
+    group, atts = rb["idx_to_group_img"].to(dev), rb["image_atts"].to(dev)
+    d_full = torch.randn(n_img, N, D, device=dev, generator=g)
+    d_reg = torch.randn(7, N, D, device=dev, generator=g)
+    full = XF.pool_tail(x, w, b, 1e-6)
+    reg = XF.pool_tail(x, w, b, 1e-6, group, atts)
+    ((full * d_full).sum() + (reg * d_reg).sum()).backward()
+    got = [full.detach(), reg.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone()]
+    x.grad = w.grad = b.grad = None
+    xn = F.layer_norm(x[:, 1:], (D,), w, b, 1e-6)
+    full_r = torch.cat([xn.mean(1, keepdim=True), xn], 1)
+    xb = xn[group]
+    wt = atts[:, 1:].unsqueeze(2).float()
+    reg_r = torch.cat([(wt * xb).sum(1, keepdim=True) / wt.sum(1, keepdim=True), xb], 1)
+    ((full_r * d_full).sum() + (reg_r * d_reg).sum()).backward()
+    want = [full_r.detach(), reg_r.detach(), x.grad, w.grad, b.grad]
+    for name, a, b_ in zip(("full", "region", "dx", "dw", "db"), got, want):
+        err = ((a - b_).norm() / b_.norm().clamp_min(1e-20)).item()
+        assert err < 2e-5, (name, err)
+    assert float(got[2][:, 0].abs().max()) == 0.0   # the cls output is dropped: no gradient reaches it

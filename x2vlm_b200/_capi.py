@@ -39,6 +39,8 @@ class X2kGemmArgs(ctypes.Structure):
         ("out_f32", c_void_p), ("ld_out_f32", c_int64),
         ("tile_n", c_int32), ("max_ctas", c_int32), ("split_k", c_int32),
         ("dropout_offset_dev", c_void_p),
+        ("ce_mode", c_int32), ("ce_labels", c_void_p), ("ce_partials", c_void_p), ("ce_target_logit", c_void_p),
+        ("ce_lse", c_void_p), ("ce_row_grad", c_void_p),
     ]
 
 
@@ -89,6 +91,17 @@ SYMBOLS = {
     "x2k_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "x2k_segment_sum_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "x2k_cast_f32_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "x2k_embed_ln_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    "x2k_embed_ln_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_uint64, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "x2k_pool_tail_fwd": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "x2k_pool_tail_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "x2k_ce_finalize": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "x2k_attn_fwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
     "x2k_attn_bwd": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_void_p]),
     "x2k_attn_probs": (ctypes.c_int, [ctypes.POINTER(X2kAttnArgs), c_int32, c_void_p, c_void_p]),

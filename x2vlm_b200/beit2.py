@@ -230,9 +230,8 @@ class VisionTransformer(nn.Module):
     def no_weight_decay(self):
         return {'pos_embed', 'cls_token'}
 
-    def forward_features(self, x, all_states=None, all_attentions=None):
-        """patch embed -> cls cat -> blocks -> drop cls -> fc_norm.  Returns (patch tokens [B,P,D], their mean
-        [B,1,D], hidden states tuple or None); with all_attentions (a list) the per-block attention maps are appended."""
+    def forward_blocks(self, x, all_states=None, all_attentions=None):
+        """patch embed -> cls cat -> blocks.  Returns (last block output [B, N, D] incl. the cls row, hidden states or None)."""
         x = self.patch_embed(x)
         batch_size = x.shape[0]
         x = torch.cat((self.cls_token.expand(batch_size, -1, -1), x), dim=1)
@@ -246,13 +245,22 @@ class VisionTransformer(nn.Module):
             x, attn = blk(x, output_attentions=all_attentions is not None)
             if all_attentions is not None:
                 all_attentions.append(attn)
-        x = x[:, 1:]  # the cls output is dropped (beit2.py:409)
-        x = XF.layer_norm(x, self.fc_norm.weight, self.fc_norm.bias, self.fc_norm.eps)
-        return x, x.mean(dim=1, keepdim=True), all_states
+        return x, all_states
+
+    def tail(self, x, idx_to_group_img=None, image_atts=None):
+        """models/beit2.py:409-436 as one kernel (x2k_pool_tail): the cls output is dropped, fc_norm over the patch tokens,
+        their mean becomes token 0; with idx_to_group_img / image_atts the per-region gather + mask-weighted mean."""
+        return XF.pool_tail(x.float(), self.fc_norm.weight, self.fc_norm.bias, self.fc_norm.eps, idx_to_group_img, image_atts)
+
+    def forward_features(self, x, all_states=None, all_attentions=None):
+        """Returns (normalised patch tokens [B,P,D], their mean [B,1,D], hidden states tuple or None)."""
+        x, all_states = self.forward_blocks(x, all_states, all_attentions)
+        full = self.tail(x)
+        return full[:, 1:], full[:, :1], all_states
 
     @staticmethod
     def region_pool(x, idx_to_group_img, image_atts):
-        """Per-region gather + mask-weighted mean of the patch tokens (beit2.py:430-434)."""
+        """Per-region gather + mask-weighted mean of the (already normalised) patch tokens (beit2.py:430-434), in torch."""
         x_bs = x[idx_to_group_img]
         weights = image_atts[:, 1:].unsqueeze(2).to(x.dtype)
         x_bs_cls = (weights * x_bs).sum(dim=1, keepdim=True) / weights.sum(dim=1, keepdim=True)
@@ -261,17 +269,17 @@ class VisionTransformer(nn.Module):
     def forward(self, x, idx_to_group_img=None, image_atts=None, output_attentions=None, output_hidden_states=None):
         assert output_attentions == output_hidden_states
         attns = [] if output_attentions else None
-        x, x_cls, all_states = self.forward_features(x, () if output_hidden_states else None, attns)
+        x, all_states = self.forward_blocks(x, () if output_hidden_states else None, attns)
+        full = self.tail(x)
         if idx_to_group_img is None:
-            x = torch.cat([x_cls, x], dim=1)
             if output_hidden_states:
-                all_states = all_states + (x,)
+                all_states = all_states + (full,)
                 assert len(all_states) == len(attns) + 1
-                return {'last_hidden_state': x, 'hidden_states': all_states, 'attentions': tuple(attns)}
-            return x
+                return {'last_hidden_state': full, 'hidden_states': all_states, 'attentions': tuple(attns)}
+            return full
         if output_hidden_states:
             raise NotImplementedError("not implemented KD for BBox Loss")
-        return self.region_pool(x, idx_to_group_img, image_atts), torch.cat([x_cls, x], dim=1)
+        return self.tail(x, idx_to_group_img, image_atts), full
 
 
 def beit_base_patch16(img_size, **kwargs):

@@ -50,7 +50,50 @@ struct EpiParams {
   int64_t ld_out_f32;
   // debug overrides for the MN-major smem descriptors (0 = defaults); env X2K_DBG_MN="lbo,sbo,kadv"
   uint32_t dbg_lbo, dbg_sbo, dbg_kadv;
+  // fused cross entropy over the N (vocabulary) dimension, generic epilogue only (X2kGemmArgs.ce_*)
+  int ce_mode;                // 0 off, 1 softmax statistics (no logits are stored), 2 gradient (exp(v - lse) - onehot) * row_grad
+  const int64_t* ce_labels;   // [M], negative = ignored row
+  float* ce_partials;         // mode 1: [M, ceil(N/16), 2] (max, sum exp(v - max)) per 16-column group
+  float* ce_target_logit;     // mode 1: [M] logit of the label
+  const float* ce_lse;        // mode 2: [M] log-sum-exp from x2k_ce_finalize
+  const float* ce_row_grad;   // mode 2: [M] upstream gradient of the per-row loss
 };
+
+// natural-log online-softmax statistics of 16 logits (columns >= n_valid excluded)
+__device__ __forceinline__ void ce_stats16(const float (&v)[16], int n_valid, float& mx, float& sum) {
+  mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < n_valid) mx = fmaxf(mx, v[j]);
+  sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < n_valid) sum += fast_exp2((v[j] - mx) * 1.4426950408889634f);
+}
+// fused-CE work on the 16 columns [n0, n0+16) of row m (after the bias add); returns through v in mode 2
+__device__ __forceinline__ void ce_apply16(const EpiParams& p, int m, int n0, float (&v)[16]) {
+  if (m >= p.M) return;
+  const int n_valid = min(16, p.N - n0);
+  const long long lbl = p.ce_labels ? p.ce_labels[m] : -1;
+  const int t = (lbl >= n0 && lbl < n0 + n_valid) ? static_cast<int>(lbl - n0) : -1;
+  if (p.ce_mode == 1) {
+    float mx, sum;
+    ce_stats16(v, n_valid, mx, sum);
+    const int64_t groups = (p.N + 15) >> 4;
+    float2* dst = reinterpret_cast<float2*>(p.ce_partials) + static_cast<int64_t>(m) * groups + (n0 >> 4);
+    *dst = make_float2(mx, sum);
+    if (t >= 0) {
+      float tl = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tl = (j == t) ? v[j] : tl;
+      p.ce_target_logit[m] = tl;
+    }
+  } else {
+    const float lse = __ldg(p.ce_lse + m), g = __ldg(p.ce_row_grad + m);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = g * (fast_exp2((v[j] - lse) * 1.4426950408889634f) - (j == t ? 1.0f : 0.0f));
+  }
+}
 
 namespace {
 
@@ -83,6 +126,7 @@ __device__ __forceinline__ void epilogue_tail16(const EpiParams& p, int m, int n
     for (int j = 0; j < 16; ++j)
       if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
   }
+  if (p.ce_mode) ce_apply16(p, m, n0, v);
   if (p.act == X2K_ACT_GELU_SAVE_GRAD) {  // preact_out receives GELU'(v), v becomes GELU(v)
     __nv_bfloat16* dst = p.preact_out + static_cast<int64_t>(m) * p.ld_preact + n0;
 #pragma unroll
@@ -293,6 +337,9 @@ __device__ __forceinline__ void epilogue_chunk32(const EpiParams& p, uint32_t sa
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nh + j));
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
+    }
+    if constexpr (kGeneric) {
+      if (p.ce_mode) ce_apply16(p, m, nh, v);
     }
     if (f_save) {
       // staged 8 elements at a time (all reciprocals / exponentials, then the polynomials): 8 independent
@@ -927,6 +974,7 @@ int dispatch_epi(int tile_n, const X2kGemmArgs& a, const EpiParams& ep, cudaStre
   if ((MASK) != EF_GENERIC && m == (MASK)) idx = I;
   X2K_EPI_LIST(X2K_EPI_CASE)
 #undef X2K_EPI_CASE
+  if (a.ce_mode) idx = 10;  // the fused cross entropy lives in the generic variant
   switch (idx % 4) {
     case 0: return gemm_epi_part0(idx, tile_n, a, ep, stream);
     case 1: return gemm_epi_part1(idx, tile_n, a, ep, stream);
@@ -951,7 +999,11 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
               (long long)a.lda, (long long)a.ldb);
   X2K_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
               "x2k_gemm: A/B must be 16-byte aligned");
-  X2K_REQUIRE(a.out_bf16 || a.out_f32 || a.preact_out, "x2k_gemm: no output");
+  X2K_REQUIRE(a.out_bf16 || a.out_f32 || a.preact_out || a.ce_mode == 1, "x2k_gemm: no output");
+  X2K_REQUIRE(a.ce_mode >= 0 && a.ce_mode <= 2, "x2k_gemm: ce_mode must be 0, 1 or 2");
+  X2K_REQUIRE(a.ce_mode != 1 || (a.ce_partials && a.ce_target_logit && a.ce_labels), "x2k_gemm: ce_mode 1 needs ce_partials, ce_target_logit, ce_labels");
+  X2K_REQUIRE(a.ce_mode != 2 || (a.ce_lse && a.ce_row_grad && a.ce_labels && a.out_bf16), "x2k_gemm: ce_mode 2 needs ce_lse, ce_row_grad, ce_labels, out_bf16");
+  X2K_REQUIRE(!a.ce_mode || a.act == X2K_ACT_NONE, "x2k_gemm: the fused cross entropy takes no activation");
   X2K_REQUIRE(!a.accumulate || a.out_f32, "x2k_gemm: accumulate needs out_f32");
   X2K_REQUIRE(a.act >= X2K_ACT_NONE && a.act <= X2K_ACT_MUL_AUX, "x2k_gemm: unknown act %d", a.act);
   X2K_REQUIRE((a.act != X2K_ACT_GELU_BWD && a.act != X2K_ACT_MUL_AUX) || a.aux, "x2k_gemm: GELU_BWD / MUL_AUX need aux");
@@ -979,6 +1031,8 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); ep.ld_out_bf16 = a.ld_out_bf16;
   ep.out_f32 = a.out_f32; ep.ld_out_f32 = a.ld_out_f32;
   ep.dbg_lbo = ep.dbg_sbo = ep.dbg_kadv = 0;
+  ep.ce_mode = a.ce_mode; ep.ce_labels = a.ce_labels; ep.ce_partials = a.ce_partials; ep.ce_target_logit = a.ce_target_logit;
+  ep.ce_lse = a.ce_lse; ep.ce_row_grad = a.ce_row_grad;
   ep.raster_m = 0;
   if (const char* r = getenv("X2K_GEMM_RASTER")) ep.raster_m = atoi(r);
 

@@ -608,3 +608,49 @@ extern "C" int x2k_segment_sum_bf16(const void* in_bf16, const int32_t* index, i
   count_launch();
   return X2K_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// fused cross entropy, second half: reduce the per-16-column online-softmax partials of x2k_gemm(ce_mode 1)
+// ---------------------------------------------------------------------------------------------
+namespace x2k {
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const float2* __restrict__ partials, const float* __restrict__ tlogit, const int64_t* __restrict__ labels,
+                   int M, int groups, float* __restrict__ lse, float* __restrict__ loss) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float2* pr = partials + static_cast<int64_t>(row) * groups;
+  float mx = -INFINITY, sum = 0.f;
+  for (int g = lane; g < groups; g += 32) {
+    const float2 v = __ldg(pr + g);
+    const float nm = fmaxf(mx, v.x);
+    if (nm > -INFINITY) sum = sum * __expf(mx - nm) + v.y * __expf(v.x - nm);
+    mx = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float nm = fmaxf(mx, om);
+    if (nm > -INFINITY) sum = sum * __expf(mx - nm) + os * __expf(om - nm);
+    mx = nm;
+  }
+  if (lane == 0) {
+    const float l = mx + __logf(sum);
+    lse[row] = l;
+    const long long lbl = labels[row];
+    loss[row] = lbl >= 0 ? l - tlogit[row] : 0.f;
+  }
+}
+}  // namespace x2k
+
+extern "C" int x2k_ce_finalize(const float* partials, const float* target_logit, const int64_t* labels, int32_t M, int32_t N,
+                               float* lse, float* loss, void* stream_) {
+  using namespace x2k;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  X2K_REQUIRE(partials && target_logit && labels && lse && loss && M > 0 && N > 0, "x2k_ce_finalize: bad arguments");
+  X2K_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 7) == 0, "x2k_ce_finalize: partials must be 8-byte aligned");
+  ce_finalize_kernel<<<(M + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const float2*>(partials), target_logit, labels, M,
+                                                      (N + 15) / 16, lse, loss);
+  X2K_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return X2K_OK;
+}

@@ -204,6 +204,145 @@ def linear(x, shadow, bias=None, gelu=False, out_bf16=False, pad_value=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# BertEmbeddings (models/xbert.py:189-216) and the vision tail (models/beit2.py:409-436) as single kernels
+# ----------------------------------------------------------------------------------------------
+class _EmbedLnFn(torch.autograd.Function):
+    """dropout(LayerNorm(word[ids] + pos[p] + type[t])): one gather + LayerNorm + dropout kernel forward, one kernel
+    backward that recomputes the row and scatters its gradient into the three tables (x2k_embed_ln_{fwd,bwd})."""
+
+    @staticmethod
+    def forward(ctx, ids, type_ids, pos_ids, pos_offset, eps, drop, word, pos, typ, ln_w, ln_b):
+        B, L = ids.shape
+        M, D, dev = B * L, word.shape[1], word.device
+        flat = lambda t: t.reshape(-1).contiguous() if t is not None else None
+        ids_f, type_f = flat(ids), flat(type_ids)
+        pos_f = flat(pos_ids.expand(B, L)) if pos_ids is not None else None
+        y = torch.empty(M, D, dtype=torch.float32, device=dev)
+        mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ops.embed_ln_fwd(ids_f, type_f, pos_f, L, pos_offset, word, pos, typ, ln_w, ln_b, eps, y, None, mean, rstd,
+                         dropout_p=drop[0], dropout_seed=drop[1], dropout_offset=drop[2])
+        ctx.meta = (L, pos_offset, drop)
+        ctx.P = (word, pos, typ, ln_w, ln_b)
+        ctx.save_for_backward(ids_f, type_f, pos_f, mean, rstd, word, pos, typ, ln_w, ln_b)
+        return y.view(B, L, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids_f, type_f, pos_f, mean, rstd, word, pos, typ, ln_w, ln_b = ctx.saved_tensors
+        L, pos_offset, drop = ctx.meta
+        dev = dy.device
+        G = [_G(q, dev) for q in ctx.P]
+        dy2 = dy.contiguous().view(-1, dy.shape[-1])
+        ops.embed_ln_bwd(dy2, ids_f, type_f, pos_f, L, pos_offset, word, pos, typ, ln_w, ln_b, mean, rstd, G[0].buf, G[1].buf,
+                         G[2].buf, G[3].buf, G[4].buf, dropout_p=drop[0], dropout_seed=drop[1], dropout_offset=drop[2])
+        return (None, None, None, None, None, None, *[g.ret() for g in G])
+
+
+def embed_ln(ids, type_ids, pos_ids, pos_offset, word, pos, typ, ln_w, ln_b, eps, p_drop, training):
+    """ids [B, L] int64 -> fp32 [B, L, D].  pos_ids None = pos_offset + arange(L) (BertEmbeddings' default)."""
+    _note_uses(word, pos, typ, ln_w, ln_b)
+    drop = _drop(p_drop, training, ids.numel() * word.shape[1])
+    return _EmbedLnFn.apply(ids, type_ids, pos_ids, int(pos_offset), float(eps), drop, word, pos, typ, ln_w, ln_b)
+
+
+class _PoolTailFn(torch.autograd.Function):
+    """[n_out, N, D]: fc_norm of the patch tokens of image group[s] (cls output dropped) with their (mask-weighted) mean
+    as token 0 (x2k_pool_tail_{fwd,bwd})."""
+
+    @staticmethod
+    def forward(ctx, x, group, atts, eps, w, b):
+        x = x.contiguous()
+        n_img, N, D = x.shape
+        n_out = group.numel() if group is not None else n_img
+        out = torch.empty(n_out, N, D, dtype=torch.float32, device=x.device)
+        need = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+        mean = torch.empty(n_out, N, device=x.device) if need else None
+        rstd = torch.empty(n_out, N, device=x.device) if need else None
+        atts_c = atts.contiguous() if atts is not None else None
+        ops.pool_tail_fwd(x, n_out, group, atts_c, w, b, eps, out, mean, rstd)
+        ctx.P = (w, b)
+        ctx.n_out = n_out
+        ctx.save_for_backward(x, group, atts_c, w, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, group, atts, w, mean, rstd = ctx.saved_tensors
+        G = [_G(q, d_out.device) for q in ctx.P]
+        dx = torch.empty_like(x)
+        ops.pool_tail_bwd(d_out.contiguous(), x, ctx.n_out, group, atts, w, mean, rstd, dx, G[0].buf, G[1].buf)
+        return (dx, None, None, None, G[0].ret(), G[1].ret())
+
+
+def pool_tail(x, w, b, eps, group=None, atts=None):
+    """Vision tail on the last block's output x [n_img, N, D] (fp32): see _PoolTailFn."""
+    _note_uses(w, b)
+    return _PoolTailFn.apply(x, group, atts, float(eps), w, b)
+
+
+# ----------------------------------------------------------------------------------------------
+# vocabulary projection fused with the cross entropy (SURVEY.md §8f rank 3)
+# ----------------------------------------------------------------------------------------------
+class _VocabCEFn(torch.autograd.Function):
+    """loss[m] = CrossEntropy(h[m] · Wᵀ + b, labels[m]) per row (0 where labels[m] < 0), without ever storing the
+    [M, vocab] logits: the GEMM epilogue emits online-softmax statistics per 16-column group (x2k_gemm ce_mode 1), a
+    streaming kernel reduces them (x2k_ce_finalize); backward recomputes the logits tile by tile and writes
+    dlogits = g[m] · (softmax - onehot) straight as the bf16 operand of the dgrad / wgrad GEMMs (ce_mode 2).
+    Replaces decoder Linear + CrossEntropyLoss of models/xbert.py:805-834,1653-1661."""
+
+    @staticmethod
+    def forward(ctx, h, bias, labels, shadow, *weights):
+        dev = h.device
+        M, K = h.shape
+        N = shadow.total_rows
+        hb = h if h.dtype == torch.bfloat16 else ops.to_bf16(h)
+        labels = labels.contiguous()
+        groups = (N + 15) // 16
+        partials = torch.empty(M, groups, 2, dtype=torch.float32, device=dev)
+        tlogit = torch.zeros(M, dtype=torch.float32, device=dev)
+        ops.gemm(hb, shadow.get(), M, N, K, bias=bias, ce=dict(mode=1, labels=labels, partials=partials, target_logit=tlogit))
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        loss = torch.empty(M, dtype=torch.float32, device=dev)
+        ops.ce_finalize(partials, tlogit, labels, M, N, lse, loss)
+        ctx.shadow, ctx.dims, ctx.h_dtype, ctx.has_bias = shadow, (M, N, K), h.dtype, bias is not None
+        ctx.save_for_backward(hb, bias, labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        hb, bias, labels, lse = ctx.saved_tensors
+        M, N, K = ctx.dims
+        dev = g.device
+        shadow = ctx.shadow
+        ld = (N + 7) // 8 * 8
+        dl = _empty_bf16(M, ld, dev=dev)
+        if ld != N:
+            dl[:, N:].zero_()
+        ops.gemm(hb, shadow.get_nograd(), M, N, K, bias=bias, out_bf16=dl,
+                 ce=dict(mode=2, labels=labels, lse=lse, row_grad=g.contiguous().float()))
+        dbias = None
+        if ctx.has_bias:
+            dbias = _zeros(N, dev)
+            ops.colsum_bf16(dl, M, N, dbias)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            if ctx.h_dtype == torch.bfloat16:
+                dh = _empty_bf16(M, K, dev=dev)
+                ops.gemm(dl, shadow.get_nograd(), M, K, N, b_mn=True, out_bf16=dh)
+            else:
+                dh = torch.empty(M, K, dtype=torch.float32, device=dev)
+                ops.gemm(dl, shadow.get_nograd(), M, K, N, b_mn=True, out_f32=dh)
+        wg = _wgrad(shadow, dl, hb, N, K, M)
+        return (dh, dbias, None, None, *wg)
+
+
+def vocab_cross_entropy(h, shadow, bias, labels):
+    """Per-row cross entropy of the vocabulary projection of h [M, K] (labels int64 [M], negative = ignored -> 0)."""
+    _note_uses(shadow)
+    return _VocabCEFn.apply(h, bias, labels, shadow, *shadow.params)
+
+
+# ----------------------------------------------------------------------------------------------
 # LayerNorm (stand-alone, fp32 in -> fp32 out)
 # ----------------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):

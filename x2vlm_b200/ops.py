@@ -100,7 +100,7 @@ def dropout_base(device):
 
 def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=None, preact_out=None,
          dropout_p=0.0, dropout_seed=0, dropout_offset=0, gamma=None, row_scale=None, rows_per_scale=0,
-         residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0, split_k=0):
+         residual=None, accumulate=False, out_bf16=None, out_f32=None, tile_n=0, split_k=0, ce=None):
     """C[M,N] = epilogue(A·Bᵀ) — see x2k_gemm in include/x2k.h.  `a`/`b` are 2-D bf16 views whose
     stride(0) is the leading dimension; MN-major operands are passed as their stored [K, M|N] matrix."""
     _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
@@ -137,6 +137,13 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
         g.out_f32, g.ld_out_f32 = out_f32.data_ptr(), out_f32.stride(0)
     g.tile_n = tile_n
     g.split_k = split_k
+    if ce is not None:  # fused cross entropy over N: dict(mode, labels, partials, target_logit) or dict(mode, labels, lse, row_grad)
+        _req(ce["labels"], torch.int64, "ce.labels")
+        g.ce_mode, g.ce_labels = int(ce["mode"]), ce["labels"].data_ptr()
+        for k in ("partials", "target_logit", "lse", "row_grad"):
+            if ce.get(k) is not None:
+                _req(ce[k], torch.float32, "ce." + k)
+                setattr(g, "ce_" + k, ce[k].data_ptr())
     def tag():
         epi = "+".join(n for n, on in (("bias", bias is not None), ("preact", preact_out is not None), ("gelu", act == C.ACT_GELU),
                                        ("gelu'", act == C.ACT_GELU_BWD), ("drop", dropout_p > 0.0),
@@ -144,6 +151,48 @@ def gemm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, act=C.ACT_NONE, aux=N
                                        ("acc", accumulate), ("f32", out_f32 is not None), ("bf16", out_bf16 is not None)) if on)
         return "%dx%dx%d %s%s %s" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", epi)
     _timed("gemm", 2.0 * M * N * K, lambda: C.check(C.lib().x2k_gemm(ctypes.byref(g), _stream()), "x2k_gemm"), tag)
+
+
+def embed_ln_fwd(ids, type_ids, pos_ids, L, pos_offset, word, pos, typ, ln_w, ln_b, eps, y_f32, y_bf16, mean, rstd, dropout_p=0.0,
+                 dropout_seed=0, dropout_offset=0):
+    """ids / type_ids / pos_ids: flat int64 [M] (type_ids / pos_ids may be None)."""
+    _req(ids, torch.int64, "ids"); _req(type_ids, torch.int64, "type_ids"); _req(pos_ids, torch.int64, "pos_ids")
+    for t, n in ((word, "word"), (pos, "pos"), (typ, "type"), (ln_w, "ln_w"), (ln_b, "ln_b"), (y_f32, "y_f32")):
+        _req(t, torch.float32, n)
+    M, D = ids.numel(), word.shape[1]
+    C.check(C.lib().x2k_embed_ln_fwd(_p(ids), _p(type_ids), _p(pos_ids), M, D, int(L), int(pos_offset), _p(word), _p(pos), _p(typ),
+                                     _p(ln_w), _p(ln_b), float(eps), float(dropout_p), int(dropout_seed), int(dropout_offset),
+                                     _p(dropout_base(word.device)) if dropout_p > 0.0 else None, _p(y_f32), _p(y_bf16), _p(mean),
+                                     _p(rstd), _stream()), "x2k_embed_ln_fwd")
+
+
+def embed_ln_bwd(dy, ids, type_ids, pos_ids, L, pos_offset, word, pos, typ, ln_w, ln_b, mean, rstd, dword, dpos, dtype, dw, db,
+                 dropout_p=0.0, dropout_seed=0, dropout_offset=0):
+    _req(dy, torch.float32, "dy")
+    M, D = ids.numel(), word.shape[1]
+    C.check(C.lib().x2k_embed_ln_bwd(_p(dy), _p(ids), _p(type_ids), _p(pos_ids), M, D, int(L), int(pos_offset), _p(word), _p(pos),
+                                     _p(typ), _p(ln_w), _p(ln_b), _p(mean), _p(rstd), float(dropout_p), int(dropout_seed),
+                                     int(dropout_offset), _p(dropout_base(word.device)) if dropout_p > 0.0 else None, _p(dword),
+                                     _p(dpos), _p(dtype), _p(dw), _p(db), _stream()), "x2k_embed_ln_bwd")
+
+
+def pool_tail_fwd(x, n_out, group, atts, w, b, eps, out, mean=None, rstd=None):
+    """x fp32 [n_img, N, D] contiguous; group int64 [n_out] or None; atts int64 [n_out, N] or None."""
+    _req(x, torch.float32, "x"); _req(group, torch.int64, "group"); _req(atts, torch.int64, "atts")
+    n_img, N, D = x.shape
+    C.check(C.lib().x2k_pool_tail_fwd(_p(x), n_img, int(n_out), N, D, _p(group), _p(atts), _p(w), _p(b), float(eps), _p(out), _p(mean),
+                                      _p(rstd), _stream()), "x2k_pool_tail_fwd")
+
+
+def pool_tail_bwd(d_out, x, n_out, group, atts, w, mean, rstd, dx, dw, db, accumulate=False):
+    _req(d_out, torch.float32, "d_out"); _req(dx, torch.float32, "dx")
+    n_img, N, D = x.shape
+    C.check(C.lib().x2k_pool_tail_bwd(_p(d_out), _p(x), n_img, int(n_out), N, D, _p(group), _p(atts), _p(w), _p(mean), _p(rstd),
+                                      _p(dx), int(accumulate), _p(dw), _p(db), _stream()), "x2k_pool_tail_bwd")
+
+
+def ce_finalize(partials, target_logit, labels, M, N, lse, loss):
+    C.check(C.lib().x2k_ce_finalize(_p(partials), _p(target_logit), _p(labels), M, N, _p(lse), _p(loss), _stream()), "x2k_ce_finalize")
 
 
 def layernorm_fwd(x, w, b, eps, y_bf16=None, y_f32=None, mean=None, rstd=None):

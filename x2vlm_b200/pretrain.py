@@ -328,16 +328,15 @@ class XVLM(nn.Module):
         if ib["image"].dim() == 5:  # video iteration (Pretrain.py:run_video_iter): frames -> per-frame encoding -> avgpool
             assert not has_r, "video batches carry no region sub-batch"
             full, _ = self.get_frame_embeds(ib["image"])
-            patches = x_cls = None
         else:
             images = torch.cat([ib["image"], rb["image"]]) if has_r else ib["image"]
-            patches, x_cls, _ = self.vision_encoder.forward_features(images)
-            full = torch.cat([x_cls, patches], dim=1)  # [Bi + n_img_r, N, D]
+            blocks_out, _ = self.vision_encoder.forward_blocks(images)
+            full = self.vision_encoder.tail(blocks_out)  # [Bi + n_img_r, N, D]
         emb_i = full[:Bi]
         N = full.shape[1]
         atts_i = torch.ones(Bi, N, dtype=torch.long, device=dev)
         if has_r:
-            emb_r = self.vision_encoder.region_pool(patches[Bi:], rb["idx_to_group_img"], rb["image_atts"])
+            emb_r = self.vision_encoder.tail(blocks_out[Bi:], rb["idx_to_group_img"], rb["image_atts"])
             atts_r = rb["image_atts"]
         # ---- text layers: clean + masked captions of both sub-batches once ----
         ids = [ib["text_ids"], ib["text_ids_masked"]] + ([rb["text_ids"], rb["text_ids_masked"]] if has_r else [])
@@ -388,20 +387,19 @@ class XVLM(nn.Module):
                 coord, rb["target_bbox"], is_image=rb["is_image"])
         # ---- MLM head once over the masked positions of both sub-batches ----
         seq = self.text_encoder.gather_seq_out_by_pos(torch.cat(mlm_seq), torch.cat(mpos))
-        logits_p = self.text_encoder.cls.predictions(seq, padded=True)   # [B, n, pad8(V)], columns beyond V are -inf
-        Vp = logits_p.shape[-1]
-        logits = logits_p[..., :self.text_encoder.config.vocab_size]
-        # ONE cross entropy over all masked positions (per-row losses), then the two means: slicing the 30k-wide logits
-        # per sub-batch would make autograd materialise and add two full-size zero-padded gradients
+        # vocabulary GEMM fused with the cross entropy: per-position losses (0 where the target is -100) without the
+        # [positions, 30522] logits; then the two means
         tgt = torch.cat(mids).reshape(-1)
-        ce = F.cross_entropy(logits_p.reshape(-1, Vp), tgt, reduction='none')   # 0 where the target is -100
+        ce = self.text_encoder.cls.predictions.loss_rows(seq, tgt)
         n_i = mids[0].numel()
         losses["image"]["loss_mlm"] = ce[:n_i].sum() / (tgt[:n_i] != -100).sum()
         if has_r:
             losses["region"]["loss_mlm"] = ce[n_i:].sum() / (tgt[n_i:] != -100).sum()
         if out is not None:
+            with torch.no_grad():  # only on request (tests): the step itself never forms the logits
+                logits = self.text_encoder.cls.predictions(seq[:Bi])
             out.update(image_embeds=emb_i, text_embeds=te_i, image_feat=fi_i, text_feat=ft_i, itm_logits=itm_logits_i,
-                       mlm_logits=logits[:Bi], cross=cross)
+                       mlm_logits=logits, cross=cross)
             if has_r:
                 out.update(bbox_coord=coord)
         return losses

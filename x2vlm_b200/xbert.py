@@ -54,8 +54,14 @@ class BertEmbeddings(nn.Module):
     def forward(self, input_ids=None, token_type_ids=None, position_ids=None, inputs_embeds=None, past_key_values_length=0):
         input_shape = input_ids.size() if input_ids is not None else inputs_embeds.size()[:-1]
         seq_length = input_shape[1]
+        explicit_pos = position_ids is not None
         if position_ids is None:
             position_ids = self.position_ids[:, past_key_values_length: seq_length + past_key_values_length]
+        if inputs_embeds is None and self.position_embedding_type == "absolute" and input_ids.is_cuda:
+            # one kernel: three gathers + LayerNorm + dropout (x2k_embed_ln_fwd); token_type_ids None = all zeros
+            return XF.embed_ln(input_ids, token_type_ids, position_ids if explicit_pos else None, past_key_values_length,
+                               self.word_embeddings.weight, self.position_embeddings.weight, self.token_type_embeddings.weight,
+                               self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, self.dropout.p, self.training)
         if token_type_ids is None:
             token_type_ids = torch.zeros(input_shape, dtype=torch.long, device=self.position_ids.device)
         if inputs_embeds is None:
@@ -414,6 +420,14 @@ class BertLMPredictionHead(nn.Module):
         return logits.reshape(*shp[:-1], -1)
 
 
+    def loss_rows(self, hidden_states, labels):
+        """Per-position cross entropy (0 where the label is negative / -100) of transform + tied decoder WITHOUT storing
+        the [positions, vocab] logits: vocabulary GEMM fused with an online-softmax cross entropy (functional._VocabCEFn).
+        hidden_states [..., D], labels [...] -> [positions] fp32."""
+        h = self.transform(hidden_states)
+        return XF.vocab_cross_entropy(h.reshape(-1, h.shape[-1]), self._decoder_shadow(), self.bias, labels.reshape(-1))
+
+
 class BertOnlyMLMHead(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -632,6 +646,23 @@ class BertLMHeadModel(BertPreTrainedModel):
                             use_cache=use_cache, output_attentions=output_attentions,
                             output_hidden_states=output_hidden_states, return_dict=return_dict, is_decoder=is_decoder, mode=mode)
         sequence_output = outputs[0]
+        if (labels is not None and not return_logits and self.label_smoothing <= 0 and getattr(self.config, "x2k_fused_ce", True)
+                and sequence_output.shape[1] > 1):
+            # shifted next-token loss (xbert.py:1359-1371) with the vocabulary GEMM fused into the cross entropy: position
+            # t predicts token t+1, the last position predicts nothing; `logits` of the output is None on this path
+            B_, L_ = sequence_output.shape[:2]
+            rows = self.cls.predictions.loss_rows(sequence_output[:, :-1].contiguous(), labels[:, 1:].contiguous())
+            if reduction == 'none':
+                lm_loss = rows.view(B_, L_ - 1).sum(1)
+            elif reduction == 'sum':
+                lm_loss = rows.sum()
+            else:
+                lm_loss = rows.sum() / (labels[:, 1:] != -100).sum()
+            if not return_dict:
+                return (lm_loss, None) + tuple(outputs[2:])
+            return CausalLMOutputWithCrossAttentions(loss=lm_loss, logits=None, past_key_values=outputs.past_key_values,
+                                                     hidden_states=outputs.hidden_states, attentions=outputs.attentions,
+                                                     cross_attentions=outputs.cross_attentions)
         prediction_scores = self.cls(sequence_output)
         if return_logits:
             return prediction_scores[:, :-1, :].contiguous()
@@ -791,6 +822,15 @@ class BertForMaskedLM(BertPreTrainedModel):
         if masked_pos is None:
             raise NotImplementedError("need check!")  # as in the reference (xbert.py:1650)
         sequence_output = self.gather_seq_out_by_pos(sequence_output, masked_pos)
+        if labels is not None and not return_logits and getattr(self.config, "x2k_fused_ce", True):
+            # loss only (what XVLMBase.get_mlm_loss reads, models/xvlm.py:900-908): the [B, n, 30522] logits are never
+            # materialised — `logits` of the returned output is None; set config.x2k_fused_ce = False to get them back
+            rows = self.cls.predictions.loss_rows(sequence_output, labels)
+            masked_lm_loss = rows.sum() / (labels.reshape(-1) != -100).sum()
+            if not return_dict:
+                return (masked_lm_loss, None) + tuple(outputs[2:])
+            return MaskedLMOutput(loss=masked_lm_loss, logits=None, hidden_states=outputs.hidden_states,
+                                  attentions=outputs.attentions)
         padded_scores = self.cls.predictions(sequence_output, padded=True)       # [B, n, pad8(V)], -inf beyond V
         prediction_scores = padded_scores[..., :self.config.vocab_size]
         if return_logits:

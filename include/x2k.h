@@ -329,12 +329,14 @@ int x2k_pool_tail_bwd(const float* d_out, const float* x, int32_t n_img, int32_t
  *   grads are pre-scaled by *grad_scale_dev (clip coefficient computed on device);
  *   also writes the bf16 shadow copy used by the GEMMs.  The step count (bias correction) is
  *   `step`, or *step_dev when step_dev != NULL (so a captured CUDA graph can advance it).
+ *   zero_grad != 0: every gradient element is set to 0 right after it has been consumed (the next step's
+ *   optimizer.zero_grad() for 4 more bytes per parameter instead of a separate 1 GB fill).
  * ------------------------------------------------------------------------------------------ */
 int x2k_sumsq(const float* g, int64_t n, float* out, void* stream);
-int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+int x2k_adamw_flat(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n,
                    const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int32_t n_seg,
                    float beta1, float beta2, float eps, int32_t step, const int32_t* step_dev,
-                   const float* grad_scale_dev, void* stream);
+                   const float* grad_scale_dev, int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

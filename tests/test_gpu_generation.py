@@ -57,6 +57,16 @@ def test_lm_head_model_vqa_losses(dev, gold):
         m.label_smoothing = 0.1
         ls = m(t("a_ids"), attention_mask=t("a_atts"), encoder_hidden_states=t("q_states"), encoder_attention_mask=t("q_atts"),
                labels=t("targets"), return_dict=True, reduction='mean')
+        # the loss-only call above is the fused vocabulary-GEMM + cross-entropy path (no logits are formed: o.logits is None);
+        # the logits themselves come from the un-fused path, whose loss must agree with the fused one
+        assert o.logits is None
+        m.label_smoothing = 0.0
+        m.config.x2k_fused_ce = False
+        o2 = m(t("a_ids"), attention_mask=t("a_atts"), encoder_hidden_states=t("q_states"), encoder_attention_mask=t("q_atts"),
+               labels=t("targets"), return_dict=True, reduction='none')
+        m.config.x2k_fused_ce = True
+    assert torch.allclose(o.loss, o2.loss, rtol=2e-3, atol=2e-3)
+    o.logits = o2.logits
     valid = g["a_atts"].bool()
     assert rel_l2(o.logits.cpu()[valid], g["vqa_logits"][valid]) < 2e-2
     assert torch.allclose(o.loss.cpu(), g["vqa_loss"], rtol=2e-2, atol=2e-2)

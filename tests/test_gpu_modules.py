@@ -81,6 +81,10 @@ def test_text_small_vs_reference_golden(dev):
         o = m(t("ids"), attention_mask=t("atts"), encoder_hidden_states=t("img"), encoder_attention_mask=t("iatt"),
               return_dict=True, labels=t("labels"), masked_pos=t("masked_pos"))
         t3 = m.bert(t("ids"), attention_mask=t("mask3d"), return_dict=True, mode="text").last_hidden_state
+        # loss-only calls run the fused vocabulary-GEMM + cross-entropy (o.logits is None); logits on request
+        assert o.logits is None
+        o.logits = m(t("ids"), attention_mask=t("atts"), encoder_hidden_states=t("img"), encoder_attention_mask=t("iatt"),
+                     return_dict=True, return_logits=True, masked_pos=t("masked_pos"))
     valid = g["atts"].bool()
     assert rel_l2(text.cpu()[valid], g["text"][valid]) < 1e-2
     assert rel_l2(cross.cpu()[valid], g["cross"][valid]) < 1e-2

@@ -85,7 +85,7 @@ for step in (1, 2, 3):
     for pp, sl in zip(prefs, (slice(0, 30000), slice(30000, 70000), slice(70000, n))):
         pp.grad = gr[sl].clone() * 0.5
     opt.step()
-    C.check(L.x2k_adamw_flat(P(p), P(gr), P(m), P(v), P(pb), n, P(seg_end), P(seg_lr), P(seg_wd), 3, 0.9, 0.98, 1e-8, step, None, P(gs), S()), "adamw")
+    C.check(L.x2k_adamw_flat(P(p), P(gr), P(m), P(v), P(pb), n, P(seg_end), P(seg_lr), P(seg_wd), 3, 0.9, 0.98, 1e-8, step, None, P(gs), 0, S()), "adamw")
 rep("adamw 3 steps", (p - torch.cat([pp.detach() for pp in prefs])).abs().max().item(), 1e-5)
 rep("adamw bf16 shadow", (pb.float() - p.bfloat16().float()).abs().max().item(), 0)
 torch.cuda.synchronize()

@@ -115,7 +115,7 @@ SYMBOLS = {
     "x2k_sumsq": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "x2k_adamw_flat": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_float,
-                                      c_int32, c_void_p, c_void_p, c_void_p]),
+                                      c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -147,8 +147,10 @@ class FlatAdamW(torch.optim.Optimizer):
         self._upload_hparams()  # picks up LambdaLR-style mutations of param_groups[i]['lr']
         self.step_dev += 1
         a = self.arena
+        # the kernel zeroes every gradient right after consuming it: the next zero_grad() is free (ParamArena.zero_grad)
         ops.adamw_flat(a.flat, a.grad, self.exp_avg, self.exp_avg_sq, a.bf16, a.numel, self.seg_end, self.seg_lr, self.seg_wd,
-                       self.betas[0], self.betas[1], self.eps, step_dev=self.step_dev, grad_scale=self.grad_scale)
+                       self.betas[0], self.betas[1], self.eps, step_dev=self.step_dev, grad_scale=self.grad_scale, zero_grad=True)
+        a.grad_is_zero = True
         self.grad_scale.fill_(1.0)
 
     def state_dict(self):

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as XF
-from .params import Shadow
+from .params import GappedBias, Shadow
 
 
 def _trunc_normal_(t, std=0.02):
@@ -127,6 +127,8 @@ class Block(nn.Module):
         # bf16 shadows / gradient sinks of the four GEMM weights
         self._x2k = {"qkv": Shadow(self.attn.qkv.weight), "proj": Shadow(self.attn.proj.weight),
                      "fc1": Shadow(self.mlp.fc1.weight), "fc2": Shadow(self.mlp.fc2.weight)}
+        if self.attn.q_bias is not None:
+            self._x2k["bqv"] = GappedBias(self.attn.q_bias, self.attn.v_bias)
         self._x2k_shadows = list(self._x2k.values())
 
     def forward(self, x, rel_pos_bias=None, return_attention=False, return_qkv=False, image_atts=None,

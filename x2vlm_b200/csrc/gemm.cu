@@ -89,7 +89,7 @@ __device__ __forceinline__ void ce_apply16(const EpiParams& p, int m, int n0, fl
       p.ce_target_logit[m] = tl;
     }
   } else {
-    const float lse = __ldg(p.ce_lse + m), g = __ldg(p.ce_row_grad + m);
+    const float lse = __ldg(p.ce_lse + m), g = lbl >= 0 ? __ldg(p.ce_row_grad + m) : 0.0f;  // ignored rows: loss == 0
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = g * (fast_exp2((v[j] - lse) * 1.4426950408889634f) - (j == t ? 1.0f : 0.0f));
   }

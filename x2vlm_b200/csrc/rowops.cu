@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 // Flat AdamW (decoupled weight decay, torch.optim.AdamW semantics):
 //   p *= 1 - lr*wd;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;
 //   p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          __nv_bfloat16* __restrict__ p_bf16, int64_t n,
                                                          const int64_t* __restrict__ seg_end,
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
                                                          const float* __restrict__ seg_wd, int n_seg, float beta1,
                                                          float beta2, float eps, int step,
                                                          const int32_t* __restrict__ step_dev,
-                                                         const float* __restrict__ grad_scale_dev) {
+                                                         const float* __restrict__ grad_scale_dev, int zero_grad) {
   const float gs = grad_scale_dev ? *grad_scale_dev : 1.0f;
   const float stepf = static_cast<float>(step_dev ? *step_dev : step);
   const float bc1 = 1.0f - powf(beta1, stepf);
@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
     const float decay = 1.0f - lr * wd, step_size = lr / bc1;
     float4 pv = reinterpret_cast<float4*>(p)[i4];
     const float4 gv = reinterpret_cast<const float4*>(g)[i4];
+    if (zero_grad) reinterpret_cast<float4*>(g)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);  // next step's zero_grad, for 4 B / param
     float4 mv = reinterpret_cast<float4*>(m)[i4];
     float4 vv = reinterpret_cast<float4*>(v)[i4];
 #define X2K_ADAM1(c)                                                         \
@@ -574,10 +575,10 @@ extern "C" int x2k_sumsq(const float* g, int64_t n, float* out, void* stream_) {
   return X2K_OK;
 }
 
-extern "C" int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+extern "C" int x2k_adamw_flat(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n,
                               const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int32_t n_seg,
                               float beta1, float beta2, float eps, int32_t step, const int32_t* step_dev,
-                              const float* grad_scale_dev, void* stream_) {
+                              const float* grad_scale_dev, int32_t zero_grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   X2K_REQUIRE(p && g && m && v && n > 0 && seg_end && seg_lr && seg_wd && n_seg > 0 && (step > 0 || step_dev),
               "x2k_adamw_flat: bad arguments");
@@ -589,7 +590,7 @@ extern "C" int x2k_adamw_flat(float* p, const float* g, float* m, float* v, void
   if (blocks > cap) blocks = cap;
   adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n,
                                                                    seg_end, seg_lr, seg_wd, n_seg, beta1, beta2, eps,
-                                                                   step, step_dev, grad_scale_dev);
+                                                                   step, step_dev, grad_scale_dev, zero_grad);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;

@@ -255,7 +255,7 @@ class _PoolTailFn(torch.autograd.Function):
         n_img, N, D = x.shape
         n_out = group.numel() if group is not None else n_img
         out = torch.empty(n_out, N, D, dtype=torch.float32, device=x.device)
-        need = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+        need = any(ctx.needs_input_grad)  # LayerNorm statistics are only kept for a backward pass
         mean = torch.empty(n_out, N, device=x.device) if need else None
         rstd = torch.empty(n_out, N, device=x.device) if need else None
         atts_c = atts.contiguous() if atts is not None else None
@@ -321,9 +321,10 @@ class _VocabCEFn(torch.autograd.Function):
         ops.gemm(hb, shadow.get_nograd(), M, N, K, bias=bias, out_bf16=dl,
                  ce=dict(mode=2, labels=labels, lse=lse, row_grad=g.contiguous().float()))
         dbias = None
-        if ctx.has_bias:
-            dbias = _zeros(N, dev)
-            ops.colsum_bf16(dl, M, N, dbias)
+        if ctx.has_bias:  # the column-sum kernel works on whole 8-column groups: sum the padded width, drop the pad
+            dbias = _zeros(ld, dev)
+            ops.colsum_bf16(dl, M, ld, dbias)
+            dbias = dbias[:N]
         dh = None
         if ctx.needs_input_grad[0]:
             if ctx.h_dtype == torch.bfloat16:
@@ -418,6 +419,7 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.gemm(act, sh["fc2"].get(), M, D, Dh, bias=fc2b, preact_out=y2, gamma=g2, row_scale=dp_scale2,
                  rows_per_scale=N, residual=x1, out_f32=out)
         ctx.blk, ctx.dims, ctx.scale = blk, (B, N, D, H, Dh, ldb), scale
+        ctx.bias_in_arena = qkv_bias is not None and not qkv_bias.requires_grad  # a view of the arena (GappedBias), not a torch.cat
         ctx.P = (n1w, n1b, table, projb, g1, n2w, n2b, fc1b, fc2b, g2)
         ctx.save_for_backward(x2, dp_scale, dp_scale2, n1w, table, g1, n2w, g2, mean1, rstd1, ln1, qkv, bias_g, attn_o, lse, y1, x1,
                               mean2, rstd2, ln2, hpre, act, y2)
@@ -462,8 +464,19 @@ class _BeitBlockFn(torch.autograd.Function):
                      dqkv[:, D:2 * D], dqkv[:, 2 * D:], ds_out=ds_out, bias=bias_g)
         if table is not None:
             ops.relpos_bias_scatter(ds_out, B, H, N, blk.attn.relative_position_index, P_table.buf)
-        d_qkvb = _zeros(3 * D, dev)
-        ops.colsum_bf16(dqkv, M, 3 * D, d_qkvb)
+        bqv = sh.get("bqv")
+        if bqv is not None and bqv.arena is not None and ctx.bias_in_arena:
+            # q / v bias gradients: column sums straight into their slices of the flat gradient (K has no bias)
+            gq, gv = bqv.grad_views()
+            if bqv.params[0].requires_grad:
+                ops.colsum_bf16(dqkv[:, :D], M, D, gq)
+            if bqv.params[1].requires_grad:
+                ops.colsum_bf16(dqkv[:, 2 * D:], M, D, gv)
+            bqv.grads_done()
+            d_qkvb = None
+        else:
+            d_qkvb = _zeros(3 * D, dev)
+            ops.colsum_bf16(dqkv, M, 3 * D, d_qkvb)
         dln1 = _empty_bf16(M, D, dev=dev)
         ops.gemm(dqkv, sh["qkv"].get_nograd(), M, D, 3 * D, b_mn=True, out_bf16=dln1)
         wg_qkv = _wgrad(sh["qkv"], dqkv, ln1, 3 * D, D, M)
@@ -471,7 +484,8 @@ class _BeitBlockFn(torch.autograd.Function):
         ops.layernorm_bwd(dln1, x2, n1w, mean1, rstd1, dx, P_n1w.buf, P_n1b.buf, dx_residual=dx1)
         # weights were passed in the order qkv, proj, fc1, fc2
         nig = ctx.needs_input_grad
-        return (dx.view(B, N, D), None, None, None, P_n1w.ret(), P_n1b.ret(), d_qkvb if nig[6] else None, P_table.ret(),
+        return (dx.view(B, N, D), None, None, None, P_n1w.ret(), P_n1b.ret(), d_qkvb if (nig[6] and d_qkvb is not None) else None,
+                P_table.ret(),
                 P_projb.ret(), P_g1.ret(), P_n2w.ret(), P_n2b.ret(), P_fc1b.ret(), P_fc2b.ret(), P_g2.ret(), *wg_qkv, *wg_proj,
                 *wg_fc1, *wg_fc2)
 
@@ -480,9 +494,16 @@ def beit_block(x, blk, dp_scale=None, dp_scale2=None):
     """x: [B, N, D] fp32.  dp_scale / dp_scale2: per-sample DropPath keep/(1-p) [B] fp32 (or None) of the attention and of
     the MLP branch — two independent draws, as the reference calls self.drop_path twice per block (beit2.py:204-207)."""
     a = blk.attn
-    # K has no bias (beit2.py:129)
-    qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)) if a.q_bias is not None else None
     sh = blk._x2k
+    # K has no bias (beit2.py:129): [q_bias | 0 | v_bias] is a view of the arena when there is one, else a torch.cat
+    bqv = sh.get("bqv")
+    if a.q_bias is None:
+        qkv_bias = None
+    elif bqv is not None and bqv.arena is not None:
+        qkv_bias = bqv.get_f32()
+        _note_uses(bqv)
+    else:
+        qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias))
     weights = (*sh["qkv"].params, *sh["proj"].params, *sh["fc1"].params, *sh["fc2"].params)
     _note_uses(sh["qkv"], sh["proj"], sh["fc1"], sh["fc2"], blk.norm1.weight, blk.norm1.bias, a.relative_position_bias_table,
                a.proj.bias, blk.gamma_1, blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias, blk.mlp.fc2.bias, blk.gamma_2)
@@ -616,6 +637,8 @@ class _BertLayerFn(torch.autograd.Function):
         ctx.packed_bias = (b_qkv, b_kvc)
         ctx.dims = (Bt, L, D, H, Di, scale)
         ctx.enc_needs_grad = has_cross and enc.requires_grad
+        if ctx.enc_needs_grad and cfg.get("fuse_d_enc"):
+            cfg["_enc_total"] = cfg.get("_enc_total", 0) + 1
         ctx.mark_non_differentiable(yb)
         ctx.set_materialize_grads(False)  # no zero-filled [Bt, L, D] gradient for the non-differentiable bf16 copy
         return y.view(Bt, L, D), yb.view(Bt, L, D)
@@ -687,9 +710,23 @@ class _BertLayerFn(torch.autograd.Function):
                 kv_shd.grads_done()
                 d_bkvc = None
             if ctx.enc_needs_grad:
-                d_enc = torch.empty(n_kv * Nk, Dv, dtype=torch.float32, device=dev)
-                ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=d_enc)
-                d_enc = d_enc.view(n_kv, Nk, Dv)
+                if cfg.get("fuse_d_enc") and cfg.get("_enc_total", 0) > 1:
+                    # every fusion layer of this encoder call reads the same image states: their gradients are summed in
+                    # the dgrad GEMM's accumulate epilogue into ONE buffer, handed to autograd by the last layer to run
+                    acc = cfg.get("_d_enc_acc")
+                    if acc is None:
+                        acc = cfg["_d_enc_acc"] = torch.empty(n_kv * Nk, Dv, dtype=torch.float32, device=dev)
+                        ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=acc)
+                    else:
+                        ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=acc, accumulate=True)
+                    cfg["_enc_left"] = cfg.get("_enc_left", cfg["_enc_total"]) - 1
+                    if cfg["_enc_left"] == 0:
+                        d_enc = acc.view(n_kv, Nk, Dv)
+                        cfg["_d_enc_acc"], cfg["_enc_left"] = None, cfg["_enc_total"]
+                else:
+                    d_enc = torch.empty(n_kv * Nk, Dv, dtype=torch.float32, device=dev)
+                    ops.gemm(dkv, sh["kvc"].get_nograd(), n_kv * Nk, Dv, 2 * D, b_mn=True, out_f32=d_enc)
+                    d_enc = d_enc.view(n_kv, Nk, Dv)
             wg_kvc = _wgrad(sh["kvc"], dkv, sv["enc2"], 2 * D, Dv, n_kv * Nk)
             ops.colsum_bf16(dqc, M, D, P_bqc.buf)
             dx1b = _empty_bf16(M, D, dev=dev)

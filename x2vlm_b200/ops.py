@@ -371,10 +371,11 @@ def sumsq(g, out, n=None):
     C.check(C.lib().x2k_sumsq(_p(g), int(n if n is not None else g.numel()), _p(out), _stream()), "x2k_sumsq")
 
 
-def adamw_flat(p, g, m, v, p_bf16, n, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step=0, step_dev=None, grad_scale=None):
+def adamw_flat(p, g, m, v, p_bf16, n, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step=0, step_dev=None, grad_scale=None,
+               zero_grad=False):
     C.check(C.lib().x2k_adamw_flat(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), int(n), _p(seg_end), _p(seg_lr), _p(seg_wd),
                                    int(seg_end.numel()), float(beta1), float(beta2), float(eps), int(step), _p(step_dev),
-                                   _p(grad_scale), _stream()), "x2k_adamw_flat")
+                                   _p(grad_scale), int(zero_grad), _stream()), "x2k_adamw_flat")
 
 
 def pad16(n):

@@ -83,6 +83,29 @@ class Shadow:
         return out
 
 
+class GappedBias(Shadow):
+    """BEiT's QKV bias (models/beit2.py:129): cat(q_bias, zeros, v_bias) — K has no bias parameter.  Inside an arena the
+    two parameters are laid out with a zero gap of one bias length between them, so the [3D] bias the packed QKV GEMM adds
+    is a plain view of the flat buffer (no torch.cat / zeros_like per block per forward) and the two bias gradients are
+    column sums written straight into their slices of the flat gradient."""
+
+    def __init__(self, q_bias, v_bias):
+        super().__init__(q_bias, v_bias, K=q_bias.numel())
+        self.gap = q_bias.numel()  # elements between the first and the second member
+
+    def get_f32(self):
+        if self.arena is None:
+            return None
+        return self.arena.flat[self.offset:self.offset + 3 * self.K]
+
+    def grad_views(self):
+        g = self.arena.grad
+        return g[self.offset:self.offset + self.K], g[self.offset + 2 * self.K:self.offset + 3 * self.K]
+
+    def get(self, count_use=True):
+        raise NotImplementedError("GappedBias has no bf16 shadow: the GEMM epilogue reads the fp32 bias")
+
+
 def collect_shadows(model):
     seen, out = set(), []
     for m in model.modules():
@@ -129,6 +152,8 @@ class ParamArena:
             packed_tail = s is not None and len(s.params) > 1 and p is not s.params[0]
             if not packed_tail:
                 off = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+            elif p is s.params[1]:
+                off += getattr(s, "gap", 0)  # zero-filled hole after the group's first member (GappedBias)
             self.offsets[id(p)] = off
             off += p.numel()
         self.numel = (off + _ALIGN - 1) // _ALIGN * _ALIGN
@@ -145,7 +170,8 @@ class ParamArena:
         for s in shadows:
             o = self.offsets[id(s.params[0])]
             for a, b in zip(s.params[:-1], s.params[1:]):
-                assert self.offsets[id(b)] == self.offsets[id(a)] + a.numel(), "packed group is not adjacent"
+                gap = getattr(s, "gap", 0) if a is s.params[0] else 0
+                assert self.offsets[id(b)] == self.offsets[id(a)] + a.numel() + gap, "packed group is not adjacent"
             s.arena, s.offset = self, o
         self.shadows = shadows
         self._pending = {}      # id(shadow) -> outstanding uses in the current backward
@@ -175,7 +201,10 @@ class ParamArena:
 
     # -- gradient bookkeeping -----------------------------------------------------------------
     def zero_grad(self):
-        self.grad.zero_()
+        # FlatAdamW.step leaves the gradient buffer zeroed (x2k_adamw_flat, zero_grad = 1): the 1 GB fill is skipped then
+        if not getattr(self, "grad_is_zero", False):
+            self.grad.zero_()
+        self.grad_is_zero = False
         self._pending.clear()
 
     def note_use(self, obj):

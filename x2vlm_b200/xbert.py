@@ -321,6 +321,8 @@ class BertEncoder(nn.Module):
             _group_cross(cfg, B, L, Nk, hidden_states.device)
             if output_layer > self.config.fusion_layer:
                 encb = ops.to_bf16(enc)  # one bf16 copy feeds the K/V projection of every fusion layer
+            # no intermediate state leaves this call: the image-state gradients of all fusion layers can share one buffer
+            cfg["fuse_d_enc"] = not output_hidden_states
         all_hidden_states = () if output_hidden_states else None
         # attention maps are rebuilt on request by a forward-only pass of the layer (the fused layer never holds them)
         all_self_attentions = () if output_attentions else None

@@ -550,3 +550,46 @@ def test_pool_tail_fused(dev, D):
         err = ((a - b_).norm() / b_.norm().clamp_min(1e-20)).item()
         assert err < 2e-5, (name, err)
     assert float(got[2][:, 0].abs().max()) == 0.0   # the cls output is dropped: no gradient reaches it
+
+
+@pytest.mark.parametrize("M,N,K", [(394, 768, 768), (2307, 1024, 256), (5000, 768, 3072)])
+def test_gemm_tma_residual_epilogues(dev, M, N, K):
+    """The five fp32 residual-stream epilogues of the CTA-pair kernel (TMA-loaded residual tiles, TMA-stored output tiles):
+    ragged M (partial last tiles are clipped by the tensor maps), several tiles per CTA (the prefetch chain crosses tile
+    boundaries), strided residual / output views."""
+    from x2vlm_b200 import ops
+    from oracle import philox
+    g = torch.Generator(device=dev).manual_seed(1)
+    A = _bf(torch.randn(M, K, device=dev, generator=g)); W = _bf(torch.randn(N, K, device=dev, generator=g) * 0.05)
+    bias = torch.randn(N, device=dev, generator=g); gamma = torch.randn(N, device=dev, generator=g)
+    res_buf = torch.randn(M, 2 * N, device=dev, generator=g)
+    res = res_buf[:, N:]                                    # strided view: ld = 2N
+    rs = torch.rand((M + 196) // 197, device=dev, generator=g) + 0.5
+    acc = A.float() @ W.float().t()
+    tol = 2e-4 * max(1.0, float(acc.abs().max()))
+    out_buf = torch.full((M + 3, N + 64), float("nan"), device=dev)
+    out = out_buf[:M, :N]                                   # the kernel must not write outside [M, N]
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    rsr = rs.repeat_interleave(197)[:M, None]
+    # variant 3: bias + pre-activation + LayerScale / DropPath + residual -> fp32 (BEiT proj / fc2)
+    ops.gemm(A, W, M, N, K, bias=bias, preact_out=pre, gamma=gamma, row_scale=rs, rows_per_scale=197, residual=res, out_f32=out)
+    assert (out - (res + (acc + bias) * gamma * rsr)).abs().max() < tol
+    assert (pre.float() - (acc + bias)).abs().max() < 0.04 * max(1.0, float(acc.abs().max()) / 8)
+    assert torch.isnan(out_buf[M:]).all() and torch.isnan(out_buf[:, N:]).all()
+    # variant 4: the same without LayerScale / DropPath
+    out.fill_(float("nan")); pre.zero_()
+    ops.gemm(A, W, M, N, K, bias=bias, preact_out=pre, residual=res, out_f32=out)
+    assert (out - (res + acc + bias)).abs().max() < tol and (pre.float() - (acc + bias)).abs().max() < 0.04 * max(1.0, float(acc.abs().max()) / 8)
+    # variant 5: bias + dropout + residual (BERT dense), exact Philox mask
+    out.fill_(float("nan"))
+    ops.gemm(A, W, M, N, K, bias=bias, dropout_p=0.1, dropout_seed=99, dropout_offset=5, residual=res, out_f32=out)
+    keep = torch.from_numpy(philox.keep_scale(99, 5, M * N, 0.1)).view(M, N).to(dev)
+    assert (out - (res + (acc + bias) * keep)).abs().max() < tol
+    # variant 6: bias + residual (eval), variant 9: residual only (dgrad + residual-stream gradient)
+    out.fill_(float("nan"))
+    ops.gemm(A, W, M, N, K, bias=bias, residual=res, out_f32=out)
+    assert (out - (res + acc + bias)).abs().max() < tol
+    out.fill_(float("nan"))
+    ops.gemm(A, W, M, N, K, residual=res, out_f32=out)
+    assert (out - (res + acc)).abs().max() < tol
+    assert torch.isnan(out_buf[M:]).all() and torch.isnan(out_buf[:, N:]).all()

@@ -147,10 +147,10 @@ class FlatAdamW(torch.optim.Optimizer):
         self._upload_hparams()  # picks up LambdaLR-style mutations of param_groups[i]['lr']
         self.step_dev += 1
         a = self.arena
-        # the kernel zeroes every gradient right after consuming it: the next zero_grad() is free (ParamArena.zero_grad)
+        # (x2k_adamw_flat can also zero the gradients it consumed — zero_grad=1 — but the ninth memory stream drops the
+        #  kernel from 5.7 to 1.5 TB/s on B200: 5.8 ms instead of 1.3 ms + a 0.3 ms fill, profiles/r02g_launches_step.md)
         ops.adamw_flat(a.flat, a.grad, self.exp_avg, self.exp_avg_sq, a.bf16, a.numel, self.seg_end, self.seg_lr, self.seg_wd,
-                       self.betas[0], self.betas[1], self.eps, step_dev=self.step_dev, grad_scale=self.grad_scale, zero_grad=True)
-        a.grad_is_zero = True
+                       self.betas[0], self.betas[1], self.eps, step_dev=self.step_dev, grad_scale=self.grad_scale)
         self.grad_scale.fill_(1.0)
 
     def state_dict(self):

@@ -14,6 +14,8 @@
 //     per (query block, key block) tile, reusing the P / dS shared-memory tiles both K-major
 //     (dQ = dS·K) and MN-major (dK = dSᵀ·Q, dV = Pᵀ·dO); TMEM holds S, dP, dQ[2], dK, dV = 512 cols.
 // Replaces models/beit2.py:135-159 and models/xbert.py:364-410 (+ autograd).
+#include <cstdlib>
+
 #include "attn_common.cuh"
 
 namespace x2k {
@@ -571,7 +573,8 @@ extern "C" int x2k_attn_fwd(const X2kAttnArgs* args, void* stream_) {
     if (rc <= 0) return rc;
   }
   X2K_REQUIRE(a.kv_groups == nullptr, "x2k_attn_fwd: kv_groups given but the shape is not eligible for the grouped kernel");
-  if (a.Lk > 256) return attn_long_fwd(a, stream);  // key-blocked online-softmax kernel (attn_long.cu)
+  static const bool force_long = getenv("X2K_ATTN_LONG") != nullptr;  // developer switch: time the key-blocked kernels on short shapes
+  if (a.Lk > 256 || force_long) return attn_long_fwd(a, stream);  // key-blocked online-softmax kernel (attn_long.cu)
   AttnParams p;
   fill_params(a, p);
   const int n_kv = a.n_kv > 0 ? a.n_kv : a.B;
@@ -646,7 +649,8 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
     if (rc <= 0) return rc;
   }
   X2K_REQUIRE(a.kv_groups == nullptr, "x2k_attn_bwd: kv_groups given but the shape is not eligible for the grouped kernel");
-  if (a.Lq > 256 || a.Lk > 256) return attn_long_bwd(a, stream);  // key-blocked kernel, dQ through an fp32 workspace
+  static const bool force_long = getenv("X2K_ATTN_LONG") != nullptr;
+  if (a.Lq > 256 || a.Lk > 256 || (force_long && a.dq_ws)) return attn_long_bwd(a, stream);  // key-blocked kernel, dQ through an fp32 workspace
   X2K_REQUIRE(!a.ds_out || (a.ds_q_stride % 8 == 0 && a.ds_h_stride % 8 == 0 && a.ds_b_stride % 8 == 0 &&
                             a.ds_q_stride >= ((a.Lk + 15) & ~15)),
               "x2k_attn_bwd: ds_out strides must be multiples of 8 and cover Lk_pad");
@@ -676,7 +680,8 @@ extern "C" int64_t x2k_attn_bwd_workspace_bytes(const X2kAttnArgs* args) {
   const X2kAttnArgs& a = *args;
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0 || a.Lk <= 0) return 0;
   // the packed short-sequence kernels (Lq <= 64 and Lk <= 256) and the whole-range kernels (both <= 256) need none
-  return (a.Lq > 256 || a.Lk > 256) ? attn_long_bwd_ws_bytes(a) : 0;
+  static const bool force_long = getenv("X2K_ATTN_LONG") != nullptr;  // developer switch (see x2k_attn_bwd)
+  return (a.Lq > 256 || a.Lk > 256 || (force_long && a.Lq > 64)) ? attn_long_bwd_ws_bytes(a) : 0;
 }
 
 extern "C" int x2k_attn_probs(const X2kAttnArgs* args, int32_t mode, float* out, void* stream_) {

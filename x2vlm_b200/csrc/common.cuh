@@ -31,6 +31,9 @@ EncodeTiledFn encode_tiled_fn();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// fp32 [rows, cols] (ld elements), box 32 rows x 16 columns, 64B swizzle == the GEMM epilogue's transpose-tile layout.
+int make_tmap_f32_epi(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
+
 // 3-D view [n_seq][seq_rows][cols] (box [1][box_rows][64], 128B swizzle): box rows past seq_rows are zero-filled by
 // loads and skipped by stores.
 int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols, uint64_t ld,
@@ -210,6 +213,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t sme
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -50,6 +50,7 @@ struct EpiParams {
   int64_t ld_out_f32;
   // debug overrides for the MN-major smem descriptors (0 = defaults); env X2K_DBG_MN="lbo,sbo,kadv"
   uint32_t dbg_lbo, dbg_sbo, dbg_kadv;
+  int tma_epi;  // host-side decision: residual tiles TMA-loaded / fp32 output tiles TMA-stored (pair kernel, see epilogue_warp_tma)
   // fused cross entropy over the N (vocabulary) dimension, generic epilogue only (X2kGemmArgs.ce_*)
   int ce_mode;                // 0 off, 1 softmax statistics (no logits are stored), 2 gradient (exp(v - lse) - onehot) * row_grad
   const int64_t* ce_labels;   // [M], negative = ignored row
@@ -490,6 +491,142 @@ __device__ __forceinline__ void epilogue_warp_columns(const EpiParams& p, uint32
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged epilogue of the fp32 residual-stream GEMMs (bias [+ pre-activation] [+ dropout] [+ LayerScale / DropPath]
+// + residual -> fp32): out = f(acc) + residual.  The thread-per-row <-> coalesced transposition still goes through the
+// per-warp 32 x 64-byte tile, but the tile's GLOBAL side is moved by the TMA engine instead of LDG/STS and LDS/STG:
+//   * the residual tile of the NEXT 16-column half is requested (cp.async.bulk.tensor, 64B swizzle == epi_off layout)
+//     as soon as the current one has been read, so its latency hides behind the TMEM load / bias / dropout math of that
+//     half — and the first half of the next output tile is requested before this warp goes to wait for the MMAs;
+//   * the finished fp32 half is written into a second tile and leaves by one cp.async.bulk.tensor store
+//     (UTMASTG): no per-thread global stores, out-of-range rows are clipped by the tensor map.
+// One 2 KB input tile + one 2 KB output tile + one mbarrier per epilogue warp (5 operand stages instead of 6).
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+constexpr bool kTmaEpi = EPI != EF_GENERIC && (EPI & EF_RESIDUAL) != 0 && (EPI & EF_OUT_F32) != 0;
+
+struct TmaEpiState {
+  uint32_t sa_r, sa_o;  // shared-space addresses of the residual (in) and output tiles of this warp
+  uint64_t* bar;        // completion barrier of the residual loads
+  uint32_t phase;
+  bool pending;         // a residual load is in flight
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp_tma(const EpiParams& p, const CUtensorMap* tm_res, const CUtensorMap* tm_out,
+                                                  TmaEpiState& st, int lane, int mw, int n_first, uint32_t taddr, int next_mw,
+                                                  int next_n) {
+  constexpr int NCH = 2;  // 64 columns per warp
+  const int m = mw + lane;
+  const bool rows_live = mw < p.M;
+  const int rows = min(32, p.M - mw);
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int n0 = n_first + ci * 32;
+    const bool live = rows_live && n0 < p.N;  // N % 32 == 0 on this path: a chunk is whole or absent
+    uint32_t wpre[16];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int nh = n0 + 16 * hf;
+      float v[16];
+      if (live) {
+        uint32_t acc[16];
+        tmem_ld_32x16(taddr + ci * 32 + 16 * hf, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+        if constexpr ((EPI & EF_BIAS) != 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nh + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if constexpr ((EPI & EF_PREACT) != 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wpre[8 * hf + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
+        if constexpr ((EPI & EF_DROPOUT) != 0) {
+          if (p.dropout_p > 0.0f) {
+            const DropCfg dc = make_drop(p.dropout_p);
+            const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(nh);
+            const uint64_t doff = p.dropout_offset + (p.dropout_offset_dev ? __ldg(p.dropout_offset_dev) : 0ull);
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+              float k[8];
+              drop8(p.dropout_seed, doff, (base + j) >> 3, dc, k);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[j + i] *= k[i];
+            }
+          }
+        }
+        if constexpr ((EPI & EF_SCALE) != 0) {
+          if (p.gamma) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + nh + j));
+              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+            }
+          }
+          if (p.row_scale) {
+            const float sc = __ldg(p.row_scale + min(m, p.M - 1) / p.rows_per_scale);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= sc;
+          }
+        }
+      }
+      // ---- residual half: landed by TMA while the math above ran ----
+      if (st.pending) {  // warp-uniform
+        mbar_wait_warp(st.bar, st.phase);
+        st.phase ^= 1;
+        uint32_t w[16];
+        tile_get(st.sa_r, lane, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(w[j]);  // consumes the loads before the tile is re-filled
+        __syncwarp();
+      }
+      // ---- request the next half this warp will need: same chunk, next chunk, or the next output tile ----
+      {
+        int pn, pm;
+        bool pv;
+        if (hf == 0) { pn = nh + 16; pm = mw; pv = live; }
+        else if (ci + 1 < NCH) { pn = n0 + 32; pm = mw; pv = rows_live && pn < p.N; }
+        else { pn = next_n; pm = next_mw; pv = next_mw >= 0 && next_mw < p.M && next_n < p.N; }
+        if (pv && lane == 0) {
+          mbar_arrive_expect_tx(st.bar, EPI_TILE_BYTES);
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(st.sa_r), "l"(reinterpret_cast<uint64_t>(tm_res)), "r"(smem_u32(st.bar)), "r"(pn), "r"(pm) : "memory");
+        }
+        st.pending = pv;
+      }
+      // ---- fp32 half -> output tile -> one TMA store ----
+      if (live) {
+        if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the output tile
+        __syncwarp();
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[j]);
+        tile_put(st.sa_o, lane, w);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_out, st.sa_o, nh, mw);
+          tma_store_commit();
+        }
+      }
+    }
+    if constexpr ((EPI & EF_PREACT) != 0) {
+      if (live) {  // bf16 pre-activation of the whole 32-column chunk through the output tile (synchronous path)
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        tile_put(st.sa_o, lane, wpre);
+        tile_store(st.sa_o, lane, reinterpret_cast<uint8_t*>(p.preact_out + static_cast<int64_t>(mw) * p.ld_preact + n0),
+                   p.ld_preact * 2, rows, false);
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -659,21 +796,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 template <int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                          const EpiParams p) {
   constexpr int BLOCK_N = 256;
   constexpr int HALF_N = 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + HALF_N * BLOCK_K * 2;  // 32 KB
-  constexpr int STAGES = 6;  // 6 x 32 KB + 32 KB of epilogue transpose tiles
+  // 6 x 32 KB of operand stages + 32 KB of epilogue transpose tiles — or, for the fp32 residual-stream epilogues, 5 stages
+  // + 64 KB: every epilogue warp gets a TMA-filled residual tile next to its output tile (epilogue_warp_tma)
+  constexpr bool TMA_EPI = kTmaEpi<EPI>;
+  constexpr int STAGES = TMA_EPI ? 5 : 6;
+  constexpr int EPI_BYTES_PER_WARP = TMA_EPI ? 2 * EPI_TILE_BYTES : EPI_TILE_BYTES;
   constexpr int TMEM_COLS = 512;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t epi_stage = smem_u32(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_TILE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * EPI_BYTES_PER_WARP);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* epi_bar = tmem_empty_bar + 2;  // [NUM_EPI_WARPS], TMA_EPI only
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(epi_bar + (TMA_EPI ? NUM_EPI_WARPS : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -700,6 +843,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full_bar[s], 1);
         mbar_init(&tmem_empty_bar[s], 2 * NUM_EPI_WARPS);  // CTA 0: epilogue warps of both CTAs
+      }
+      if (TMA_EPI) {
+        for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(&epi_bar[s], 1);
       }
       fence_barrier_init();
     }
@@ -789,6 +935,26 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);
     int acc_stage = 0;
     uint32_t acc_phase = 0;
+    const bool use_tma = TMA_EPI && p.tma_epi;
+    TmaEpiState st;
+    st.sa_r = epi_stage + ew * EPI_BYTES_PER_WARP;
+    st.sa_o = st.sa_r + EPI_TILE_BYTES;
+    st.bar = &epi_bar[TMA_EPI ? ew : 0];
+    st.phase = 0;
+    st.pending = false;
+    if constexpr (TMA_EPI) {
+      if (use_tma && pair < num_tiles) {  // residual of this warp's first half: lands while the first tile's MMAs run
+        const int t0 = pair / split_k;
+        const int pm = (t0 / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32, pn = (t0 % n_tiles) * BLOCK_N + part * COLS_PER_WARP;
+        const bool pv = pm < p.M && pn < p.N;
+        if (pv && lane == 0) {
+          mbar_arrive_expect_tx(st.bar, EPI_TILE_BYTES);
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(st.sa_r), "l"(reinterpret_cast<uint64_t>(&tmap_res)), "r"(smem_u32(st.bar)), "r"(pn), "r"(pm) : "memory");
+        }
+        st.pending = pv;
+      }
+    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int t = tile / split_k;
       const int m0 = (t / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
@@ -796,17 +962,32 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_wait_warp(&tmem_full_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_stage * BLOCK_N + part * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
-      if (tile + num_pairs < num_tiles) {  // inputs of the next tile -> L2
-        const int tn = (tile + num_pairs) / split_k;
-        epilogue_prefetch<EPI, COLS_PER_WARP>(p, lane, (tn / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32,
-                                              (tn % n_tiles) * BLOCK_N + part * COLS_PER_WARP);
+      const bool has_next = tile + num_pairs < num_tiles;
+      const int tn = has_next ? (tile + num_pairs) / split_k : 0;
+      const int m0n = (tn / n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M, n0n = (tn % n_tiles) * BLOCK_N;
+      bool done = false;
+      if constexpr (TMA_EPI) {
+        if (use_tma) {
+          if (has_next)  // next tile's residual rows -> L2, so the per-half TMA loads only pay an L2 hit
+            epilogue_prefetch<EPI, COLS_PER_WARP>(p, lane, m0n + quad * 32, n0n + part * COLS_PER_WARP);
+          epilogue_warp_tma<EPI>(p, &tmap_res, &tmap_out, st, lane, m0 + quad * 32, n0 + part * COLS_PER_WARP, taddr,
+                                 has_next ? m0n + quad * 32 : -1, n0n + part * COLS_PER_WARP);
+          done = true;
+        }
       }
-      epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_TILE_BYTES, lane, m0 + quad * 32,
-                                                     n0 + part * COLS_PER_WARP, taddr);
+      if (!done) {
+        if (has_next)  // inputs of the next tile -> L2
+          epilogue_prefetch<EPI, COLS_PER_WARP>(p, lane, m0n + quad * 32, n0n + part * COLS_PER_WARP);
+        epilogue_warp_columns<EPI, COLS_PER_WARP / 32>(p, epi_stage + ew * EPI_BYTES_PER_WARP, lane, m0 + quad * 32,
+                                                       n0 + part * COLS_PER_WARP, taddr);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta0(&tmem_empty_bar[acc_stage]);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+    if constexpr (TMA_EPI) {
+      if (use_tma && lane == 0) tma_store_wait_read();  // the last store has read its tile before the CTA may exit
     }
   }
 
@@ -818,7 +999,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
+// 6 stages + 16 x 2 KB tiles, or 5 stages + 16 x 4 KB tiles (TMA-staged epilogue): the same 224 KB; barriers: 2*STAGES + 4 (+ 16)
 constexpr int PAIR_SMEM_BYTES = 6 * (A_TILE_BYTES + 128 * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_TILE_BYTES + 1024 + 256;
+static_assert(5 * (A_TILE_BYTES + 128 * BLOCK_K * 2) + NUM_EPI_WARPS * 2 * EPI_TILE_BYTES == 6 * (A_TILE_BYTES + 128 * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_TILE_BYTES, "smem budget");
+static_assert((2 * 5 + 4 + NUM_EPI_WARPS) * 8 + 8 <= 256 && (2 * 6 + 4) * 8 + 8 <= 256, "barrier area");
 
 template <int A_MN, int B_MN, int EPI>
 int launch_pair(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) {
@@ -830,6 +1014,11 @@ int launch_pair(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) 
   if (B_MN == 0) rc = make_tmap_bf16_2d(&tb, a.B, a.N, a.K, a.ldb, 128, BLOCK_K);
   else rc = make_tmap_bf16_2d(&tb, a.B, a.K, a.N, a.ldb, BLOCK_K, 64);
   if (rc) return rc;
+  CUtensorMap tres = ta, tout = ta;  // placeholders unless the TMA-staged epilogue runs
+  if (kTmaEpi<EPI> && ep.tma_epi) {
+    if ((rc = make_tmap_f32_epi(&tres, a.residual, a.M, a.N, a.ld_res))) return rc;
+    if ((rc = make_tmap_f32_epi(&tout, a.out_f32, a.M, a.N, a.ld_out_f32))) return rc;
+  }
   auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -854,7 +1043,7 @@ int launch_pair(const X2kGemmArgs& a, const EpiParams& ep, cudaStream_t stream) 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  X2K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep));
+  X2K_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tres, tout, ep));
   count_launch();
   return X2K_OK;
 }
@@ -1074,6 +1263,14 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
         X2K_CHECK_CUDA(cudaMemset2DAsync(a.out_f32, a.ld_out_f32 * sizeof(float), 0, static_cast<size_t>(a.N) * sizeof(float),
                                          a.M, stream));
     }
+  }
+  // TMA-staged fp32 residual epilogue (pair kernel): whole 32-column chunks only, plain (non-accumulating) fp32 output
+  ep.tma_epi = 0;
+  {
+    static const bool off = getenv("X2K_GEMM_NO_TMA_EPI") != nullptr;  // developer switch for A/B timing
+    if (!off && ep.use_pair && a.residual && a.out_f32 && !a.out_bf16 && !a.accumulate && ep.split_k <= 1 && a.N % 32 == 0 &&
+        a.ce_mode == 0)
+      ep.tma_epi = 1;
   }
   if (!ep.use_pair) {
     if (ep.split_k > 1 && tile_n == 0) tile_n = 128;

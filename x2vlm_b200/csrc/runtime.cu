@@ -72,6 +72,30 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return X2K_OK;
 }
 
+// fp32 row-major matrix [rows, cols] (ld elements), box = 32 rows x 16 columns (64 bytes), 64-byte swizzle: the shared-
+// memory image of a box is exactly the GEMM epilogue's per-warp transpose tile (16-byte chunk c of row r at chunk
+// c ^ ((r >> 1) & 3), gemm.cu epi_off) — residual tiles are TMA-loaded and fp32 output tiles TMA-stored in that layout.
+int make_tmap_f32_epi(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return X2K_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 epilogue) failed: %d (rows=%llu cols=%llu ld=%llu base=%p)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, base);
+    return X2K_ERR_CUDA;
+  }
+  return X2K_OK;
+}
+
 // 3-D view [n_seq][seq_rows][cols] of a row-major matrix whose sequences are seq_rows consecutive rows: box =
 // [1][box_rows][64].  Rows of a box beyond seq_rows are out of bounds in dim 1: loads zero-fill them, stores skip
 // them — a tile may be taller than the sequence without touching its neighbour.

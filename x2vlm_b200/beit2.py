@@ -132,7 +132,7 @@ class Block(nn.Module):
         self._x2k_shadows = list(self._x2k.values())
 
     def forward(self, x, rel_pos_bias=None, return_attention=False, return_qkv=False, image_atts=None,
-                output_attentions=None):
+                output_attentions=None, drop_path_scales=None):
         if return_attention or return_qkv or rel_pos_bias is not None or image_atts is not None:
             # the reference never passes these on the hot path (VisionTransformer.forward, beit2.py:401-407)
             raise NotImplementedError("x2k Block: return_attention / return_qkv / rel_pos_bias / image_atts "
@@ -140,7 +140,9 @@ class Block(nn.Module):
         # attention maps are rebuilt on request only (knowledge distillation): the fused block never materialises them
         attn_prob = XF.beit_attention_map(x, self) if output_attentions else None
         dp1 = dp2 = None
-        if isinstance(self.drop_path, DropPath):  # two independent per-sample draws per block (beit2.py:204-207)
+        if drop_path_scales is not None:  # pre-sampled for the whole encoder in one shot (VisionTransformer.forward_blocks)
+            dp1, dp2 = drop_path_scales
+        elif isinstance(self.drop_path, DropPath):  # two independent per-sample draws per block (beit2.py:204-207)
             dp1 = self.drop_path.sample_scale(x.shape[0], x.device)
             dp2 = self.drop_path.sample_scale(x.shape[0], x.device)
         return XF.beit_block(x, self, dp1, dp2), attn_prob
@@ -205,6 +207,8 @@ class VisionTransformer(nn.Module):
             for i in range(depth)])
         self.norm = nn.Identity()
         self.fc_norm = norm_layer(embed_dim)
+        self.register_buffer("_x2k_dp_keep", 1.0 - torch.tensor(dpr, dtype=torch.float32).view(-1, 1, 1), persistent=False)
+        self._x2k_dp_any = max(dpr) > 0
         if self.pos_embed is not None:
             _trunc_normal_(self.pos_embed, std=.02)
         _trunc_normal_(self.cls_token, std=.02)
@@ -241,10 +245,16 @@ class VisionTransformer(nn.Module):
             if x.shape[1] != self.pos_embed.shape[1]:
                 raise NotImplementedError("pos_embed interpolation (use_abs_pos_emb is False in X2-VLM)")
             x = x + self.pos_embed
-        for blk in self.blocks:
+        # stochastic depth: the 2 x depth per-sample masks of this pass in three kernels instead of six per block
+        dps = None
+        if self.training and self._x2k_dp_any:
+            keep = self._x2k_dp_keep  # [depth, 1, 1] on the module's device (non-persistent buffer)
+            dps = torch.floor(keep + torch.rand(len(self.blocks), 2, batch_size, device=x.device)) / keep
+        for i, blk in enumerate(self.blocks):
             if all_states is not None:
                 all_states = all_states + (x,)
-            x, attn = blk(x, output_attentions=all_attentions is not None)
+            blk_dps = (dps[i, 0], dps[i, 1]) if (dps is not None and isinstance(blk.drop_path, DropPath)) else None
+            x, attn = blk(x, output_attentions=all_attentions is not None, drop_path_scales=blk_dps)
             if all_attentions is not None:
                 all_attentions.append(attn)
         return x, all_states

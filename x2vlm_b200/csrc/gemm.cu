@@ -1249,7 +1249,12 @@ extern "C" int x2k_gemm(const X2kGemmArgs* args, void* stream_) {
     const int kbt = (a.K + BLOCK_K - 1) / BLOCK_K;
     int s = a.split_k > 1 ? a.split_k : 1;
     if (a.split_k == 0 && units < slots && kbt >= 32) {
-      s = static_cast<int>((2L * slots + units - 1) / units);
+      // Work units are dealt round-robin to the persistent CTAs (pairs), so the launch takes ceil(units * s / slots)
+      // rounds of one slice each: pick the largest s whose units still fit WHOLE rounds (2 by default — the second
+      // round's MMAs hide the first round's atomic epilogue).  Rounding s up instead (17 slices of a 9-tile output on 74
+      // pairs = 153 units) spills a few units into a third round and costs ~30% of the launch.
+      static const int waves = getenv("X2K_GEMM_SPLITK_WAVES") ? atoi(getenv("X2K_GEMM_SPLITK_WAVES")) : 2;
+      s = static_cast<int>((static_cast<long>(waves > 0 ? waves : 2) * slots) / units);
       if (s > kbt / 8) s = kbt / 8;  // keep >= 8 k-blocks per slice
       if (s < 1) s = 1;
     }

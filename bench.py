@@ -138,6 +138,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))  # see X2kDDPAccelerator.set_up
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     C = CONFIGS[args.config]
@@ -690,6 +691,7 @@ def main():
     ap.add_argument("--region-images", type=int, default=None)
     ap.add_argument("--image-only", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=48.0)
+    ap.add_argument("--nccl-max-ctas", type=int, default=8, help="NCCL_MAX_CTAS for the gradient all-reduce (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager comparator (N = 1 leg)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the step graph")

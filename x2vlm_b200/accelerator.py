@@ -418,6 +418,9 @@ class X2kDDPAccelerator:
         and `scheduler.step()` keep working on what set_up returns."""
         torch.cuda.set_device(local_rank)
         model = model.cuda()
+        # The gradient all-reduce moves ~1 GB per step under a ~25 ms backward: a few NCCL CTAs saturate that need, and
+        # every SM NCCL takes is one the persistent GEMMs (one CTA pair per TPC, tiles dealt statically) then wait for.
+        os.environ.setdefault("NCCL_MAX_CTAS", str(self.cfg.get("nccl_max_ctas", 8)))
         if world_size > 1 and not dist.is_initialized():
             addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
             port = int(os.environ.get("MASTER_PORT", 34171))

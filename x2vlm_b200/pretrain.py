@@ -191,10 +191,11 @@ class XVLM(nn.Module):
         return F.normalize(self.vision_proj(image_embeds[:, 0, :]), dim=-1), \
             F.normalize(self.text_proj(text_embeds[:, 0, :]), dim=-1)
 
-    def get_contrastive_loss(self, image_feat, text_feat, idx=None):
+    def get_contrastive_loss(self, image_feat, text_feat, idx=None, gathered=None):
         """models/xvlm.py:794-826.  idx [B] (retrieval fine-tuning): samples with the same id are positives of each
-        other — soft labels = row-normalised id-equality matrix over the gathered batch."""
-        image_feat_all, text_feat_all = allgather(image_feat), allgather(text_feat)
+        other — soft labels = row-normalised id-equality matrix over the gathered batch.  `gathered` = (image_feat_all,
+        text_feat_all) when the caller has already all-gathered the features (one collective for several losses)."""
+        image_feat_all, text_feat_all = gathered if gathered is not None else (allgather(image_feat), allgather(text_feat))
         logits = image_feat_all @ text_feat_all.t() / self.temp
         if idx is None:
             labels = torch.arange(logits.shape[0], device=logits.device)
@@ -349,11 +350,21 @@ class XVLM(nn.Module):
         # ---- ITC + hard negatives ----
         losses = {"image": {}, "region": {}}
         fi_i, ft_i = self.get_features(emb_i, te_i)
-        losses["image"]["loss_itc"] = self.get_contrastive_loss(fi_i, ft_i)
-        ineg_i, tneg_i = neg_idx_i if neg_idx_i is not None else self.get_hard_negatives(fi_i, ft_i)
         if has_r:
             fi_r, ft_r = self.get_features(emb_r, te_r)
-            losses["region"]["loss_itc"] = self.get_contrastive_loss(fi_r, ft_r)
+        # ONE all-gather for the (up to) four ITC feature matrices of the step instead of one per matrix
+        g_i = g_r = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            W = dist.get_world_size()
+            packed = torch.cat([fi_i, ft_i] + ([fi_r, ft_r] if has_r else []), dim=0)
+            allp = allgather(packed).view(W, packed.shape[0], -1)
+            g_i = (allp[:, :Bi].reshape(W * Bi, -1), allp[:, Bi:2 * Bi].reshape(W * Bi, -1))
+            if has_r:
+                g_r = (allp[:, 2 * Bi:2 * Bi + Br].reshape(W * Br, -1), allp[:, 2 * Bi + Br:].reshape(W * Br, -1))
+        losses["image"]["loss_itc"] = self.get_contrastive_loss(fi_i, ft_i, gathered=g_i)
+        ineg_i, tneg_i = neg_idx_i if neg_idx_i is not None else self.get_hard_negatives(fi_i, ft_i)
+        if has_r:
+            losses["region"]["loss_itc"] = self.get_contrastive_loss(fi_r, ft_r, gathered=g_r)
             ineg_r, tneg_r = neg_idx_r if neg_idx_r is not None else self.get_hard_negatives(fi_r, ft_r)
         # ---- one fusion call: [ITM pos | ITM img-neg | ITM txt-neg | MLM] (image) + same (region) + bbox ----
         ar_i = torch.arange(Bi, device=dev)

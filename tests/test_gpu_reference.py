@@ -373,3 +373,44 @@ def test_per_query_cross_attention_mask(models):
     finally:
         ours.zero_grad(set_to_none=True)
         ours.eval()
+
+
+def test_gradients_vs_reference_at_batch16(models):
+    """Backward parity through the unmodified caller: d(loss_itc + loss_mlm + bbox losses)/d(parameters) of the x2k path
+    against the reference in fp32, with the reference's own bf16-autocast backward as the yardstick (same criterion as the
+    forward outputs: ours may not be further from fp32 than the reference's mixed-precision path).  Eval mode (no dropout),
+    image + region iteration, 16 + 16 pairs."""
+    ref, ours = models
+    ib = _dev(synth.image_text_batch(16, 40, seed=17))
+    rb = _dev(synth.region_batch(6, 16, 40, seed=18))
+    names = ["vision_encoder.blocks.0.attn.qkv.weight", "vision_encoder.blocks.5.attn.relative_position_bias_table",
+             "vision_encoder.blocks.11.mlp.fc2.weight", "vision_encoder.blocks.3.gamma_1", "vision_encoder.fc_norm.weight",
+             "text_encoder.bert.embeddings.word_embeddings.weight", "text_encoder.bert.embeddings.position_embeddings.weight",
+             "text_encoder.bert.encoder.layer.5.intermediate.dense.weight", "text_encoder.bert.encoder.layer.5.attention.self.query.bias",
+             "text_encoder.bert.encoder.layer.12.crossattention.self.key.weight", "text_encoder.bert.encoder.layer.17.output.LayerNorm.weight",
+             "text_encoder.cls.predictions.transform.dense.weight", "vision_proj.weight", "bbox_head.0.weight"]
+
+    def grads(m, autocast=False):
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            li = m(ib["image"], ib["text_ids"], ib["text_atts"], text_ids_masked=ib["text_ids_masked"], masked_pos=ib["masked_pos"],
+                   masked_ids=ib["masked_ids"], ret_match_loss=False)
+            lr = m(rb["image"], rb["text_ids"], rb["text_atts"], text_ids_masked=rb["text_ids_masked"], masked_pos=rb["masked_pos"],
+                   masked_ids=rb["masked_ids"], image_atts=rb["image_atts"], idx_to_group_img=rb["idx_to_group_img"],
+                   target_bbox=rb["target_bbox"], is_image=rb["is_image"], ret_bbox_loss=True, ret_match_loss=False)
+            loss = li["loss_itc"] + li["loss_mlm"] + lr["loss_itc"] + lr["loss_mlm"] + lr["loss_bbox"] + lr["loss_giou"]
+        loss.backward()
+        p = dict(m.named_parameters())
+        out = {n: p[n].grad.detach().float().clone() for n in names}
+        m.zero_grad(set_to_none=True)
+        return out
+
+    want, auto, got = grads(ref), grads(ref, True), grads(ours)
+    rows = {n: {"ours_vs_fp32": _rel(got[n], want[n]), "ref_bf16_autocast_vs_fp32": _rel(auto[n], want[n])} for n in names}
+    with open(os.path.join(ROOT, "gpurun_out", "parity_gradients_vs_reference_b16.json"), "w") as fh:
+        json.dump(rows, fh, indent=1)
+    print("\n%-70s %10s %12s" % ("gradient", "ours/fp32", "ref-bf16/fp32"))
+    for n, r in rows.items():
+        print("%-70s %10.3e %12.3e" % (n, r["ours_vs_fp32"], r["ref_bf16_autocast_vs_fp32"]))
+    bad = [n for n, r in rows.items() if r["ours_vs_fp32"] > max(RATIO * r["ref_bf16_autocast_vs_fp32"], 5e-3)]
+    assert not bad, {n: rows[n] for n in bad}

@@ -393,3 +393,26 @@ def test_set_up_takes_over_reference_optimizer_and_scheduler(xvlm):
     # anything that is not AdamW is rejected loudly
     with pytest.raises(TypeError):
         FlatAdamW.from_optimizer(m, arena, torch.optim.SGD(m.parameters(), lr=0.1))
+
+
+def test_arena_gapped_beit_bias(xvlm):
+    """BEiT's QKV bias [q_bias | 0 | v_bias] (models/beit2.py:129) is a plain view of the arena: the two parameters are laid
+    out with a zero hole of one bias length between them, gradients land in their own slices."""
+    import copy
+    from x2vlm_b200.params import GappedBias, ParamArena
+    blk = copy.deepcopy(xvlm.vision_encoder.blocks[2])
+    with torch.no_grad():
+        blk.attn.q_bias.copy_(torch.arange(768.0))
+        blk.attn.v_bias.copy_(-torch.arange(768.0))
+    arena = ParamArena(blk)
+    g = blk._x2k["bqv"]
+    assert isinstance(g, GappedBias) and g.arena is arena
+    packed = g.get_f32()
+    assert packed.shape == (3 * 768,)
+    assert torch.equal(packed[:768], blk.attn.q_bias) and torch.equal(packed[1536:], blk.attn.v_bias)
+    assert float(packed[768:1536].abs().sum()) == 0.0
+    gq, gv = g.grad_views()
+    assert gq.data_ptr() == blk.attn.q_bias.grad.data_ptr() and gv.data_ptr() == blk.attn.v_bias.grad.data_ptr()
+    sq, eq = arena.span(blk.attn.q_bias)
+    sv, ev = arena.span(blk.attn.v_bias)
+    assert sv == eq + 768 and sq % 8 == 0

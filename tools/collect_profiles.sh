@@ -23,7 +23,12 @@ cap() {  # name, kernel regex, skip, python script, [env]
 X2K_CASE="fc1 fwd bias+gelu+gelu'" cap gemm_fc1_gelu gemm_tcgen05 6 tools/profile_gemm.py
 X2K_CASE="plain fwd bf16" cap gemm_plain_bf16 gemm_tcgen05 6 tools/profile_gemm.py
 X2K_CASE="o-proj bias+drop+res+f32" cap gemm_oproj_drop_res gemm_tcgen05 6 tools/profile_gemm.py
+X2K_ATTN_CASE=beit577 cap attn_long_fwd_577 attn_long_fwd 2 tools/profile_attn.py
+X2K_ATTN_CASE=beit577 cap attn_long_bwd_577 attn_long_bwd 2 tools/profile_attn.py
 X2K_ATTN_CASE=beit cap attn_bwd_beit attn_bwd_kernel 2 tools/profile_attn.py
 X2K_ATTN_CASE=cross cap attn_bwd_cross attn_pack_bwd 2 tools/profile_attn.py
 X2K_ATTN_CASE=cross cap attn_fwd_cross attn_pack_fwd 2 tools/profile_attn.py
+cap layernorm_bwd_dropcast "layernorm_bwd_kernel.*6.*1" 4 "bench.py --profile --steps 1 --warmup 3"
+python tools/profile_attn.py > $O/${TAG}_attn_shapes.txt 2>&1
+python tools/epilogue_ab.py > $O/${TAG}_gemm_epilogue_ab.txt 2>&1
 ls -la $O | grep ${TAG}_

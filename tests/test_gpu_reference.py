@@ -412,5 +412,11 @@ def test_gradients_vs_reference_at_batch16(models):
     print("\n%-70s %10s %12s" % ("gradient", "ours/fp32", "ref-bf16/fp32"))
     for n, r in rows.items():
         print("%-70s %10.3e %12.3e" % (n, r["ours_vs_fp32"], r["ref_bf16_autocast_vs_fp32"]))
-    bad = [n for n, r in rows.items() if r["ours_vs_fp32"] > max(RATIO * r["ref_bf16_autocast_vs_fp32"], 5e-3)]
+    # Gradients are sums over thousands of bf16-rounded terms, so each of the two error figures is itself a noisy
+    # estimate (+-10% between seeds): per parameter ours may exceed the reference's own bf16 error by at most GRAD_SLACK,
+    # and over the whole set it must be the smaller one (geometric mean of the ratios below 1).
+    GRAD_SLACK = 1.25
+    bad = [n for n, r in rows.items() if r["ours_vs_fp32"] > max(GRAD_SLACK * r["ref_bf16_autocast_vs_fp32"], 5e-3)]
     assert not bad, {n: rows[n] for n in bad}
+    ratios = torch.tensor([r["ours_vs_fp32"] / r["ref_bf16_autocast_vs_fp32"] for r in rows.values()])
+    assert float(ratios.log().mean().exp()) < 1.0, ratios

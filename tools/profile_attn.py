@@ -29,7 +29,7 @@ def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps
     o = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, Lq, device=dev)
     do = torch.randn(B * Lq, D, device=dev).bfloat16()
     dq = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16); dkv = torch.empty((n_kv if grouped else B) * Lk, 2 * D, device=dev, dtype=torch.bfloat16)
-    ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if bias else None
+    ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if bias and not os.environ.get("X2K_ATTN_NO_DS") else None
     kw = dict(kv_index=idx, n_kv=n_kv, kv_groups=groups, bias=b, mask=m, dropout_p=p, dropout_seed=1, dropout_offset=0)
     for _ in range(reps):
         ops.attn_fwd(qv, kk, vv, B, H, Lq, Lk, 0.125, o, lse, **kw)

@@ -211,251 +211,432 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // backward: grid (H, B), 256 threads, 1 CTA / SM (TMEM 512 columns)
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_SQ = 0, BWD_SDO = 32768, BWD_SK = 65536, BWD_SV = 81920, BWD_SP = 98304, BWD_SDS = 131072;
-constexpr int BWD_STAGE = 163840;              // bias staging, 8 warps x 4 KB
+// Optional phase trace (compile with -DX2K_ATTN_TRACE): clock64 stamps of one CTA, read back by x2k_debug_attn_trace.
+#ifdef X2K_ATTN_TRACE
+__device__ long long g_attn_trace[2][64];
+#define AT_TRACE(i)                                                                           \
+  do {                                                                                        \
+    if (blockIdx.x == 5 && blockIdx.y == 40 && (threadIdx.x == 0 || threadIdx.x == 200))      \
+      g_attn_trace[threadIdx.x ? 1 : 0][(i)] = clock64();                                     \
+  } while (0)
+#else
+#define AT_TRACE(i) do {} while (0)
+#endif
+constexpr int BWD_SQ = 0, BWD_SDO = 32768, BWD_SK = 65536, BWD_SV = 98304, BWD_SP = 131072, BWD_SDS = 163840;
+constexpr int BWD_STAGE = 196608;  // bias staging, 8 warps x 4 KB
 constexpr int BWD_BARS = BWD_STAGE + 32768;
-constexpr int BWD_SMEM = BWD_BARS + 1024 + 128;
+constexpr int BWD_SMEM = BWD_BARS + 128 + 1024;
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
+// Descriptor = constant fields | (shared address >> 4): the issuing thread adds small address deltas instead of
+// rebuilding the 64-bit word for every MMA (the single issuing thread is on the critical path of every tile).
+__device__ __forceinline__ uint64_t desc_at(uint64_t fields, uint32_t addr) {
+  return fields | static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+}
+
+// geometry of (key block, query block) tile t as seen by one warp
+struct BwdTile {
+  int kb, qb, nkc, u_begin, u_end, q_warp0;
+  bool warp_live;
+  const float* bias_blk;  // first bias element of the warp's 32 rows at the key block's first column, or nullptr
+};
+__device__ __forceinline__ BwdTile bwd_tile(const AttnParams& p, int t, int nqb, int quad, int half, int h) {
+  BwdTile g;
+  g.kb = nqb == 2 ? (t >> 1) : t;
+  g.qb = nqb == 2 ? (t & 1) : 0;
+  g.nkc = (min(p.Lk - g.kb * 128, 128) + 15) >> 4;  // valid keys of the block in 16-column chunks
+  const int nunit = (g.nkc + 1) >> 1;               // 32-column units, split between the two halves
+  g.u_begin = half == 0 ? 0 : (nunit + 1) >> 1;
+  g.u_end = half == 0 ? (nunit + 1) >> 1 : nunit;
+  g.q_warp0 = g.qb * 128 + quad * 32;
+  // a warp whose rows all lie beyond Lq has nothing to produce (its P/dS rows only feed dQ rows never stored)
+  g.warp_live = g.q_warp0 < p.Lq;
+  g.bias_blk = (p.bias && g.warp_live)
+                   ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(g.q_warp0) * p.bias_q_stride + g.kb * 128
+                   : nullptr;
+  return g;
+}
+
+// Bias block [32 rows x 32 cols] fp32 of one warp in two steps, so the L2 latency of the loads hides behind an MMA wait
+// or the previous unit's math: issue (8 coalesced LDG.128 per lane, 4 rows x 128 B per instruction) ... commit (transpose
+// through the warp's 4 KB XOR-swizzled staging tile: every thread ends up with the 32 values of ITS row).
+__device__ __forceinline__ void bias_issue(const float* __restrict__ base, int64_t row_stride, int rows_left, int lane,
+                                           float4 (&v)[8]) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const int rc = r < rows_left ? r : (rows_left - 1);
+    v[i] = __ldg(reinterpret_cast<const float4*>(base + rc * row_stride) + ch);
+  }
+}
+__device__ __forceinline__ void bias_commit(const float4 (&v)[8], uint32_t stage_addr, int lane, float (&out)[32]) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr + r * 128 + ((ch ^ (r & 7)) << 4)), "f"(v[i].x),
+                 "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                 : "r"(stage_addr + lane * 128 + ((c ^ (lane & 7)) << 4))
+                 : "memory");
+    out[4 * c] = w.x; out[4 * c + 1] = w.y; out[4 * c + 2] = w.z; out[4 * c + 3] = w.w;
+  }
+  __syncwarp();
+}
+
+// TMEM row (this thread's lane) -> 32 fp32 columns -> scaled bf16 -> the thread's row of a 128B-swizzled [128 x 64]
+// staging tile (columns col0 .. col0+31), from where one TMA store writes the tile (rows past the sequence are clipped).
+__device__ __forceinline__ void stage_row32(uint32_t tile_addr, int row, int col0, uint32_t tcol_addr, float mul) {
+  uint32_t a[16], c[16];
+  tmem_ld_32x16(tcol_addr, a);
+  tmem_ld_32x16(tcol_addr + 16, c);
+  tmem_wait_ld();
+  st_shared_v4(tile_addr + swz_off(row, col0), pack_bf16x2(__uint_as_float(a[0]) * mul, __uint_as_float(a[1]) * mul),
+               pack_bf16x2(__uint_as_float(a[2]) * mul, __uint_as_float(a[3]) * mul),
+               pack_bf16x2(__uint_as_float(a[4]) * mul, __uint_as_float(a[5]) * mul),
+               pack_bf16x2(__uint_as_float(a[6]) * mul, __uint_as_float(a[7]) * mul));
+  st_shared_v4(tile_addr + swz_off(row, col0 + 8), pack_bf16x2(__uint_as_float(a[8]) * mul, __uint_as_float(a[9]) * mul),
+               pack_bf16x2(__uint_as_float(a[10]) * mul, __uint_as_float(a[11]) * mul),
+               pack_bf16x2(__uint_as_float(a[12]) * mul, __uint_as_float(a[13]) * mul),
+               pack_bf16x2(__uint_as_float(a[14]) * mul, __uint_as_float(a[15]) * mul));
+  st_shared_v4(tile_addr + swz_off(row, col0 + 16), pack_bf16x2(__uint_as_float(c[0]) * mul, __uint_as_float(c[1]) * mul),
+               pack_bf16x2(__uint_as_float(c[2]) * mul, __uint_as_float(c[3]) * mul),
+               pack_bf16x2(__uint_as_float(c[4]) * mul, __uint_as_float(c[5]) * mul),
+               pack_bf16x2(__uint_as_float(c[6]) * mul, __uint_as_float(c[7]) * mul));
+  st_shared_v4(tile_addr + swz_off(row, col0 + 24), pack_bf16x2(__uint_as_float(c[8]) * mul, __uint_as_float(c[9]) * mul),
+               pack_bf16x2(__uint_as_float(c[10]) * mul, __uint_as_float(c[11]) * mul),
+               pack_bf16x2(__uint_as_float(c[12]) * mul, __uint_as_float(c[13]) * mul),
+               pack_bf16x2(__uint_as_float(c[14]) * mul, __uint_as_float(c[15]) * mul));
+}
+
+// delta = rowsum(dO ∘ O) of one query row and head, when no pre-kernel supplied it
+__device__ __forceinline__ float row_delta(const AttnParams& p, int b, int q, int h) {
+  const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64);
+  const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_do + h * 64);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+    acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
+           bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
+           bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+  }
+  return acc;
+}
+
+// Schedule of one CTA = one (b, h), up to 2 x 2 tiles of 128 queries x 128 keys, key block outer:
+//   * every operand tile (Q, dO of both query blocks, K, V of both key blocks) is TMA-loaded once, up front;
+//   * per tile: S = Q·Kᵀ and dP = dO·Vᵀ (tensor pipe) -> P / dS pass (all threads; the first bias block of the tile was
+//     requested before the wait) -> dS leaves by TMA store straight from the UMMA operand tile (rel-pos bias gradient)
+//     -> dQ += dS·K, dK += dSᵀ·Q, dV += Pᵀ·dO, and the NEXT tile's S / dP are issued right behind them;
+//   * dK / dV of a key block and dQ at the end are staged as bf16 tiles in the (then idle) P / dS buffers and written
+//     by TMA stores (3-D maps clip the rows past the sequence); the drain of a key block overlaps the next S / dP;
+//   * a tcgen05.commit issued AFTER the bulk stores have read their staging tiles is the gate that lets the next
+//     pass overwrite them — no extra CTA barrier.
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
+                const __grid_constant__ CUtensorMap tmap_dv, const __grid_constant__ CUtensorMap tmap_ds, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + BWD_BARS);
-  uint64_t* bar_kv = bar_q + 1;
-  uint64_t* bar_mma = bar_q + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 3);
+  AT_TRACE(0);
+  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + BWD_BARS);  // [0] Q0 dO0 K0 V0, [1] Q1 dO1, [2] K1 V1
+  uint64_t* bar_s = bar_ld + 3;                                     // S / dP of a tile are in TMEM
+  uint64_t* bar_acc = bar_ld + 4;                                   // dK / dV of a key block (and finally dQ) are complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_ld + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The MMA / TMA issue code runs warp-converged in warp 0 (index taken through a shuffle so that the compiler can prove
+  // it uniform) with only the instruction itself under elect.sync: descriptors then live in uniform registers.  Issued
+  // from a divergent `threadIdx.x == 0` branch every tcgen05.mma costs ~91 cycles (R2UR moves) whatever its shape;
+  // this way an N = 64 MMA costs 58 and an N = 128 one 67 (tools/mma_bench.cu).
+  const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
   const int h = blockIdx.x, b = blockIdx.y;
   const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int nqb = (p.Lq + 127) >> 7, nkb = (p.Lk + 127) >> 7;
+  const int ntile = nqb * nkb;
+  const uint32_t sbase = smem_u32(smem);
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_mma, 1);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(bar_ld + i, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(bar_ld, 4 * 16384);
+    tma_load_2d(smem + BWD_SQ, &tmap_q, bar_ld, h * 64, b * p.Lq);
+    tma_load_2d(smem + BWD_SK, &tmap_k, bar_ld, h * 64, kvb * p.Lk);
+    tma_load_2d(smem + BWD_SDO, &tmap_do, bar_ld, h * 64, b * p.Lq);
+    tma_load_2d(smem + BWD_SV, &tmap_v, bar_ld, h * 64, kvb * p.Lk);
+    if (nqb > 1) {
+      mbar_arrive_expect_tx(bar_ld + 1, 2 * 16384);
+      tma_load_2d(smem + BWD_SQ + 16384, &tmap_q, bar_ld + 1, h * 64, b * p.Lq + 128);
+      tma_load_2d(smem + BWD_SDO + 16384, &tmap_do, bar_ld + 1, h * 64, b * p.Lq + 128);
+    }
+    if (nkb > 1) {
+      mbar_arrive_expect_tx(bar_ld + 2, 2 * 16384);
+      tma_load_2d(smem + BWD_SK + 16384, &tmap_k, bar_ld + 2, h * 64, kvb * p.Lk + 128);
+      tma_load_2d(smem + BWD_SV + 16384, &tmap_v, bar_ld + 2, h * 64, kvb * p.Lk + 128);
+    }
   }
+  __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
+
+  // per-row statistics of both query blocks while the tiles fly in: lse (log2 domain) and delta = rowsum(dO ∘ O)
+  const int64_t stat0 = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
+  float lse_0 = 0.f, lse_1 = 0.f, dl_0 = 0.f, dl_1 = 0.f;
+  if (row < p.Lq) {
+    lse_0 = p.lse[stat0 + row];
+    dl_0 = p.delta ? __ldg(p.delta + stat0 + row) : row_delta(p, b, row, h);
+  }
+  if (128 + row < p.Lq) {
+    lse_1 = p.lse[stat0 + 128 + row];
+    dl_1 = p.delta ? __ldg(p.delta + stat0 + 128 + row) : row_delta(p, b, 128 + row, h);
+  }
+
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  const uint32_t sbase = smem_u32(smem);
   const uint32_t stage_addr = sbase + BWD_STAGE + warp * 4096;
-
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_q, nqb * 2 * 16384);
-    for (int qb = 0; qb < nqb; ++qb) {
-      tma_load_2d(smem + BWD_SQ + qb * 16384, &tmap_q, bar_q, h * 64, b * p.Lq + qb * 128);
-      tma_load_2d(smem + BWD_SDO + qb * 16384, &tmap_do, bar_q, h * 64, b * p.Lq + qb * 128);
-    }
-  }
-
-  // per-row statistics (both halves of a row compute them): lse (log2 domain) and delta = rowsum(dO ∘ O)
-  float lse2[2] = {0.f, 0.f}, delta[2] = {0.f, 0.f};
-  for (int qb = 0; qb < nqb; ++qb) {
-    const int q = qb * 128 + row;
-    if (q < p.Lq) {
-      lse2[qb] = p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q];
-      if (p.delta) {
-        delta[qb] = __ldg(p.delta + (static_cast<int64_t>(b) * p.H + h) * p.Lq + q);
-        continue;
-      }
-      const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_o + h * 64);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_do + h * 64);
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 a = __ldg(po + i), d = __ldg(pd + i);
-        acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) +
-               bf16_hi(a.y) * bf16_hi(d.y) + bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) +
-               bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
-      }
-      delta[qb] = acc;
-    }
-  }
+  AT_TRACE(1);
 
   const DropCfg dc = make_drop(p.dropout_p);
   const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
-  uint32_t mma_phase = 0;
   const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
+  const uint64_t f_k = make_smem_desc(0, 16, 1024);       // K-major operand
+  const uint64_t f_mn = make_smem_desc(0, 8192, 1024);    // MN-major [k rows][64] operand (Q, dO, K as B)
+  const uint64_t f_mnp = make_smem_desc(0, 16384, 1024);  // MN-major P / dS as A: 64-key chunks are 16 KB apart
+  uint32_t s_phase = 0, acc_phase = 0;
 
-  for (int kb = 0; kb < nkb; ++kb) {
-    // valid keys of this block in 16-column chunks: S/dP are only formed (N = nkc*16) and consumed up to there
-    const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
-    const int nunit = (nkc + 1) >> 1;  // 32-column units, split between the two halves
-    const int u_begin = half == 0 ? 0 : (nunit + 1) >> 1;
-    const int u_end = half == 0 ? (nunit + 1) >> 1 : nunit;
-    const uint32_t idesc_skb = make_idesc_bf16(128, nkc * 16, 0, 0);
-    if (threadIdx.x == 0) {
-      mbar_arrive_expect_tx(bar_kv, 2 * 16384);
-      tma_load_2d(smem + BWD_SK, &tmap_k, bar_kv, h * 64, kvb * p.Lk + kb * 128);
-      tma_load_2d(smem + BWD_SV, &tmap_v, bar_kv, h * 64, kvb * p.Lk + kb * 128);
-    }
-    for (int qb = 0; qb < nqb; ++qb) {
-      if (threadIdx.x == 0) {
-        if (qb == 0) mbar_wait(bar_kv, kb & 1);
-        if (kb == 0 && qb == 0) mbar_wait(bar_q, 0);
-        tc_fence_after();
-        const uint32_t aq = sbase + BWD_SQ + qb * 16384, ado = sbase + BWD_SDO + qb * 16384;
-        const uint32_t ak = sbase + BWD_SK, av = sbase + BWD_SV;
+  // S = Q[qb]·K[kb]ᵀ and dP = dO[qb]·V[kb]ᵀ, N = the block's valid keys rounded up to 16 (issuer warp, converged)
+  auto issue_scores = [&](int kb, int qb, int nkc) {
+    const uint32_t idesc = make_idesc_bf16(128, nkc * 16, 0, 0);
+    const uint64_t dq_ = desc_at(f_k, sbase + BWD_SQ + qb * 16384), dk_ = desc_at(f_k, sbase + BWD_SK + kb * 16384);
+    const uint64_t ddo = desc_at(f_k, sbase + BWD_SDO + qb * 16384), dv_ = desc_at(f_k, sbase + BWD_SV + kb * 16384);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + TM_S, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_skb,
-                    k != 0);
+    for (int k = 0; k < 4; ++k)
+      if (elect_one()) umma_bf16(tmem + TM_S, dq_ + 2 * k, dk_ + 2 * k, idesc, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + TM_DP, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024),
-                    idesc_skb, k != 0);
-        umma_commit(bar_mma);
-      }
-      __syncwarp();
-      mbar_wait_warp(bar_mma, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
+    for (int k = 0; k < 4; ++k)
+      if (elect_one()) umma_bf16(tmem + TM_DP, ddo + 2 * k, dv_ + 2 * k, idesc, k != 0);
+  };
 
-      // ---- P and dS for this (q block, key block) tile; thread == query row, half == column range ----
-      const int q = qb * 128 + row;
-      const bool qvalid = q < p.Lq;
-      const int q_warp0 = qb * 128 + quad * 32;
-      // a warp whose rows all lie beyond Lq has nothing to produce (its P/dS rows only feed dQ rows never stored)
-      const bool warp_live = q_warp0 < p.Lq;
-      const float* bias_blk = (p.bias && warp_live) ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(q_warp0) * p.bias_q_stride : nullptr;
-      const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
-      const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad;
-      __nv_bfloat16* ds_row =
-          (p.ds_out && qvalid) ? p.ds_out + b * p.ds_b_stride + h * p.ds_h_stride + q * p.ds_q_stride : nullptr;
-      const float my_lse = lse2[qb], my_delta = delta[qb];
-      if (warp_live) {
+  BwdTile g = bwd_tile(p, 0, nqb, quad, half, h);
+  float4 bv[8];
+  if (g.bias_blk && g.u_begin < g.u_end) bias_issue(g.bias_blk + g.u_begin * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
+  if (issuer_warp) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    AT_TRACE(3);
+    issue_scores(0, 0, g.nkc);
+    if (elect_one()) umma_commit(bar_s);
+    __syncwarp();
+  }
+  AT_TRACE(2);
+
+  for (int t = 0; t < ntile; ++t) {
+    const int kb = g.kb, qb = g.qb, nkc = g.nkc;
+    mbar_wait_spin_warp(bar_s, s_phase);
+    s_phase ^= 1;
+    tc_fence_after();
+    AT_TRACE(4 + t * 6);
+
+    // ---- P and dS for this (q block, key block) tile; thread == query row, half == column range ----
+    const int q = qb * 128 + row;
+    const bool qvalid = q < p.Lq;
+    const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
+    const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad;
+    const float my_lse = qb ? lse_1 : lse_0, my_delta = qb ? dl_1 : dl_0;
+    if (g.warp_live) {
 #pragma unroll 1
-        for (int u = u_begin; u < u_end; ++u) {
-          const bool two = (2 * u + 1) < nkc;
-          uint32_t s[2][16], dp[2][16];
-          tmem_ld_32x16(trow + TM_S + u * 32, s[0]);
-          tmem_ld_32x16(trow + TM_DP + u * 32, dp[0]);
-          if (two) {
-            tmem_ld_32x16(trow + TM_S + u * 32 + 16, s[1]);
-            tmem_ld_32x16(trow + TM_DP + u * 32 + 16, dp[1]);
+      for (int u = g.u_begin; u < g.u_end; ++u) {
+        float add[32];
+        if (g.bias_blk) {
+          bias_commit(bv, stage_addr, lane, add);
+          if (u + 1 < g.u_end) bias_issue(g.bias_blk + (u + 1) * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) add[j] = 0.f;
+        }
+        if (mask_row) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + kb * 128 + u * 32 + j));
+            add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
           }
-          float add[32];
-          additive32(p, bias_blk, p.Lq - q_warp0, mask_row, kb * 128 + u * 32, stage_addr, lane, add);
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int c = 2 * u + v;
+          if (c >= nkc) break;  // warp-uniform
+          const int k0 = kb * 128 + c * 16;
+          uint32_t s[16], dp[16];
+          tmem_ld_32x16(trow + TM_S + c * 16, s);
+          tmem_ld_32x16(trow + TM_DP + c * 16, dp);
           tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
+          float pr[16], ds[16];
+          if (qvalid) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            if (v == 1 && !two) continue;  // warp-uniform
-            const int c = 2 * u + v;
-            const int k0 = kb * 128 + c * 16;
-            float pr[16], ds[16];
-            if (qvalid) {
+            for (int j = 0; j < 16; ++j) {
+              const float tt = fmaf(__uint_as_float(s[j]), p.scale_log2, add[16 * v + j] * kLog2e);
+              pr[j] = (k0 + j < p.Lk) ? fast_exp2(tt - my_lse) : 0.f;
+              ds[j] = __uint_as_float(dp[j]);
+            }
+            if (p.dropout_p > 0.f) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float t = fmaf(__uint_as_float(s[v][j]), p.scale_log2, add[16 * v + j]);
-                pr[j] = (k0 + j < p.Lk) ? fast_exp2(t - my_lse) : 0.f;
-                ds[j] = __uint_as_float(dp[v][j]);
-              }
-              if (p.dropout_p > 0.f) {
+              for (int j = 0; j < 16; j += 8) {
+                float k[8];
+                drop8(p.seed, doff, (drop_base + k0 + j) >> 3, dc, k);
 #pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                  float k[8];
-                  drop8(p.seed, doff, (drop_base + k0 + j) >> 3, dc, k);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    // dS uses the un-dropped P; the P that feeds dV is the dropped one
-                    const float pu = pr[j + i];
-                    ds[j + i] = pu * (ds[j + i] * k[i] - my_delta);
-                    pr[j + i] = pu * k[i];
-                  }
+                for (int i = 0; i < 8; ++i) {
+                  // dS uses the un-dropped P; the P that feeds dV is the dropped one
+                  const float pu = pr[j + i];
+                  ds[j + i] = pu * (ds[j + i] * k[i] - my_delta);
+                  pr[j + i] = pu * k[i];
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
+              for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
             }
-            uint32_t pk[8], dk[8];
+          } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              pk[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
-              dk[j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
-            }
-            const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
-            st_shared_v4(sbase + BWD_SP + o0, pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(sbase + BWD_SP + o1, pk[4], pk[5], pk[6], pk[7]);
-            st_shared_v4(sbase + BWD_SDS + o0, dk[0], dk[1], dk[2], dk[3]);
-            st_shared_v4(sbase + BWD_SDS + o1, dk[4], dk[5], dk[6], dk[7]);
-            if (ds_row) {
-              *reinterpret_cast<uint4*>(ds_row + k0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-              *reinterpret_cast<uint4*>(ds_row + k0 + 8) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
-            }
+            for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
           }
+          const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
+          st_shared_v4(sbase + BWD_SP + o0, pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]),
+                       pack_bf16x2(pr[6], pr[7]));
+          st_shared_v4(sbase + BWD_SP + o1, pack_bf16x2(pr[8], pr[9]), pack_bf16x2(pr[10], pr[11]),
+                       pack_bf16x2(pr[12], pr[13]), pack_bf16x2(pr[14], pr[15]));
+          st_shared_v4(sbase + BWD_SDS + o0, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                       pack_bf16x2(ds[6], ds[7]));
+          st_shared_v4(sbase + BWD_SDS + o1, pack_bf16x2(ds[8], ds[9]), pack_bf16x2(ds[10], ds[11]),
+                       pack_bf16x2(ds[12], ds[13]), pack_bf16x2(ds[14], ds[15]));
         }
       }
+    }
+    AT_TRACE(5 + t * 6);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    AT_TRACE(6 + t * 6);
+
+    const bool kb_end = qb == nqb - 1;
+    const bool last = t == ntile - 1;
+    BwdTile gn = g;
+    if (!last) gn = bwd_tile(p, t + 1, nqb, quad, half, h);
+    // the next tile's first bias block is requested now and consumed after the wait for its S / dP (the issuer warp
+    // first gets the tensor pipe going)
+    if (!last && !issuer_warp && gn.bias_blk && gn.u_begin < gn.u_end)
+      bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
+
+    if (issuer_warp) {
+      const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
+      if (p.ds_out) {  // dS tile -> ds_out[b, h, q block, key block] (columns past pad16(Lk) and rows past Lq are clipped)
+        for (int blk = 0; blk * 4 < nkc; ++blk)
+          if (elect_one()) tma_store_4d(&tmap_ds, ads + blk * 16384, kb * 128 + blk * 64, qb * 128, h, b);
+        if (elect_one()) tma_store_commit();
+      }
+      AT_TRACE(46 + (t & 1) * 4);
+      const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
+      // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
+      {
+        const uint64_t db0 = desc_at(f_mn, sbase + BWD_SK + kb * 16384);
+        for (int ks = 0; ks < nkc; ++ks) {
+          const uint64_t da = desc_at(f_k, ads + (ks >> 2) * 16384 + (ks & 3) * 32);
+          if (elect_one()) umma_bf16(tmem + TM_DQ + qb * 64, da, db0 + ks * 128, idesc_dq, (kb | ks) != 0);
+        }
+      }
+      // dK += dSᵀ · Q[qb], dV += Pᵀ · dO[qb]   (A: dS / P MN-major over keys, K = query rows; B: Q / dO MN-major)
+      {
+        const uint64_t da0 = desc_at(f_mnp, ads), db0 = desc_at(f_mn, sbase + BWD_SQ + qb * 16384);
+        for (int ks = 0; ks < nqc; ++ks)
+          if (elect_one()) umma_bf16(tmem + TM_DK, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
+      }
+      {
+        const uint64_t da0 = desc_at(f_mnp, ap), db0 = desc_at(f_mn, sbase + BWD_SDO + qb * 16384);
+        for (int ks = 0; ks < nqc; ++ks)
+          if (elect_one()) umma_bf16(tmem + TM_DV, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
+      }
+      AT_TRACE(47 + (t & 1) * 4);
+      if (kb_end && elect_one()) {
+        if (last && p.ds_out) tma_store_wait_read();  // the dQ staging below reuses the dS tile
+        umma_commit(bar_acc);
+      }
+      if (!last) {
+        if (gn.qb == 1 && gn.kb == 0) mbar_wait(bar_ld + 1, 0);
+        if (gn.kb == 1 && gn.qb == 0) mbar_wait(bar_ld + 2, 0);
+        tc_fence_after();
+        issue_scores(gn.kb, gn.qb, gn.nkc);
+        AT_TRACE(48 + (t & 1) * 4);
+        if (!kb_end && elect_one()) {
+          if (p.ds_out) tma_store_wait_read();  // the next pass overwrites the dS tile
+          umma_commit(bar_s);
+        }
+      }
+      __syncwarp();
+      if (!last && gn.bias_blk && gn.u_begin < gn.u_end)
+        bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
+    }
+    AT_TRACE(7 + t * 6);
+
+    if (kb_end) {
+      // ---- dK / dV of this key block (and, after the last tile, dQ) -> bf16 staging tiles -> TMA stores ----
+      mbar_wait_spin_warp(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      AT_TRACE(40 + kb * 3);
+      stage_row32(sbase + BWD_SP, row, half * 32, trow + TM_DK + half * 32, p.scale);
+      stage_row32(sbase + BWD_SP + 16384, row, half * 32, trow + TM_DV + half * 32, 1.0f);
+      if (last) {
+        for (int i = 0; i < nqb; ++i)
+          stage_row32(sbase + BWD_SDS + i * 16384, row, half * 32, trow + TM_DQ + i * 64 + half * 32, p.scale);
+      }
+      AT_TRACE(41 + kb * 3);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-
-      if (threadIdx.x == 0) {
-        const uint32_t aq = sbase + BWD_SQ + qb * 16384, ado = sbase + BWD_SDO + qb * 16384;
-        const uint32_t ak = sbase + BWD_SK;
-        const uint32_t ap = sbase + BWD_SP, ads = sbase + BWD_SDS;
-        const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
-        // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
-        for (int ks = 0; ks < nkc; ++ks)
-          umma_bf16(tmem + TM_DQ + qb * 64, make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                    make_smem_desc(ak + ks * 2048, 8192, 1024), idesc_dq, (kb | ks) != 0);
-        // dK += dSᵀ · Q[qb]         (A: dS MN-major over keys, K = query rows; B: Q tile MN-major)
-        for (int ks = 0; ks < nqc; ++ks)
-          umma_bf16(tmem + TM_DK, make_smem_desc(ads + ks * 2048, 16384, 1024), make_smem_desc(aq + ks * 2048, 8192, 1024),
-                    idesc_dkv, (qb | ks) != 0);
-        // dV += Pᵀ · dO[qb]
-        for (int ks = 0; ks < nqc; ++ks)
-          umma_bf16(tmem + TM_DV, make_smem_desc(ap + ks * 2048, 16384, 1024), make_smem_desc(ado + ks * 2048, 8192, 1024),
-                    idesc_dkv, (qb | ks) != 0);
-        if (qb == nqb - 1) umma_commit(bar_mma);
+      if (issuer_warp) {
+        if (elect_one()) {
+          tma_store_3d(&tmap_dk, sbase + BWD_SP, h * 64, kb * 128, b);
+          tma_store_3d(&tmap_dv, sbase + BWD_SP + 16384, h * 64, kb * 128, b);
+          if (last)
+            for (int i = 0; i < nqb; ++i) tma_store_3d(&tmap_dq, sbase + BWD_SDS + i * 16384, h * 64, i * 128, b);
+          tma_store_commit();
+          tma_store_wait_read();  // staging tiles (and, at the end, shared memory as a whole) are free again
+          if (!last) umma_commit(bar_s);  // gate of the next pass: its S / dP were issued before the drain
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      AT_TRACE(42 + kb * 3);
     }
-    // ---- drain dK / dV of this key block; thread == key row, each half stores 32 of the 64 dims ----
-    mbar_wait_warp(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    {
-      const int key = kb * 128 + row;
-      const bool kvalid = key < p.Lk;
-      const int64_t r = static_cast<int64_t>(b) * p.Lk + key;
-      store_row_bf16<2>(p.dk + r * p.ld_dk + h * 64 + half * 32, trow + TM_DK + half * 32, p.scale, kvalid);
-      store_row_bf16<2>(p.dv + r * p.ld_dv + h * 64 + half * 32, trow + TM_DV + half * 32, 1.0f, kvalid);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    g = gn;
   }
-  // ---- drain dQ (all MMAs retired: the last commit covered them) ----
-  for (int qb = 0; qb < nqb; ++qb) {
-    const int q = qb * 128 + row;
-    store_row_bf16<2>(p.dq + (static_cast<int64_t>(b) * p.Lq + q) * p.ld_dq + h * 64 + half * 32,
-                      trow + TM_DQ + qb * 64 + half * 32, p.scale, q < p.Lq);
-  }
+  AT_TRACE(60);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  AT_TRACE(61);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -657,19 +838,31 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
   AttnParams p;
   fill_params(a, p);
   const int n_kv = a.n_kv > 0 ? a.n_kv : a.B;
-  CUtensorMap tq, tk, tv, tdo;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  X2K_REQUIRE(al16(a.d_o) && al16(a.dq) && al16(a.dk) && al16(a.dv) && al16(a.ds_out), "x2k_attn_bwd: 16-byte alignment");
+  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv, tds;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tq, a.q, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_q, 128, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tk, a.k, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_k, 128, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tv, a.v, static_cast<uint64_t>(n_kv) * a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_v, 128, 64))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tdo, a.d_o, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_do, 128, 64))) return rc;
+  const uint64_t cols = static_cast<uint64_t>(a.H) * 64;
+  if ((rc = make_tmap_bf16_2d(&tq, a.q, static_cast<uint64_t>(a.B) * a.Lq, cols, a.ld_q, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, a.k, static_cast<uint64_t>(n_kv) * a.Lk, cols, a.ld_k, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, a.v, static_cast<uint64_t>(n_kv) * a.Lk, cols, a.ld_v, 128, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, a.d_o, static_cast<uint64_t>(a.B) * a.Lq, cols, a.ld_do, 128, 64))) return rc;
+  // gradients leave as TMA stores of [128 x 64] tiles; the per-sequence view clips the rows past Lq / Lk
+  if ((rc = make_tmap_bf16_seq3d(&tdq, a.dq, a.B, a.Lq, cols, a.ld_dq, 128))) return rc;
+  if ((rc = make_tmap_bf16_seq3d(&tdk, a.dk, a.B, a.Lk, cols, a.ld_dk, 128))) return rc;
+  if ((rc = make_tmap_bf16_seq3d(&tdv, a.dv, a.B, a.Lk, cols, a.ld_dv, 128))) return rc;
+  if (a.ds_out) {
+    if ((rc = make_tmap_bf16_4d(&tds, a.ds_out, p.Lk_pad, a.Lq, a.H, a.B, a.ds_q_stride, a.ds_h_stride, a.ds_b_stride))) return rc;
+  } else {
+    tds = tdq;  // never used by the kernel
+  }
   static bool attr_set = false;
   if (!attr_set) {
     X2K_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_set = true;
   }
   dim3 grid(a.H, a.B);
-  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, tds, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;
@@ -734,3 +927,9 @@ extern "C" int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H
   count_launch();
   return X2K_OK;
 }
+
+#ifdef X2K_ATTN_TRACE
+extern "C" int x2k_debug_attn_trace(long long* out128) {
+  return cudaMemcpyFromSymbol(out128, g_attn_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -38,6 +38,10 @@ int make_tmap_f32_epi(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
 // loads and skipped by stores.
 int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint64_t seq_rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows);
+// 4-D view [d3][d2][rows][cols] of bf16 data with arbitrary (16-byte multiple) strides, box = [1][1][128][64], 128B swizzle:
+// the attention backward stores its dS tiles with it (rows / columns past the extents are clipped).
+int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t d2, uint64_t d3,
+                      uint64_t row_stride, uint64_t d2_stride, uint64_t d3_stride);
 
 // attn_pack.cu: packed short-sequence attention.  0 = launched, 1 = shape not eligible (use attn.cu), < 0 = error.
 int attn_pack_fwd(const X2kAttnArgs& a, cudaStream_t stream);
@@ -137,6 +141,35 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 }
 
+// Short in-CTA waits (an MMA chain a few hundred cycles long): spin on test_wait.  The suspending try_wait above wakes
+// 600-1200 cycles after the phase flips (measured with clock64 stamps, tools/trace_attn.py) — fine for a TMA producer
+// that waits for microseconds, a tenth of an attention CTA's life when every tile pays it.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 4095u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("x2k: mbarrier watchdog (spin) block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_spin_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_spin(bar, parity);
+  __syncwarp();
+}
+
 // ---- thread-block clusters / CTA pairs (cta_group::2) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -213,6 +246,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t sme
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1) {

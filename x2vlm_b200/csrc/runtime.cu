@@ -126,6 +126,29 @@ int make_tmap_bf16_seq3d(CUtensorMap* tm, const void* base, uint64_t n_seq, uint
   return X2K_OK;
 }
 
+int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t d2, uint64_t d3,
+                      uint64_t row_stride, uint64_t d2_stride, uint64_t d3_stride) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return X2K_ERR_CUDA;
+  }
+  cuuint64_t gdim[4] = {cols, rows, d2, d3};
+  cuuint64_t gstride[3] = {row_stride * 2, d2_stride * 2, d3_stride * 2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4d) failed: %d (cols=%llu rows=%llu d2=%llu d3=%llu strides=%llu/%llu/%llu base=%p)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)d2, (unsigned long long)d3,
+              (unsigned long long)row_stride, (unsigned long long)d2_stride, (unsigned long long)d3_stride, base);
+    return X2K_ERR_CUDA;
+  }
+  return X2K_OK;
+}
+
 }  // namespace x2k
 
 extern "C" int x2k_version(void) { return X2K_VERSION; }

@@ -258,8 +258,8 @@ __device__ __forceinline__ BwdTile bwd_tile(const AttnParams& p, int t, int nqb,
 }
 
 // Bias block [32 rows x 32 cols] fp32 of one warp in two steps, so the L2 latency of the loads hides behind an MMA wait
-// or the previous unit's math: issue (8 coalesced LDG.128 per lane, 4 rows x 128 B per instruction) ... commit (transpose
-// through the warp's 4 KB XOR-swizzled staging tile: every thread ends up with the 32 values of ITS row).
+// or the previous unit's math: issue (8 coalesced LDG.128 per lane, 4 rows x 128 B per instruction) ... stage (into the
+// warp's 4 KB XOR-swizzled tile) ... read (every thread picks up 16 values of ITS row per 16-column chunk).
 __device__ __forceinline__ void bias_issue(const float* __restrict__ base, int64_t row_stride, int rows_left, int lane,
                                            float4 (&v)[8]) {
   const int sub = lane >> 3, ch = lane & 7;
@@ -270,7 +270,7 @@ __device__ __forceinline__ void bias_issue(const float* __restrict__ base, int64
     v[i] = __ldg(reinterpret_cast<const float4*>(base + rc * row_stride) + ch);
   }
 }
-__device__ __forceinline__ void bias_commit(const float4 (&v)[8], uint32_t stage_addr, int lane, float (&out)[32]) {
+__device__ __forceinline__ void bias_stage(const float4 (&v)[8], uint32_t stage_addr, int lane) {
   const int sub = lane >> 3, ch = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -280,16 +280,18 @@ __device__ __forceinline__ void bias_commit(const float4 (&v)[8], uint32_t stage
                  : "memory");
   }
   __syncwarp();
+}
+// the 16 values of this thread's row for 16-column chunk `v` (0 / 1) of the staged 32-column block
+__device__ __forceinline__ void bias_read16(uint32_t stage_addr, int lane, int v, float (&out)[16]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     float4 w;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                 : "r"(stage_addr + lane * 128 + ((c ^ (lane & 7)) << 4))
+                 : "r"(stage_addr + lane * 128 + (((4 * v + c) ^ (lane & 7)) << 4))
                  : "memory");
     out[4 * c] = w.x; out[4 * c + 1] = w.y; out[4 * c + 2] = w.z; out[4 * c + 3] = w.w;
   }
-  __syncwarp();
 }
 
 // TMEM row (this thread's lane) -> 32 fp32 columns -> scaled bf16 -> the thread's row of a 128B-swizzled [128 x 64]
@@ -334,13 +336,16 @@ __device__ __forceinline__ float row_delta(const AttnParams& p, int b, int q, in
 
 // Schedule of one CTA = one (b, h), up to 2 x 2 tiles of 128 queries x 128 keys, key block outer:
 //   * every operand tile (Q, dO of both query blocks, K, V of both key blocks) is TMA-loaded once, up front;
-//   * per tile: S = Q·Kᵀ and dP = dO·Vᵀ (tensor pipe) -> P / dS pass (all threads; the first bias block of the tile was
-//     requested before the wait) -> dS leaves by TMA store straight from the UMMA operand tile (rel-pos bias gradient)
-//     -> dQ += dS·K, dK += dSᵀ·Q, dV += Pᵀ·dO, and the NEXT tile's S / dP are issued right behind them;
-//   * dK / dV of a key block and dQ at the end are staged as bf16 tiles in the (then idle) P / dS buffers and written
-//     by TMA stores (3-D maps clip the rows past the sequence); the drain of a key block overlaps the next S / dP;
-//   * a tcgen05.commit issued AFTER the bulk stores have read their staging tiles is the gate that lets the next
-//     pass overwrite them — no extra CTA barrier.
+//   * tile t: S = Q·Kᵀ, dP = dO·Vᵀ (tensor pipe) -> every thread computes its share of P / dS INTO REGISTERS while the
+//     tensor pipe still runs the previous tile's dQ / dK / dV chains (they read the P / dS tiles in shared memory) ->
+//     once those have completed (bar_pd) the registers are stored -> CTA barrier -> warp 0 issues S / dP of tile t+1
+//     and then dQ += dS·K, dK += dSᵀ·Q, dV += Pᵀ·dO of tile t.  The CUDA-core pass of a tile thus overlaps the MMAs of
+//     its predecessor although P / dS, S / dP and the accumulators are all single-buffered (shared memory and TMEM are
+//     full: 224 KB, 512 columns);
+//   * dS leaves by TMA store straight from the UMMA operand tile (rel-pos bias gradient); dK / dV of a finished key
+//     block are staged as bf16 in that block's (now dead) K / V tiles, dQ at the end in the Q tiles, and written by
+//     TMA stores whose 3-D maps clip the rows past the sequence.  Warp 7 owns all bulk stores; its elected lane joins
+//     bar_pd once the dS store has read its tile, so nobody overwrites it early and no extra CTA barrier is needed.
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -351,15 +356,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   AT_TRACE(0);
   uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + BWD_BARS);  // [0] Q0 dO0 K0 V0, [1] Q1 dO1, [2] K1 V1
   uint64_t* bar_s = bar_ld + 3;                                     // S / dP of a tile are in TMEM
-  uint64_t* bar_acc = bar_ld + 4;                                   // dK / dV of a key block (and finally dQ) are complete
+  uint64_t* bar_pd = bar_ld + 4;  // dQ / dK / dV chains of a tile are complete (and its dS store has read the tile)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_ld + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // The MMA / TMA issue code runs warp-converged in warp 0 (index taken through a shuffle so that the compiler can prove
-  // it uniform) with only the instruction itself under elect.sync: descriptors then live in uniform registers.  Issued
-  // from a divergent `threadIdx.x == 0` branch every tcgen05.mma costs ~91 cycles (R2UR moves) whatever its shape;
-  // this way an N = 64 MMA costs 58 and an N = 128 one 67 (tools/mma_bench.cu).
-  const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
+  // The MMA / TMA issue code runs warp-converged (warp index taken through a shuffle so that the compiler can prove it
+  // uniform) with only the instruction itself under elect.sync: descriptors then live in uniform registers
+  // (tools/mma_bench.cu: 58 / 67 cycles per N = 64 / 128 MMA instead of 91 from a divergent `threadIdx.x == 0` branch).
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const bool issuer_warp = warp_u == 0, store_warp = warp_u == 7;
+  const bool store_lane = store_warp && elect_one();
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -370,7 +376,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) mbar_init(bar_ld + i, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_ld + i, 1);
+    mbar_init(bar_pd, p.ds_out ? 2 : 1);
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_ld, 4 * 16384);
     tma_load_2d(smem + BWD_SQ, &tmap_q, bar_ld, h * 64, b * p.Lq);
@@ -421,7 +428,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint64_t f_k = make_smem_desc(0, 16, 1024);       // K-major operand
   const uint64_t f_mn = make_smem_desc(0, 8192, 1024);    // MN-major [k rows][64] operand (Q, dO, K as B)
   const uint64_t f_mnp = make_smem_desc(0, 16384, 1024);  // MN-major P / dS as A: 64-key chunks are 16 KB apart
-  uint32_t s_phase = 0, acc_phase = 0;
+  uint32_t s_phase = 0, pd_phase = 0;
 
   // S = Q[qb]·K[kb]ᵀ and dP = dO[qb]·V[kb]ᵀ, N = the block's valid keys rounded up to 16 (issuer warp, converged)
   auto issue_scores = [&](int kb, int qb, int nkc) {
@@ -438,7 +445,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   BwdTile g = bwd_tile(p, 0, nqb, quad, half, h);
   float4 bv[8];
-  if (g.bias_blk && g.u_begin < g.u_end) bias_issue(g.bias_blk + g.u_begin * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
   if (issuer_warp) {
     mbar_wait(bar_ld, 0);
     tc_fence_after();
@@ -447,8 +453,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (elect_one()) umma_commit(bar_s);
     __syncwarp();
   }
+  if (g.bias_blk && g.u_begin < g.u_end) bias_issue(g.bias_blk + g.u_begin * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
   AT_TRACE(2);
 
+  int drain_kb = -1;  // key block whose dK / dV are final with the pending bar_pd phase and not yet staged
   for (int t = 0; t < ntile; ++t) {
     const int kb = g.kb, qb = g.qb, nkc = g.nkc;
     mbar_wait_spin_warp(bar_s, s_phase);
@@ -456,81 +464,118 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     AT_TRACE(4 + t * 6);
 
-    // ---- P and dS for this (q block, key block) tile; thread == query row, half == column range ----
+    // ---- P and dS of this (q block, key block) tile into registers; thread == query row, half == column range ----
     const int q = qb * 128 + row;
     const bool qvalid = q < p.Lq;
     const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
     const uint64_t drop_base = (static_cast<uint64_t>(b * p.H + h) * p.Lq + q) * p.Lk_pad;
     const float my_lse = qb ? lse_1 : lse_0, my_delta = qb ? dl_1 : dl_0;
-    if (g.warp_live) {
-#pragma unroll 1
-      for (int u = g.u_begin; u < g.u_end; ++u) {
-        float add[32];
+    uint32_t oP[4][8], oD[4][8];
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui) {
+      const int u = g.u_begin + ui;
+      if (g.warp_live && u < g.u_end) {  // warp-uniform
         if (g.bias_blk) {
-          bias_commit(bv, stage_addr, lane, add);
+          bias_stage(bv, stage_addr, lane);
           if (u + 1 < g.u_end) bias_issue(g.bias_blk + (u + 1) * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) add[j] = 0.f;
-        }
-        if (mask_row) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + kb * 128 + u * 32 + j));
-            add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
-          }
         }
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const int c = 2 * u + v;
-          if (c >= nkc) break;  // warp-uniform
-          const int k0 = kb * 128 + c * 16;
-          uint32_t s[16], dp[16];
-          tmem_ld_32x16(trow + TM_S + c * 16, s);
-          tmem_ld_32x16(trow + TM_DP + c * 16, dp);
-          tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
-          float pr[16], ds[16];
-          if (qvalid) {
+          if (c < nkc) {  // warp-uniform
+            const int k0 = kb * 128 + c * 16;
+            uint32_t s[16], dp[16];
+            tmem_ld_32x16(trow + TM_S + c * 16, s);
+            tmem_ld_32x16(trow + TM_DP + c * 16, dp);
+            float add[16];
+            if (g.bias_blk) {
+              bias_read16(stage_addr, lane, v, add);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float tt = fmaf(__uint_as_float(s[j]), p.scale_log2, add[16 * v + j] * kLog2e);
-              pr[j] = (k0 + j < p.Lk) ? fast_exp2(tt - my_lse) : 0.f;
-              ds[j] = __uint_as_float(dp[j]);
+              for (int j = 0; j < 16; ++j) add[j] = 0.f;
             }
-            if (p.dropout_p > 0.f) {
+            if (mask_row) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 8) {
-                float k[8];
-                drop8(p.seed, doff, (drop_base + k0 + j) >> 3, dc, k);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + k0 + j));
+                add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
+              }
+            }
+            tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
+            float pr[16], ds[16];
+            if (qvalid) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  // dS uses the un-dropped P; the P that feeds dV is the dropped one
-                  const float pu = pr[j + i];
-                  ds[j + i] = pu * (ds[j + i] * k[i] - my_delta);
-                  pr[j + i] = pu * k[i];
+              for (int j = 0; j < 16; ++j) {
+                const float tt = fmaf(__uint_as_float(s[j]), p.scale_log2, add[j] * kLog2e);
+                pr[j] = (k0 + j < p.Lk) ? fast_exp2(tt - my_lse) : 0.f;
+                ds[j] = __uint_as_float(dp[j]);
+              }
+              if (p.dropout_p > 0.f) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  float k[8];
+                  drop8(p.seed, doff, (drop_base + k0 + j) >> 3, dc, k);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    // dS uses the un-dropped P; the P that feeds dV is the dropped one
+                    const float pu = pr[j + i];
+                    ds[j + i] = pu * (ds[j + i] * k[i] - my_delta);
+                    pr[j + i] = pu * k[i];
+                  }
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (ds[j] - my_delta);
+              for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
             }
-          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
+            for (int j = 0; j < 8; ++j) {
+              oP[ui * 2 + v][j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
+              oD[ui * 2 + v][j] = pack_bf16x2(ds[2 * j], ds[2 * j + 1]);
+            }
           }
-          const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
-          st_shared_v4(sbase + BWD_SP + o0, pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]),
-                       pack_bf16x2(pr[6], pr[7]));
-          st_shared_v4(sbase + BWD_SP + o1, pack_bf16x2(pr[8], pr[9]), pack_bf16x2(pr[10], pr[11]),
-                       pack_bf16x2(pr[12], pr[13]), pack_bf16x2(pr[14], pr[15]));
-          st_shared_v4(sbase + BWD_SDS + o0, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
-                       pack_bf16x2(ds[6], ds[7]));
-          st_shared_v4(sbase + BWD_SDS + o1, pack_bf16x2(ds[8], ds[9]), pack_bf16x2(ds[10], ds[11]),
-                       pack_bf16x2(ds[12], ds[13]), pack_bf16x2(ds[14], ds[15]));
         }
+        if (g.bias_blk) __syncwarp();  // the staging tile is rewritten by the next unit
       }
     }
     AT_TRACE(5 + t * 6);
+
+    // ---- the previous tile's MMAs have read P / dS (and its dS store too): drain a finished key block, store ----
+    if (t > 0) {
+      if (p.ds_out && store_lane) {
+        tma_store_wait_read();
+        mbar_arrive(bar_pd);
+      }
+      mbar_wait_spin_warp(bar_pd, pd_phase);
+      pd_phase ^= 1;
+      tc_fence_after();
+      if (drain_kb >= 0) {  // dK / dV of the finished key block -> bf16 staging in its K / V tiles (dead from here on)
+        stage_row32(sbase + BWD_SK + drain_kb * 16384, row, half * 32, trow + TM_DK + half * 32, p.scale);
+        stage_row32(sbase + BWD_SV + drain_kb * 16384, row, half * 32, trow + TM_DV + half * 32, 1.0f);
+      }
+    }
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui) {
+      const int u = g.u_begin + ui;
+      if (g.warp_live && u < g.u_end) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int c = 2 * u + v;
+          if (c < nkc) {
+            const uint32_t o0 = swz_off(row, c * 16), o1 = swz_off(row, c * 16 + 8);
+            const uint32_t(&a)[8] = oP[ui * 2 + v];
+            const uint32_t(&d)[8] = oD[ui * 2 + v];
+            st_shared_v4(sbase + BWD_SP + o0, a[0], a[1], a[2], a[3]);
+            st_shared_v4(sbase + BWD_SP + o1, a[4], a[5], a[6], a[7]);
+            st_shared_v4(sbase + BWD_SDS + o0, d[0], d[1], d[2], d[3]);
+            st_shared_v4(sbase + BWD_SDS + o1, d[4], d[5], d[6], d[7]);
+          }
+        }
+      }
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -541,19 +586,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const bool last = t == ntile - 1;
     BwdTile gn = g;
     if (!last) gn = bwd_tile(p, t + 1, nqb, quad, half, h);
-    // the next tile's first bias block is requested now and consumed after the wait for its S / dP (the issuer warp
-    // first gets the tensor pipe going)
-    if (!last && !issuer_warp && gn.bias_blk && gn.u_begin < gn.u_end)
-      bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
 
     if (issuer_warp) {
-      const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
-      if (p.ds_out) {  // dS tile -> ds_out[b, h, q block, key block] (columns past pad16(Lk) and rows past Lq are clipped)
-        for (int blk = 0; blk * 4 < nkc; ++blk)
-          if (elect_one()) tma_store_4d(&tmap_ds, ads + blk * 16384, kb * 128 + blk * 64, qb * 128, h, b);
-        if (elect_one()) tma_store_commit();
+      if (!last) {  // S / dP of the next tile go first: its pass then runs under this tile's gradient chains
+        if (gn.qb == 1 && gn.kb == 0) mbar_wait(bar_ld + 1, 0);
+        if (gn.kb == 1 && gn.qb == 0) mbar_wait(bar_ld + 2, 0);
+        tc_fence_after();
+        issue_scores(gn.kb, gn.qb, gn.nkc);
+        if (elect_one()) umma_commit(bar_s);
       }
       AT_TRACE(46 + (t & 1) * 4);
+      const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
       const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
       // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
       {
@@ -574,64 +617,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int ks = 0; ks < nqc; ++ks)
           if (elect_one()) umma_bf16(tmem + TM_DV, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
       }
+      if (elect_one()) umma_commit(bar_pd);
+      __syncwarp();
       AT_TRACE(47 + (t & 1) * 4);
-      if (kb_end && elect_one()) {
-        if (last && p.ds_out) tma_store_wait_read();  // the dQ staging below reuses the dS tile
-        umma_commit(bar_acc);
-      }
-      if (!last) {
-        if (gn.qb == 1 && gn.kb == 0) mbar_wait(bar_ld + 1, 0);
-        if (gn.kb == 1 && gn.qb == 0) mbar_wait(bar_ld + 2, 0);
-        tc_fence_after();
-        issue_scores(gn.kb, gn.qb, gn.nkc);
-        AT_TRACE(48 + (t & 1) * 4);
-        if (!kb_end && elect_one()) {
-          if (p.ds_out) tma_store_wait_read();  // the next pass overwrites the dS tile
-          umma_commit(bar_s);
+    }
+    if (store_warp) {
+      if (store_lane) {
+        if (drain_kb >= 0) {  // staged in this tile's pass, visible since the barrier above
+          tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
+          tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
         }
+        if (p.ds_out)  // dS tile -> ds_out[b, h, q block, key block] (columns past pad16(Lk), rows past Lq are clipped)
+          for (int blk = 0; blk * 4 < nkc; ++blk)
+            tma_store_4d(&tmap_ds, sbase + BWD_SDS + blk * 16384, kb * 128 + blk * 64, qb * 128, h, b);
+        tma_store_commit();
       }
       __syncwarp();
-      if (!last && gn.bias_blk && gn.u_begin < gn.u_end)
-        bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
     }
+    drain_kb = kb_end ? kb : -1;
+    // the next tile's first bias block is requested now and consumed after the wait for its S / dP
+    if (!last && gn.bias_blk && gn.u_begin < gn.u_end)
+      bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
     AT_TRACE(7 + t * 6);
-
-    if (kb_end) {
-      // ---- dK / dV of this key block (and, after the last tile, dQ) -> bf16 staging tiles -> TMA stores ----
-      mbar_wait_spin_warp(bar_acc, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      AT_TRACE(40 + kb * 3);
-      stage_row32(sbase + BWD_SP, row, half * 32, trow + TM_DK + half * 32, p.scale);
-      stage_row32(sbase + BWD_SP + 16384, row, half * 32, trow + TM_DV + half * 32, 1.0f);
-      if (last) {
-        for (int i = 0; i < nqb; ++i)
-          stage_row32(sbase + BWD_SDS + i * 16384, row, half * 32, trow + TM_DQ + i * 64 + half * 32, p.scale);
-      }
-      AT_TRACE(41 + kb * 3);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-      if (issuer_warp) {
-        if (elect_one()) {
-          tma_store_3d(&tmap_dk, sbase + BWD_SP, h * 64, kb * 128, b);
-          tma_store_3d(&tmap_dv, sbase + BWD_SP + 16384, h * 64, kb * 128, b);
-          if (last)
-            for (int i = 0; i < nqb; ++i) tma_store_3d(&tmap_dq, sbase + BWD_SDS + i * 16384, h * 64, i * 128, b);
-          tma_store_commit();
-          tma_store_wait_read();  // staging tiles (and, at the end, shared memory as a whole) are free again
-          if (!last) umma_commit(bar_s);  // gate of the next pass: its S / dP were issued before the drain
-        }
-        __syncwarp();
-      }
-      AT_TRACE(42 + kb * 3);
-    }
     g = gn;
   }
-  AT_TRACE(60);
+
+  // ---- last key block's dK / dV and dQ: staged in the K / V / Q tiles (every MMA has completed), TMA-stored ----
+  if (p.ds_out && store_lane) {
+    tma_store_wait_read();
+    mbar_arrive(bar_pd);
+  }
+  mbar_wait_spin_warp(bar_pd, pd_phase);
+  tc_fence_after();
+  AT_TRACE(40);
+  stage_row32(sbase + BWD_SK + drain_kb * 16384, row, half * 32, trow + TM_DK + half * 32, p.scale);
+  stage_row32(sbase + BWD_SV + drain_kb * 16384, row, half * 32, trow + TM_DV + half * 32, 1.0f);
+  for (int i = 0; i < nqb; ++i)
+    stage_row32(sbase + BWD_SQ + i * 16384, row, half * 32, trow + TM_DQ + i * 64 + half * 32, p.scale);
+  AT_TRACE(41);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (store_warp) {
+    if (store_lane) {
+      tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
+      tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
+      for (int i = 0; i < nqb; ++i) tma_store_3d(&tmap_dq, sbase + BWD_SQ + i * 16384, h * 64, i * 128, b);
+      tma_store_commit();
+      tma_store_wait_read();  // shared memory must stay intact until the bulk stores have read it
+    }
+    __syncwarp();
+  }
+  AT_TRACE(60);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);

@@ -40,7 +40,7 @@ def run(name, B, Lq, Lk, n_kv, bias=False, mask=False, shared=False, p=0.0, reps
     st.record(); ops.attn_bwd(qv, kk, vv, B, H, Lq, Lk, 0.125, o, lse, do, dq, dkv[:, :D], dkv[:, D:], ds_out=ds, **kw); en.record(); torch.cuda.synchronize()
     print("ATTN %-12s B=%d Lq=%d Lk=%d fwd %.1f us bwd %.1f us" % (name, B, Lq, Lk, tf * 1e3, st.elapsed_time(en) * 1e3))
 only = os.environ.get("X2K_ATTN_CASE")
-for case in (("beit", 90, 197, 197, 90, dict(bias=True)), ("beit577", 16, 577, 577, 16, dict(bias=True)),
+for case in (("beit", 90, 197, 197, 90, dict(bias=True)), ("beit-nobias", 90, 197, 197, 90, dict()), ("beit577", 16, 577, 577, 16, dict(bias=True)),
              ("beit2305", 2, 2305, 2305, 2, dict(bias=True)), ("cross577", 64, 40, 577, 16, dict(mask=True, shared=True, p=0.1)),
              ("text", 256, 40, 40, 256, dict(mask=True, p=0.1)),
              ("fus-self", 576, 40, 40, 576, dict(mask=True, p=0.1)),

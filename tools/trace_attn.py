@@ -25,14 +25,16 @@ import torch
 from x2vlm_b200 import _capi as C
 
 
-def dump(fn, names):
-    buf = (ctypes.c_longlong * 128)()
+def dump(fn, names, threads=(("thread 0", 0), ("thread 200", 64))):
+    buf = (ctypes.c_longlong * 192)()
     f = getattr(C.lib(), fn)
     f.argtypes = [ctypes.c_void_p]
     assert f(buf) == 0
-    for who, base in (("thread 0", 0), ("thread 200", 64)):
+    for who, base in threads:
         t = [buf[base + i] for i in range(64)]
         print(" ", who)
+        if t[0] == 0:
+            t[0] = min(x for x in t if x > 0)
         prev = t[0]
         for i in sorted(names):
             if t[i] == 0 or t[i] < t[0]:
@@ -59,8 +61,8 @@ def attn_names():
         for k, n in enumerate(["dK/dV ready", "dK/dV drained", "synced"]):
             names[40 + kb * 3 + k] = "key block %d: %s" % (kb, n)
     for i in range(2):
-        for k, n in enumerate(["dS store issued", "dQ/dK/dV MMAs issued", "next S/dP issued"]):
-            names[46 + i * 4 + k] = "issuer, last %s tile: %s" % ("even" if i == 0 else "odd", n)
+        for k, n in enumerate(["next S/dP issued", "P/dS stored (barrier passed)", "dQ/dK/dV MMAs issued"]):
+            names[46 + i * 4 + k] = "MMA warp, last %s tile: %s" % ("even" if i == 0 else "odd", n)
     return names
 
 
@@ -74,4 +76,7 @@ for case, fn, names in (("beit", "x2k_debug_attn_trace", attn_names()), ("fus-se
     runpy.run_path(os.path.join(ROOT, "tools", "profile_attn.py"))
     torch.cuda.synchronize()
     print("TRACE", case)
-    dump(fn, names)
+    if case == "beit":
+        dump(fn, names, (("thread 0", 0), ("thread 200", 64), ("thread 256 (MMA warp)", 128)))
+    else:
+        dump(fn, names)

@@ -209,15 +209,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: grid (H, B), 256 threads, 1 CTA / SM (TMEM 512 columns)
+// backward: grid (H, B), 384 threads (8 compute warps + MMA warp + store warp), 1 CTA / SM (TMEM 512 columns)
 // ---------------------------------------------------------------------------------------------
 // Optional phase trace (compile with -DX2K_ATTN_TRACE): clock64 stamps of one CTA, read back by x2k_debug_attn_trace.
 #ifdef X2K_ATTN_TRACE
-__device__ long long g_attn_trace[2][64];
+__device__ long long g_attn_trace[3][64];
 #define AT_TRACE(i)                                                                           \
   do {                                                                                        \
-    if (blockIdx.x == 5 && blockIdx.y == 40 && (threadIdx.x == 0 || threadIdx.x == 200))      \
-      g_attn_trace[threadIdx.x ? 1 : 0][(i)] = clock64();                                     \
+    if (blockIdx.x == 5 && blockIdx.y == 40 && (threadIdx.x == 0 || threadIdx.x == 200 || threadIdx.x == 256)) \
+      g_attn_trace[threadIdx.x == 0 ? 0 : threadIdx.x == 200 ? 1 : 2][(i)] = clock64();       \
   } while (0)
 #else
 #define AT_TRACE(i) do {} while (0)
@@ -334,19 +334,31 @@ __device__ __forceinline__ float row_delta(const AttnParams& p, int b, int q, in
   return acc;
 }
 
-// Schedule of one CTA = one (b, h), up to 2 x 2 tiles of 128 queries x 128 keys, key block outer:
+// Schedule of one CTA = one (b, h), up to 2 x 2 tiles of 128 queries x 128 keys, key block outer.  Three warpgroups:
+// warps 0-7 compute (thread == query row, half == column range), warp 8 issues every MMA, warp 9 every bulk store
+// (setmaxnreg moves the registers of warpgroup 2 to the compute warps).
 //   * every operand tile (Q, dO of both query blocks, K, V of both key blocks) is TMA-loaded once, up front;
-//   * tile t: S = Q·Kᵀ, dP = dO·Vᵀ (tensor pipe) -> every thread computes its share of P / dS INTO REGISTERS while the
-//     tensor pipe still runs the previous tile's dQ / dK / dV chains (they read the P / dS tiles in shared memory) ->
-//     once those have completed (bar_pd) the registers are stored -> CTA barrier -> warp 0 issues S / dP of tile t+1
-//     and then dQ += dS·K, dK += dSᵀ·Q, dV += Pᵀ·dO of tile t.  The CUDA-core pass of a tile thus overlaps the MMAs of
-//     its predecessor although P / dS, S / dP and the accumulators are all single-buffered (shared memory and TMEM are
-//     full: 224 KB, 512 columns);
-//   * dS leaves by TMA store straight from the UMMA operand tile (rel-pos bias gradient); dK / dV of a finished key
-//     block are staged as bf16 in that block's (now dead) K / V tiles, dQ at the end in the Q tiles, and written by
-//     TMA stores whose 3-D maps clip the rows past the sequence.  Warp 7 owns all bulk stores; its elected lane joins
-//     bar_pd once the dS store has read its tile, so nobody overwrites it early and no extra CTA barrier is needed.
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+//   * tile t, compute warps: wait S/dP(t) (bar_s) -> P / dS INTO REGISTERS -> arrive "S/dP consumed" -> wait for the
+//     previous tile's dQ / dK / dV chains (bar_pd: they read the P / dS tiles in shared memory) -> drain a finished key
+//     block -> store the registers -> arrive "P/dS stored".  They never stop at a CTA-wide barrier;
+//   * MMA warp: "consumed" -> S = Q·Kᵀ, dP = dO·Vᵀ of tile t+1;  "stored" -> dQ += dS·K, dK += dSᵀ·Q, dV += Pᵀ·dO of
+//     tile t.  The CUDA-core pass of a tile overlaps the gradient chains of its predecessor although P / dS, S / dP
+//     and the accumulators are all single-buffered (shared memory and TMEM are full: 224 KB, 512 columns);
+//   * store warp: dS leaves by TMA store straight from the UMMA operand tile (rel-pos bias gradient); dK / dV of a
+//     finished key block are staged as bf16 in that block's (now dead) K / V tiles, dQ at the end in the Q tiles, and
+//     written by TMA stores whose 3-D maps clip the rows past the sequence.  Its elected lane joins bar_pd once the
+//     dS store has read the tile, so nobody overwrites it early.
+constexpr int BWD_THREADS = 384;
+constexpr int NB_CONSUMED = 1, NB_STORED = 2, NB_FINAL = 3;  // named barriers (0 = __syncthreads)
+
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
@@ -360,48 +372,163 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_ld + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // The MMA / TMA issue code runs warp-converged (warp index taken through a shuffle so that the compiler can prove it
-  // uniform) with only the instruction itself under elect.sync: descriptors then live in uniform registers
-  // (tools/mma_bench.cu: 58 / 67 cycles per N = 64 / 128 MMA instead of 91 from a divergent `threadIdx.x == 0` branch).
+  // Issue code runs warp-converged (warp index taken through a shuffle so that the compiler can prove it uniform) with
+  // only the instruction itself under elect.sync: descriptors then live in uniform registers (tools/mma_bench.cu:
+  // 58 / 67 cycles per N = 64 / 128 MMA instead of 91 from a divergent `threadIdx.x == 0` branch).
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const bool issuer_warp = warp_u == 0, store_warp = warp_u == 7;
-  const bool store_lane = store_warp && elect_one();
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int nqb = (p.Lq + 127) >> 7, nkb = (p.Lk + 127) >> 7;
   const int ntile = nqb * nkb;
   const uint32_t sbase = smem_u32(smem);
 
-  if (threadIdx.x == 0) {
+  if (warp_u == 8) {
+    if (elect_one()) {
+      const int kvb = p.kv_index ? p.kv_index[b] : b;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(bar_ld + i, 1);
-    mbar_init(bar_pd, p.ds_out ? 2 : 1);
-    fence_barrier_init();
-    mbar_arrive_expect_tx(bar_ld, 4 * 16384);
-    tma_load_2d(smem + BWD_SQ, &tmap_q, bar_ld, h * 64, b * p.Lq);
-    tma_load_2d(smem + BWD_SK, &tmap_k, bar_ld, h * 64, kvb * p.Lk);
-    tma_load_2d(smem + BWD_SDO, &tmap_do, bar_ld, h * 64, b * p.Lq);
-    tma_load_2d(smem + BWD_SV, &tmap_v, bar_ld, h * 64, kvb * p.Lk);
-    if (nqb > 1) {
-      mbar_arrive_expect_tx(bar_ld + 1, 2 * 16384);
-      tma_load_2d(smem + BWD_SQ + 16384, &tmap_q, bar_ld + 1, h * 64, b * p.Lq + 128);
-      tma_load_2d(smem + BWD_SDO + 16384, &tmap_do, bar_ld + 1, h * 64, b * p.Lq + 128);
+      for (int i = 0; i < 4; ++i) mbar_init(bar_ld + i, 1);
+      mbar_init(bar_pd, p.ds_out ? 2 : 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(bar_ld, 4 * 16384);
+      tma_load_2d(smem + BWD_SQ, &tmap_q, bar_ld, h * 64, b * p.Lq);
+      tma_load_2d(smem + BWD_SK, &tmap_k, bar_ld, h * 64, kvb * p.Lk);
+      tma_load_2d(smem + BWD_SDO, &tmap_do, bar_ld, h * 64, b * p.Lq);
+      tma_load_2d(smem + BWD_SV, &tmap_v, bar_ld, h * 64, kvb * p.Lk);
+      if (nqb > 1) {
+        mbar_arrive_expect_tx(bar_ld + 1, 2 * 16384);
+        tma_load_2d(smem + BWD_SQ + 16384, &tmap_q, bar_ld + 1, h * 64, b * p.Lq + 128);
+        tma_load_2d(smem + BWD_SDO + 16384, &tmap_do, bar_ld + 1, h * 64, b * p.Lq + 128);
+      }
+      if (nkb > 1) {
+        mbar_arrive_expect_tx(bar_ld + 2, 2 * 16384);
+        tma_load_2d(smem + BWD_SK + 16384, &tmap_k, bar_ld + 2, h * 64, kvb * p.Lk + 128);
+        tma_load_2d(smem + BWD_SV + 16384, &tmap_v, bar_ld + 2, h * 64, kvb * p.Lk + 128);
+      }
     }
-    if (nkb > 1) {
-      mbar_arrive_expect_tx(bar_ld + 2, 2 * 16384);
-      tma_load_2d(smem + BWD_SK + 16384, &tmap_k, bar_ld + 2, h * 64, kvb * p.Lk + 128);
-      tma_load_2d(smem + BWD_SV + 16384, &tmap_v, bar_ld + 2, h * 64, kvb * p.Lk + 128);
-    }
-  }
-  __syncwarp();
-  if (warp == 0) {
+    __syncwarp();
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  AT_TRACE(1);
 
-  // per-row statistics of both query blocks while the tiles fly in: lse (log2 domain) and delta = rowsum(dO ∘ O)
+  if (warp_u >= 8) {
+    // =========================== warpgroup 2: MMA issue (warp 8), bulk stores (warp 9) ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp_u == 8) {
+      const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t f_k = make_smem_desc(0, 16, 1024);       // K-major operand
+      const uint64_t f_mn = make_smem_desc(0, 8192, 1024);    // MN-major [k rows][64] operand (Q, dO, K as B)
+      const uint64_t f_mnp = make_smem_desc(0, 16384, 1024);  // MN-major P / dS as A: 64-key chunks are 16 KB apart
+      // S = Q[qb]·K[kb]ᵀ and dP = dO[qb]·V[kb]ᵀ, N = the block's valid keys rounded up to 16
+      auto issue_scores = [&](int kb, int qb) {
+        const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
+        const uint32_t idesc = make_idesc_bf16(128, nkc * 16, 0, 0);
+        const uint64_t dq_ = desc_at(f_k, sbase + BWD_SQ + qb * 16384), dk_ = desc_at(f_k, sbase + BWD_SK + kb * 16384);
+        const uint64_t ddo = desc_at(f_k, sbase + BWD_SDO + qb * 16384), dv_ = desc_at(f_k, sbase + BWD_SV + kb * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (elect_one()) umma_bf16(tmem + TM_S, dq_ + 2 * k, dk_ + 2 * k, idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (elect_one()) umma_bf16(tmem + TM_DP, ddo + 2 * k, dv_ + 2 * k, idesc, k != 0);
+        if (elect_one()) umma_commit(bar_s);
+      };
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      issue_scores(0, 0);
+      for (int t = 0; t < ntile; ++t) {
+        const int kb = nqb == 2 ? (t >> 1) : t, qb = nqb == 2 ? (t & 1) : 0;
+        const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
+        named_sync(NB_CONSUMED, 256 + 32);  // every compute thread has read S / dP of tile t out of TMEM
+        tc_fence_after();
+        if (t + 1 < ntile) {
+          const int kbn = nqb == 2 ? ((t + 1) >> 1) : t + 1, qbn = nqb == 2 ? ((t + 1) & 1) : 0;
+          if (qbn == 1 && kbn == 0) mbar_wait(bar_ld + 1, 0);
+          if (kbn == 1 && qbn == 0) mbar_wait(bar_ld + 2, 0);
+          issue_scores(kbn, qbn);
+        }
+        AT_TRACE(46 + (t & 1) * 4);
+        named_sync(NB_STORED, 256 + 64);  // P / dS of tile t are in shared memory (fenced for the async proxy)
+        tc_fence_after();
+        AT_TRACE(47 + (t & 1) * 4);
+        const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
+        const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
+        // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
+        {
+          const uint64_t db0 = desc_at(f_mn, sbase + BWD_SK + kb * 16384);
+          for (int ks = 0; ks < nkc; ++ks) {
+            const uint64_t da = desc_at(f_k, ads + (ks >> 2) * 16384 + (ks & 3) * 32);
+            if (elect_one()) umma_bf16(tmem + TM_DQ + qb * 64, da, db0 + ks * 128, idesc_dq, (kb | ks) != 0);
+          }
+        }
+        // dK += dSᵀ · Q[qb], dV += Pᵀ · dO[qb]   (A: dS / P MN-major over keys, K = query rows; B: Q / dO MN-major)
+        {
+          const uint64_t da0 = desc_at(f_mnp, ads), db0 = desc_at(f_mn, sbase + BWD_SQ + qb * 16384);
+          for (int ks = 0; ks < nqc; ++ks)
+            if (elect_one()) umma_bf16(tmem + TM_DK, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
+        }
+        {
+          const uint64_t da0 = desc_at(f_mnp, ap), db0 = desc_at(f_mn, sbase + BWD_SDO + qb * 16384);
+          for (int ks = 0; ks < nqc; ++ks)
+            if (elect_one()) umma_bf16(tmem + TM_DV, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
+        }
+        if (elect_one()) umma_commit(bar_pd);
+        __syncwarp();
+        AT_TRACE(48 + (t & 1) * 4);
+      }
+      named_sync(NB_FINAL, 256 + 64);  // every accumulator has been read out of TMEM
+      tc_fence_after();
+      tmem_dealloc(tmem, 512);
+    } else if (warp_u == 9) {
+      const bool lead = elect_one();
+      int drain_kb = -1;
+      for (int t = 0; t < ntile; ++t) {
+        const int kb = nqb == 2 ? (t >> 1) : t, qb = nqb == 2 ? (t & 1) : 0;
+        const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
+        named_sync(NB_STORED, 256 + 64);  // dS of tile t (and the key block staged during its pass) are in shared memory
+        if (lead) {
+          if (drain_kb >= 0) {
+            tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
+            tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
+          }
+          if (p.ds_out) {  // dS tile -> ds_out[b, h, q block, key block] (columns past pad16(Lk), rows past Lq clipped)
+            for (int blk = 0; blk * 4 < nkc; ++blk)
+              tma_store_4d(&tmap_ds, sbase + BWD_SDS + blk * 16384, kb * 128 + blk * 64, qb * 128, h, b);
+            tma_store_commit();
+            tma_store_wait_read();
+            mbar_arrive(bar_pd);  // the dS tile may be overwritten (once the MMAs that read it have completed too)
+          } else {
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
+        drain_kb = (qb == nqb - 1) ? kb : -1;
+      }
+      named_sync(NB_FINAL, 256 + 64);  // last key block's dK / dV and dQ are staged in the K / V / Q tiles
+      if (lead) {
+        tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
+        tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
+        for (int i = 0; i < nqb; ++i) tma_store_3d(&tmap_dq, sbase + BWD_SQ + i * 16384, h * 64, i * 128, b);
+        tma_store_commit();
+        tma_store_wait_read();  // shared memory must stay intact until the bulk stores have read it
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ======================================= warpgroups 0, 1: compute ============================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+  const uint32_t stage_addr = sbase + BWD_STAGE + warp * 4096;
+
+  // per-row statistics of both query blocks: lse (log2 domain) and delta = rowsum(dO ∘ O)
   const int64_t stat0 = (static_cast<int64_t>(b) * p.H + h) * p.Lq;
   float lse_0 = 0.f, lse_1 = 0.f, dl_0 = 0.f, dl_1 = 0.f;
   if (row < p.Lq) {
@@ -412,47 +539,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     lse_1 = p.lse[stat0 + 128 + row];
     dl_1 = p.delta ? __ldg(p.delta + stat0 + 128 + row) : row_delta(p, b, 128 + row, h);
   }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  const uint32_t stage_addr = sbase + BWD_STAGE + warp * 4096;
-  AT_TRACE(1);
-
   const DropCfg dc = make_drop(p.dropout_p);
   const uint64_t doff = p.offset + (p.offset_dev ? __ldg(p.offset_dev) : 0ull);
-  const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
-  const uint32_t idesc_dkv = make_idesc_bf16(128, 64, 1, 1);
-  const uint64_t f_k = make_smem_desc(0, 16, 1024);       // K-major operand
-  const uint64_t f_mn = make_smem_desc(0, 8192, 1024);    // MN-major [k rows][64] operand (Q, dO, K as B)
-  const uint64_t f_mnp = make_smem_desc(0, 16384, 1024);  // MN-major P / dS as A: 64-key chunks are 16 KB apart
   uint32_t s_phase = 0, pd_phase = 0;
-
-  // S = Q[qb]·K[kb]ᵀ and dP = dO[qb]·V[kb]ᵀ, N = the block's valid keys rounded up to 16 (issuer warp, converged)
-  auto issue_scores = [&](int kb, int qb, int nkc) {
-    const uint32_t idesc = make_idesc_bf16(128, nkc * 16, 0, 0);
-    const uint64_t dq_ = desc_at(f_k, sbase + BWD_SQ + qb * 16384), dk_ = desc_at(f_k, sbase + BWD_SK + kb * 16384);
-    const uint64_t ddo = desc_at(f_k, sbase + BWD_SDO + qb * 16384), dv_ = desc_at(f_k, sbase + BWD_SV + kb * 16384);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (elect_one()) umma_bf16(tmem + TM_S, dq_ + 2 * k, dk_ + 2 * k, idesc, k != 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (elect_one()) umma_bf16(tmem + TM_DP, ddo + 2 * k, dv_ + 2 * k, idesc, k != 0);
-  };
 
   BwdTile g = bwd_tile(p, 0, nqb, quad, half, h);
   float4 bv[8];
-  if (issuer_warp) {
-    mbar_wait(bar_ld, 0);
-    tc_fence_after();
-    AT_TRACE(3);
-    issue_scores(0, 0, g.nkc);
-    if (elect_one()) umma_commit(bar_s);
-    __syncwarp();
-  }
   if (g.bias_blk && g.u_begin < g.u_end) bias_issue(g.bias_blk + g.u_begin * 32, p.bias_q_stride, p.Lq - g.q_warp0, lane, bv);
   AT_TRACE(2);
 
@@ -464,7 +556,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     AT_TRACE(4 + t * 6);
 
-    // ---- P and dS of this (q block, key block) tile into registers; thread == query row, half == column range ----
+    // ---- P and dS of this (q block, key block) tile into registers ----
     const int q = qb * 128 + row;
     const bool qvalid = q < p.Lq;
     const float* mask_row = (p.mask && qvalid) ? p.mask + b * p.mask_b_stride + q * p.mask_q_stride : nullptr;
@@ -504,12 +596,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tmem_wait_ld();  // .sync.aligned: reached by the whole warp, never inside a divergent branch
             float pr[16], ds[16];
             if (qvalid) {
+              // P = 2^(s·scale·log2e + (bias + mask)·log2e − lse): two FMAs and one MUFU per element
+              if (k0 + 16 <= p.Lk) {  // warp-uniform: only the sequence's last chunk needs the key bound
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float tt = fmaf(__uint_as_float(s[j]), p.scale_log2, add[j] * kLog2e);
-                pr[j] = (k0 + j < p.Lk) ? fast_exp2(tt - my_lse) : 0.f;
-                ds[j] = __uint_as_float(dp[j]);
+                for (int j = 0; j < 16; ++j)
+                  pr[j] = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, fmaf(add[j], kLog2e, -my_lse)));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  pr[j] = (k0 + j < p.Lk)
+                              ? fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, fmaf(add[j], kLog2e, -my_lse)))
+                              : 0.f;
               }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ds[j] = __uint_as_float(dp[j]);
               if (p.dropout_p > 0.f) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
@@ -541,14 +641,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (g.bias_blk) __syncwarp();  // the staging tile is rewritten by the next unit
       }
     }
+    tc_fence_before();
+    named_arrive(NB_CONSUMED, 256 + 32);  // S / dP may be overwritten by the next tile's
     AT_TRACE(5 + t * 6);
+
+    // the next tile's first bias block: requested now, consumed after the wait for its S / dP
+    const bool last = t == ntile - 1;
+    BwdTile gn = g;
+    if (!last) {
+      gn = bwd_tile(p, t + 1, nqb, quad, half, h);
+      if (gn.bias_blk && gn.u_begin < gn.u_end)
+        bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
+    }
 
     // ---- the previous tile's MMAs have read P / dS (and its dS store too): drain a finished key block, store ----
     if (t > 0) {
-      if (p.ds_out && store_lane) {
-        tma_store_wait_read();
-        mbar_arrive(bar_pd);
-      }
       mbar_wait_spin_warp(bar_pd, pd_phase);
       pd_phase ^= 1;
       tc_fence_after();
@@ -578,75 +685,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    named_arrive(NB_STORED, 256 + 64);
     AT_TRACE(6 + t * 6);
-
-    const bool kb_end = qb == nqb - 1;
-    const bool last = t == ntile - 1;
-    BwdTile gn = g;
-    if (!last) gn = bwd_tile(p, t + 1, nqb, quad, half, h);
-
-    if (issuer_warp) {
-      if (!last) {  // S / dP of the next tile go first: its pass then runs under this tile's gradient chains
-        if (gn.qb == 1 && gn.kb == 0) mbar_wait(bar_ld + 1, 0);
-        if (gn.kb == 1 && gn.qb == 0) mbar_wait(bar_ld + 2, 0);
-        tc_fence_after();
-        issue_scores(gn.kb, gn.qb, gn.nkc);
-        if (elect_one()) umma_commit(bar_s);
-      }
-      AT_TRACE(46 + (t & 1) * 4);
-      const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
-      const int nqc = (min(p.Lq - qb * 128, 128) + 15) >> 4;  // valid query rows in 16-row groups
-      // dQ[qb] += dS · K          (A: dS K-major over keys; B: K tile MN-major, N = 64 dims)
-      {
-        const uint64_t db0 = desc_at(f_mn, sbase + BWD_SK + kb * 16384);
-        for (int ks = 0; ks < nkc; ++ks) {
-          const uint64_t da = desc_at(f_k, ads + (ks >> 2) * 16384 + (ks & 3) * 32);
-          if (elect_one()) umma_bf16(tmem + TM_DQ + qb * 64, da, db0 + ks * 128, idesc_dq, (kb | ks) != 0);
-        }
-      }
-      // dK += dSᵀ · Q[qb], dV += Pᵀ · dO[qb]   (A: dS / P MN-major over keys, K = query rows; B: Q / dO MN-major)
-      {
-        const uint64_t da0 = desc_at(f_mnp, ads), db0 = desc_at(f_mn, sbase + BWD_SQ + qb * 16384);
-        for (int ks = 0; ks < nqc; ++ks)
-          if (elect_one()) umma_bf16(tmem + TM_DK, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
-      }
-      {
-        const uint64_t da0 = desc_at(f_mnp, ap), db0 = desc_at(f_mn, sbase + BWD_SDO + qb * 16384);
-        for (int ks = 0; ks < nqc; ++ks)
-          if (elect_one()) umma_bf16(tmem + TM_DV, da0 + ks * 128, db0 + ks * 128, idesc_dkv, (qb | ks) != 0);
-      }
-      if (elect_one()) umma_commit(bar_pd);
-      __syncwarp();
-      AT_TRACE(47 + (t & 1) * 4);
-    }
-    if (store_warp) {
-      if (store_lane) {
-        if (drain_kb >= 0) {  // staged in this tile's pass, visible since the barrier above
-          tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
-          tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
-        }
-        if (p.ds_out)  // dS tile -> ds_out[b, h, q block, key block] (columns past pad16(Lk), rows past Lq are clipped)
-          for (int blk = 0; blk * 4 < nkc; ++blk)
-            tma_store_4d(&tmap_ds, sbase + BWD_SDS + blk * 16384, kb * 128 + blk * 64, qb * 128, h, b);
-        tma_store_commit();
-      }
-      __syncwarp();
-    }
-    drain_kb = kb_end ? kb : -1;
-    // the next tile's first bias block is requested now and consumed after the wait for its S / dP
-    if (!last && gn.bias_blk && gn.u_begin < gn.u_end)
-      bias_issue(gn.bias_blk + gn.u_begin * 32, p.bias_q_stride, p.Lq - gn.q_warp0, lane, bv);
-    AT_TRACE(7 + t * 6);
+    drain_kb = (qb == nqb - 1) ? kb : -1;
     g = gn;
   }
 
   // ---- last key block's dK / dV and dQ: staged in the K / V / Q tiles (every MMA has completed), TMA-stored ----
-  if (p.ds_out && store_lane) {
-    tma_store_wait_read();
-    mbar_arrive(bar_pd);
-  }
   mbar_wait_spin_warp(bar_pd, pd_phase);
   tc_fence_after();
   AT_TRACE(40);
@@ -657,23 +702,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   AT_TRACE(41);
   fence_proxy_async_smem();
   tc_fence_before();
-  __syncthreads();
-  if (store_warp) {
-    if (store_lane) {
-      tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
-      tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
-      for (int i = 0; i < nqb; ++i) tma_store_3d(&tmap_dq, sbase + BWD_SQ + i * 16384, h * 64, i * 128, b);
-      tma_store_commit();
-      tma_store_wait_read();  // shared memory must stay intact until the bulk stores have read it
-    }
-    __syncwarp();
-  }
+  named_arrive(NB_FINAL, 256 + 64);
   AT_TRACE(60);
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-  AT_TRACE(61);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -899,7 +929,7 @@ extern "C" int x2k_attn_bwd(const X2kAttnArgs* args, void* stream_) {
     attr_set = true;
   }
   dim3 grid(a.H, a.B);
-  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, tds, p);
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, tds, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;
@@ -967,6 +997,6 @@ extern "C" int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H
 
 #ifdef X2K_ATTN_TRACE
 extern "C" int x2k_debug_attn_trace(long long* out128) {
-  return cudaMemcpyFromSymbol(out128, g_attn_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(out128, g_attn_trace, sizeof(long long) * 192) == cudaSuccess ? 0 : -2;
 }
 #endif

@@ -64,6 +64,7 @@ struct PackParams {
   // shared-memory byte offsets (from the 1024-aligned base)
   uint32_t off_do, off_k, off_v, off_p, off_ds, off_red, off_bar;
   uint32_t tmem_cols;
+  uint32_t tm_dk, tm_dv;  // backward: first TMEM column of the dK / dV accumulators
 };
 
 // byte offset of the 16-byte chunk holding elements [k0, k0+8) of row `row` inside a K-major, 128B-swizzled tile
@@ -119,6 +120,38 @@ __device__ __forceinline__ void store_row_part(__nv_bfloat16* dst_row, uint32_t 
   if (valid) {
     store16_bf16(dst_row + part * W, a, mul);
     if (W == 32) store16_bf16(dst_row + part * W + 16, b, mul);
+  }
+}
+
+// TMEM lane (this thread's row) -> 64 / NPART fp32 columns starting at part * (64 / NPART) -> scaled bf16 -> the row's
+// 16-byte chunks of a 128B-swizzled [rows x 64] staging tile (rows 128 B apart, tile base 1024-aligned): what a TMA
+// store with SWIZZLE_128B expects.  The gradients leave the SM as whole tiles instead of 32 scattered 16-byte stores
+// per warp instruction (the drains were a quarter of the backward CTA's life, tools/trace_attn.py).
+template <int NPART>
+__device__ __forceinline__ void stage_row_part(uint32_t tile_addr, int row, uint32_t tcol_addr, int part, float mul,
+                                               bool valid) {
+  constexpr int W = 64 / NPART;  // 32 or 16 columns
+  uint32_t a[16], b[16];
+  tmem_ld_32x16(tcol_addr + part * W, a);
+  if (W == 32) tmem_ld_32x16(tcol_addr + part * W + 16, b);
+  tmem_wait_ld();
+  if (!valid) return;  // the row lies outside the staging tile (or must keep its zero padding)
+  const uint32_t base = tile_addr + row * 128;
+  const int c0 = (part * W) >> 3;  // first 16-byte chunk of this part
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    st_shared_v4(base + (((c0 + i) ^ (row & 7)) << 4), pack_bf16x2(__uint_as_float(a[8 * i]) * mul, __uint_as_float(a[8 * i + 1]) * mul),
+                 pack_bf16x2(__uint_as_float(a[8 * i + 2]) * mul, __uint_as_float(a[8 * i + 3]) * mul),
+                 pack_bf16x2(__uint_as_float(a[8 * i + 4]) * mul, __uint_as_float(a[8 * i + 5]) * mul),
+                 pack_bf16x2(__uint_as_float(a[8 * i + 6]) * mul, __uint_as_float(a[8 * i + 7]) * mul));
+  if (W == 32) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      st_shared_v4(base + (((c0 + 2 + i) ^ (row & 7)) << 4),
+                   pack_bf16x2(__uint_as_float(b[8 * i]) * mul, __uint_as_float(b[8 * i + 1]) * mul),
+                   pack_bf16x2(__uint_as_float(b[8 * i + 2]) * mul, __uint_as_float(b[8 * i + 3]) * mul),
+                   pack_bf16x2(__uint_as_float(b[8 * i + 4]) * mul, __uint_as_float(b[8 * i + 5]) * mul),
+                   pack_bf16x2(__uint_as_float(b[8 * i + 6]) * mul, __uint_as_float(b[8 * i + 7]) * mul));
   }
 }
 
@@ -366,15 +399,18 @@ attn_pack_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // TMEM (512 columns): X = [0,256) holds S and dP (side by side when N <= 128, one after the other when
 // N > 128) and afterwards dQ; dK tiles at 256 + 64t, dV tiles at 384 + 64t (t = key tile of 128).
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t TM_DK = 256, TM_DV = 384;
 
 template <int NPART>
 __global__ void __launch_bounds__(NPART * 128, 1)
 attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                     const PackParams p) {
+                     const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
+                     const __grid_constant__ CUtensorMap tmap_dv, const PackParams p) {
   const int grp = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // MMA issue runs warp-converged in warp 0 (index through a shuffle: provably uniform) with the instruction under
+  // elect.sync, so that descriptors live in uniform registers (tools/mma_bench.cu: 58-67 instead of 91 cycles per MMA)
+  const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
   const int quad = warp & 3, part = warp >> 2;
   const int row = quad * 32 + lane;
   constexpr int NT = NPART * 128;
@@ -424,7 +460,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
   __syncwarp();
   if (warp == 0) {
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
   zero_smem(sbase + q_rows * 128, (128 - q_rows) * 128, threadIdx.x, NT);
@@ -459,6 +495,7 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int bs[PK_MAX_G];
 #pragma unroll
       for (int g = 0; g < PK_MAX_G; ++g) bs[g] = item_seq(p, item, g);
+      if (ci > 0) tma_store_wait_read();  // the previous item's dQ store has read its staging tile (= the Q tile)
       mbar_arrive_expect_tx(bar_q, 2 * q_rows * 128);
 #pragma unroll
       for (int g = 0; g < PK_MAX_G; ++g) {
@@ -490,23 +527,24 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
     PK_TRACE(3 + ci * 10);
-    if (threadIdx.x == 0) {
+    if (issuer_warp) {
       if (ci == 0) mbar_wait(bar_kv, 0);
       mbar_wait(bar_q, ci & 1);
       tc_fence_after();
       PK_TRACE(4 + ci * 10);
+      const uint64_t dq_ = make_smem_desc(aq, 16, 1024), dk_ = make_smem_desc(ak, 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s, k != 0);
+        if (elect_one()) umma_bf16(tmem, dq_ + 2 * k, dk_ + 2 * k, idesc_s, k != 0);
       if (dual) {
+        const uint64_t ddo = make_smem_desc(ado, 16, 1024), dv_ = make_smem_desc(av, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + 128, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024), idesc_s,
-                    k != 0);
+          if (elect_one()) umma_bf16(tmem + 128, ddo + 2 * k, dv_ + 2 * k, idesc_s, k != 0);
       }
-      umma_commit(bar_mma);
+      if (elect_one()) umma_commit(bar_mma);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait_warp(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
@@ -575,14 +613,15 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // ---- dP = dO · Vᵀ into the columns S occupied, then pass 2: dS = P ∘ (dP·keep − delta) ----
       tc_fence_before();
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (issuer_warp) {
         tc_fence_after();
+        const uint64_t ddo = make_smem_desc(ado, 16, 1024), dv_ = make_smem_desc(av, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024), idesc_s, k != 0);
-        umma_commit(bar_mma);
+          if (elect_one()) umma_bf16(tmem, ddo + 2 * k, dv_ + 2 * k, idesc_s, k != 0);
+        if (elect_one()) umma_commit(bar_mma);
+        __syncwarp();
       }
-      __syncwarp();
       mbar_wait_warp(bar_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
@@ -619,60 +658,81 @@ attn_pack_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();
     PK_TRACE(9 + ci * 10);
 
-    if (threadIdx.x == 0) {
+    if (issuer_warp) {
       tc_fence_after();
       // dQ = dS · K      (A: dS K-major over keys; B: K tile MN-major, N = 64 dims) -> X[0,64)
-      for (int ks = 0; ks < nchunk; ++ks)
-        umma_bf16(tmem, make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                  make_smem_desc(ak + ks * 2048, 8192, 1024), idesc_dq, ks != 0);
+      {
+        const uint64_t db0 = make_smem_desc(ak, 8192, 1024);
+        for (int ks = 0; ks < nchunk; ++ks) {
+          const uint64_t da = make_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+          if (elect_one()) umma_bf16(tmem, da, db0 + ks * 128, idesc_dq, ks != 0);
+        }
+      }
       // dK[t] += dSᵀ · Q, dV[t] += Pᵀ · dO   (A: dS / P MN-major over keys, K = query rows; B: Q / dO MN-major)
       const int nqc = (q_rows + 15) >> 4;
       for (int t = 0; t < ntile; ++t) {
+        const uint64_t das = make_smem_desc(ads + t * 32768, 16384, 1024), dbq = make_smem_desc(aq, 8192, 1024);
         for (int ks = 0; ks < nqc; ++ks)
-          umma_bf16(tmem + TM_DK + t * 64, make_smem_desc(ads + t * 32768 + ks * 2048, 16384, 1024),
-                    make_smem_desc(aq + ks * 2048, 8192, 1024), idesc_dkv, (ci | ks) != 0);
+          if (elect_one()) umma_bf16(tmem + p.tm_dk + t * 64, das + ks * 128, dbq + ks * 128, idesc_dkv, (ci | ks) != 0);
+        const uint64_t dap = make_smem_desc(ap + t * 32768, 16384, 1024), dbo = make_smem_desc(ado, 8192, 1024);
         for (int ks = 0; ks < nqc; ++ks)
-          umma_bf16(tmem + TM_DV + t * 64, make_smem_desc(ap + t * 32768 + ks * 2048, 16384, 1024),
-                    make_smem_desc(ado + ks * 2048, 8192, 1024), idesc_dkv, (ci | ks) != 0);
+          if (elect_one()) umma_bf16(tmem + p.tm_dv + t * 64, dap + ks * 128, dbo + ks * 128, idesc_dkv, (ci | ks) != 0);
       }
-      umma_commit(bar_mma);
+      if (elect_one()) umma_commit(bar_mma);
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait_warp(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
     PK_TRACE(10 + ci * 10);
-    if (warp_live)
-      store_row_part<NPART>(p.dq + (static_cast<int64_t>(ri.b) * p.Lq + ri.q) * p.ld_dq + h * 64, trow, part, p.scale, ri.ok);
+    // dQ rows -> bf16 staging in the (now idle) Q tile -> one TMA store per sequence slot (rows past Lq are clipped)
+    if (warp_live) stage_row_part<NPART>(aq, row, trow, part, p.scale, row < q_rows);
+    fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();  // X, Q, dO, P, dS are free for the next item
+    __syncthreads();  // X, dO, P, dS are free for the next item; the Q tile once the bulk store has read it
     tc_fence_after();
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < p.G; ++g) {
+        const int bq = item_seq(p, item, g);
+        if (bq >= 0) tma_store_3d(&tmap_dq, aq + g * p.Lq8 * 128, h * 64, 0, bq);
+      }
+      tma_store_commit();
+    }
     PK_TRACE(11 + ci * 10);
   }
 
   // ---- drain dK / dV: thread == key row of tile t, each part stores 64 / NPART of the 64 dims ----
+  // thread == key row of tile t: bf16 rows staged in the (dead) K / V tiles, written by TMA stores — cross: the source's
+  // whole [N x 64] tile (rows past Lk clipped); self: one [Lk8 x 64] box per sequence slot
   for (int t = 0; t < ntile; ++t) {
-    const int key = t * 128 + row;
-    bool kvalid;
-    int64_t r;
-    if (p.cross) {
-      kvalid = key < p.Lk;
-      r = static_cast<int64_t>(grp) * p.Lk + key;
-    } else {
-      const int g = key / p.Lk8, kk = key - g * p.Lk8;
-      const int b = item_seq(p, first_item, g);
-      kvalid = key < N && b >= 0 && kk < p.Lk;
-      r = static_cast<int64_t>(b) * p.Lk + kk;
-    }
-    store_row_part<NPART>(p.dk + r * p.ld_dk + h * 64, trow + TM_DK + t * 64, part, p.scale, kvalid);
-    store_row_part<NPART>(p.dv + r * p.ld_dv + h * 64, trow + TM_DV + t * 64, part, 1.0f, kvalid);
+    const int key = t * 128 + row;  // row of the K / V tile in shared memory (rows are 128 B apart in both modes)
+    stage_row_part<NPART>(ak + t * 16384, row, trow + p.tm_dk + t * 64, part, p.scale, key < N);
+    stage_row_part<NPART>(av + t * 16384, row, trow + p.tm_dv + t * 64, part, 1.0f, key < N);
   }
   PK_TRACE(62);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p.cross) {
+      tma_store_3d(&tmap_dk, ak, h * 64, 0, grp);
+      tma_store_3d(&tmap_dv, av, h * 64, 0, grp);
+    } else {
+      for (int g = 0; g < p.G; ++g) {
+        const int bk = item_seq(p, first_item, g);
+        if (bk >= 0) {
+          tma_store_3d(&tmap_dk, ak + g * p.Lk8 * 128, h * 64, 0, bk);
+          tma_store_3d(&tmap_dv, av + g * p.Lk8 * 128, h * 64, 0, bk);
+        }
+      }
+    }
+    tma_store_commit();
+    tma_store_wait_read();  // shared memory must stay intact until the bulk stores (dQ of the last item too) have read it
+  }
   if (warp == 0) {
+    __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, p.tmem_cols);
   }
   PK_TRACE(63);
 }
@@ -826,6 +886,8 @@ int attn_pack_plan(const X2kAttnArgs& a, bool backward, PackParams& p) {
     p.off_red = p.off_ds + p_bytes;
     p.off_bar = p.off_red;
     p.tmem_cols = 512;
+    p.tm_dk = 256;
+    p.tm_dv = 384;
   }
   return 1;
 }
@@ -866,6 +928,13 @@ int attn_pack_bwd_launch(const X2kAttnArgs& a, PackParams& p, cudaStream_t strea
   if ((rc = make_tmap_bf16_2d(&tk, a.k, kv_rows, static_cast<uint64_t>(a.H) * 64, a.ld_k, kbox, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, a.v, kv_rows, static_cast<uint64_t>(a.H) * 64, a.ld_v, kbox, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, a.d_o, static_cast<uint64_t>(a.B) * a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_do, p.Lq8, 64))) return rc;
+  // gradients leave as TMA stores of whole staging tiles; the per-sequence views clip the rows past Lq / Lk
+  CUtensorMap tdq, tdk, tdv;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  X2K_REQUIRE(al16(a.dq) && al16(a.dk) && al16(a.dv), "x2k_attn_bwd (packed): dq / dk / dv must be 16-byte aligned");
+  if ((rc = make_tmap_bf16_seq3d(&tdq, a.dq, a.B, a.Lq, static_cast<uint64_t>(a.H) * 64, a.ld_dq, p.Lq8))) return rc;
+  if ((rc = make_tmap_bf16_seq3d(&tdk, a.dk, p.n_kv, a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_dk, kbox))) return rc;
+  if ((rc = make_tmap_bf16_seq3d(&tdv, a.dv, p.n_kv, a.Lk, static_cast<uint64_t>(a.H) * 64, a.ld_dv, kbox))) return rc;
   const int smem = p.off_bar + 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -876,9 +945,9 @@ int attn_pack_bwd_launch(const X2kAttnArgs& a, PackParams& p, cudaStream_t strea
   X2K_REQUIRE(smem <= 227 * 1024, "x2k_attn_bwd (packed): %d bytes of shared memory", smem);
   dim3 grid(p.cross ? p.n_kv : (a.B + p.G - 1) / p.G, a.H);
   if (pack_parts(true) == 4)
-    attn_pack_bwd_kernel<4><<<grid, 512, smem, stream>>>(tq, tk, tv, tdo, p);
+    attn_pack_bwd_kernel<4><<<grid, 512, smem, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   else
-    attn_pack_bwd_kernel<2><<<grid, 256, smem, stream>>>(tq, tk, tv, tdo, p);
+    attn_pack_bwd_kernel<2><<<grid, 256, smem, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   X2K_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return X2K_OK;

@@ -66,6 +66,11 @@ def attn_names():
     return names
 
 
+def fwd_names():
+    return dict(enumerate(["start", "prologue done, S MMAs issued (thread 0)", "S ready", "pass 1 done (bias, max)", "synced", "pass 2 done (exp, P)",
+                           "sums exchanged, P·V issued", "O ready", "O stored", "end"]))
+
+
 only = os.environ.get("X2K_ATTN_CASE")
 for case, fn, names in (("beit", "x2k_debug_attn_trace", attn_names()), ("fus-self", "x2k_debug_pack_trace", pack_names()),
                         ("cross", "x2k_debug_pack_trace", pack_names())):
@@ -76,6 +81,10 @@ for case, fn, names in (("beit", "x2k_debug_attn_trace", attn_names()), ("fus-se
     runpy.run_path(os.path.join(ROOT, "tools", "profile_attn.py"))
     torch.cuda.synchronize()
     print("TRACE", case)
+    if case == "beit":
+        print(" forward (attn_fwd_kernel)")
+        dump("x2k_debug_attn_fwd_trace", fwd_names())
+        print(" backward (attn_bwd_kernel)")
     if case == "beit":
         dump(fn, names, (("thread 0", 0), ("thread 200", 64), ("thread 256 (MMA warp)", 128)))
     else:

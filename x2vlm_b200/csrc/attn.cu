@@ -21,6 +21,61 @@
 namespace x2k {
 namespace {
 
+// Bias block [32 rows x 32 cols] fp32 of one warp in two steps, so the L2 latency of the loads hides behind an MMA wait
+// or the previous unit's math: issue (8 coalesced LDG.128 per lane, 4 rows x 128 B per instruction) ... stage (into the
+// warp's 4 KB XOR-swizzled tile) ... read (every thread picks up 16 values of ITS row per 16-column chunk).
+__device__ __forceinline__ void bias_issue(const float* __restrict__ base, int64_t row_stride, int rows_left, int lane,
+                                           float4 (&v)[8]) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const int rc = r < rows_left ? r : (rows_left - 1);
+    v[i] = __ldg(reinterpret_cast<const float4*>(base + rc * row_stride) + ch);
+  }
+}
+__device__ __forceinline__ void bias_stage(const float4 (&v)[8], uint32_t stage_addr, int lane) {
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr + r * 128 + ((ch ^ (r & 7)) << 4)), "f"(v[i].x),
+                 "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
+                 : "memory");
+  }
+  __syncwarp();
+}
+// the 16 values of this thread's row for 16-column chunk `v` (0 / 1) of the staged 32-column block
+__device__ __forceinline__ void bias_read16(uint32_t stage_addr, int lane, int v, float (&out)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float4 w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                 : "r"(stage_addr + lane * 128 + (((4 * v + c) ^ (lane & 7)) << 4))
+                 : "memory");
+    out[4 * c] = w.x; out[4 * c + 1] = w.y; out[4 * c + 2] = w.z; out[4 * c + 3] = w.w;
+  }
+}
+
+// Optional phase trace (compile with -DX2K_ATTN_TRACE): clock64 stamps of one CTA, read back by x2k_debug_attn_trace.
+#ifdef X2K_ATTN_TRACE
+__device__ long long g_attn_trace[3][64];
+__device__ long long g_attn_fwd_trace[2][64];
+#define AT_TRACE(i)                                                                           \
+  do {                                                                                        \
+    if (blockIdx.x == 5 && blockIdx.y == 40 && (threadIdx.x == 0 || threadIdx.x == 200 || threadIdx.x == 256)) \
+      g_attn_trace[threadIdx.x == 0 ? 0 : threadIdx.x == 200 ? 1 : 2][(i)] = clock64();       \
+  } while (0)
+#define FT_TRACE(i)                                                                           \
+  do {                                                                                        \
+    if (blockIdx.x == 0 && blockIdx.y == 5 && blockIdx.z == 40 && (threadIdx.x == 0 || threadIdx.x == 200)) \
+      g_attn_fwd_trace[threadIdx.x == 0 ? 0 : 1][(i)] = clock64();                            \
+  } while (0)
+#else
+#define AT_TRACE(i) do {} while (0)
+#define FT_TRACE(i) do {} while (0)
+#endif
 // ---------------------------------------------------------------------------------------------
 // forward: grid (q tiles, H, B), 256 threads, 2 CTAs / SM (TMEM 256 columns, ~101 KB smem each)
 // ---------------------------------------------------------------------------------------------
@@ -47,6 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  FT_TRACE(0);
   const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int Lk_pad = p.Lk_pad;
 
@@ -79,9 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
-  mbar_wait_warp(bar_mma, 0);
-  tc_fence_after();
-
+  FT_TRACE(1);
   // ---- softmax: pass 1 forms t = scale·qk + bias + mask (log2 domain), row max, writes t back to TMEM ----
   const int q = qt * 128 + row;
   const bool qvalid = q < p.Lq;
@@ -96,37 +150,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int u_begin = half == 0 ? 0 : (nunit + 1) >> 1;
   const int u_end = half == 0 ? (nunit + 1) >> 1 : nunit;
   const uint32_t sP_addr = smem_u32(sP);
+  float4 bv[8];  // first bias block of this warp's rows: in flight while S is being formed
+  if (bias_blk && u_begin < u_end) bias_issue(bias_blk + u_begin * 32, p.bias_q_stride, p.Lq - q_warp0, lane, bv);
+  mbar_wait_warp(bar_mma, 0);
+  tc_fence_after();
+  FT_TRACE(2);
+
   float mx = -INFINITY, sum = 0.f;
   if (warp_live) {
     for (int u = u_begin; u < u_end; ++u) {
-      const bool two = (2 * u + 1) < nchunk;  // the last unit may hold a single chunk
-      uint32_t s0[16], s1[16];
-      tmem_ld_32x16(trow + u * 32, s0);
-      if (two) tmem_ld_32x16(trow + u * 32 + 16, s1);
-      float add[32];
-      additive32(p, bias_blk, p.Lq - q_warp0, mask_row, u * 32, stage_addr, lane, add);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float t = (u * 32 + j < p.Lk) ? fmaf(__uint_as_float(s0[j]), p.scale_log2, add[j]) : -INFINITY;
-        mx = fmaxf(mx, t);
-        s0[j] = __float_as_uint(t);
+      if (bias_blk) {  // this unit's bias block was requested before the wait for S / during the previous unit
+        bias_stage(bv, stage_addr, lane);
+        if (u + 1 < u_end) bias_issue(bias_blk + (u + 1) * 32, p.bias_q_stride, p.Lq - q_warp0, lane, bv);
       }
-      tmem_st_32x16(trow + u * 32, s0);
-      if (two) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int c = 2 * u + v;
+        if (c >= nchunk) break;  // warp-uniform: the last unit may hold a single chunk
+        uint32_t s0[16];
+        tmem_ld_32x16(trow + c * 16, s0);
+        float add[16];
+        if (bias_blk) {
+          bias_read16(stage_addr, lane, v, add);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) add[j] = 0.f;
+        }
+        if (mask_row) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask_row + c * 16 + j));
+            add[j] += m.x; add[j + 1] += m.y; add[j + 2] += m.z; add[j + 3] += m.w;
+          }
+        }
+        tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float t = (u * 32 + 16 + j < p.Lk) ? fmaf(__uint_as_float(s1[j]), p.scale_log2, add[16 + j]) : -INFINITY;
+          const float t = (c * 16 + j < p.Lk) ? fmaf(__uint_as_float(s0[j]), p.scale_log2, add[j] * kLog2e) : -INFINITY;
           mx = fmaxf(mx, t);
-          s1[j] = __float_as_uint(t);
+          s0[j] = __float_as_uint(t);
         }
-        tmem_st_32x16(trow + u * 32 + 16, s1);
+        tmem_st_32x16(trow + c * 16, s0);
       }
+      if (bias_blk) __syncwarp();  // the staging tile is rewritten by the next unit
     }
     tmem_wait_st();
     s_red[half * 128 + row] = mx;
   }
+  FT_TRACE(3);
   __syncthreads();  // max exchange; the bias staging area is free from here on
+  FT_TRACE(4);
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_v, Lk_pad * 128);
     tma_load_2d(sV, &tmap_v, bar_v, h * 64, kvb * p.Lk);  // lands while pass 2 runs
@@ -170,6 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   }
+  FT_TRACE(5);
   __syncthreads();  // every thread has read the partner's max before the slots are reused for the sums
   if (warp_live) s_red[half * 128 + row] = sum;
   fence_proxy_async_smem();
@@ -191,8 +265,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
+  FT_TRACE(6);
   mbar_wait_warp(bar_mma, 1);
   tc_fence_after();
+  FT_TRACE(7);
   if (warp_live) {  // each half writes 32 of the 64 output dims of its rows
     const float tot = sum + s_red[(half ^ 1) * 128 + row];
     const float inv = tot > 0.f ? 1.0f / tot : 0.f;
@@ -200,28 +276,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     store_row_bf16<2>(dst, trow + half * 32, inv, qvalid);
     if (qvalid && half == 0) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = mx + log2f(tot);
   }
+  FT_TRACE(8);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
+  FT_TRACE(9);
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward: grid (H, B), 384 threads (8 compute warps + MMA warp + store warp), 1 CTA / SM (TMEM 512 columns)
 // ---------------------------------------------------------------------------------------------
-// Optional phase trace (compile with -DX2K_ATTN_TRACE): clock64 stamps of one CTA, read back by x2k_debug_attn_trace.
-#ifdef X2K_ATTN_TRACE
-__device__ long long g_attn_trace[3][64];
-#define AT_TRACE(i)                                                                           \
-  do {                                                                                        \
-    if (blockIdx.x == 5 && blockIdx.y == 40 && (threadIdx.x == 0 || threadIdx.x == 200 || threadIdx.x == 256)) \
-      g_attn_trace[threadIdx.x == 0 ? 0 : threadIdx.x == 200 ? 1 : 2][(i)] = clock64();       \
-  } while (0)
-#else
-#define AT_TRACE(i) do {} while (0)
-#endif
 constexpr int BWD_SQ = 0, BWD_SDO = 32768, BWD_SK = 65536, BWD_SV = 98304, BWD_SP = 131072, BWD_SDS = 163840;
 constexpr int BWD_STAGE = 196608;  // bias staging, 8 warps x 4 KB
 constexpr int BWD_BARS = BWD_STAGE + 32768;
@@ -255,43 +322,6 @@ __device__ __forceinline__ BwdTile bwd_tile(const AttnParams& p, int t, int nqb,
                    ? p.bias + h * p.bias_h_stride + static_cast<int64_t>(g.q_warp0) * p.bias_q_stride + g.kb * 128
                    : nullptr;
   return g;
-}
-
-// Bias block [32 rows x 32 cols] fp32 of one warp in two steps, so the L2 latency of the loads hides behind an MMA wait
-// or the previous unit's math: issue (8 coalesced LDG.128 per lane, 4 rows x 128 B per instruction) ... stage (into the
-// warp's 4 KB XOR-swizzled tile) ... read (every thread picks up 16 values of ITS row per 16-column chunk).
-__device__ __forceinline__ void bias_issue(const float* __restrict__ base, int64_t row_stride, int rows_left, int lane,
-                                           float4 (&v)[8]) {
-  const int sub = lane >> 3, ch = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + sub;
-    const int rc = r < rows_left ? r : (rows_left - 1);
-    v[i] = __ldg(reinterpret_cast<const float4*>(base + rc * row_stride) + ch);
-  }
-}
-__device__ __forceinline__ void bias_stage(const float4 (&v)[8], uint32_t stage_addr, int lane) {
-  const int sub = lane >> 3, ch = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + sub;
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr + r * 128 + ((ch ^ (r & 7)) << 4)), "f"(v[i].x),
-                 "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
-                 : "memory");
-  }
-  __syncwarp();
-}
-// the 16 values of this thread's row for 16-column chunk `v` (0 / 1) of the staged 32-column block
-__device__ __forceinline__ void bias_read16(uint32_t stage_addr, int lane, int v, float (&out)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float4 w;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                 : "r"(stage_addr + lane * 128 + (((4 * v + c) ^ (lane & 7)) << 4))
-                 : "memory");
-    out[4 * c] = w.x; out[4 * c + 1] = w.y; out[4 * c + 2] = w.z; out[4 * c + 3] = w.w;
-  }
 }
 
 // TMEM row (this thread's lane) -> 32 fp32 columns -> scaled bf16 -> the thread's row of a 128B-swizzled [128 x 64]
@@ -996,6 +1026,9 @@ extern "C" int x2k_relpos_bias_scatter(const void* ds_bf16, int32_t B, int32_t H
 }
 
 #ifdef X2K_ATTN_TRACE
+extern "C" int x2k_debug_attn_fwd_trace(long long* out128) {
+  return cudaMemcpyFromSymbol(out128, g_attn_fwd_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+}
 extern "C" int x2k_debug_attn_trace(long long* out128) {
   return cudaMemcpyFromSymbol(out128, g_attn_trace, sizeof(long long) * 192) == cudaSuccess ? 0 : -2;
 }

@@ -196,19 +196,33 @@ def run_ours(args):
         host_batch = {"i": ib_h, "r": rb_h} if rb_h is not None else {"i": ib_h}
         if e2e and graphed is not None:
             graphed.stage(host_batch)  # step 0's inputs: this copy is exposed, the later ones overlap the previous replay
+            loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            loss_evt = [torch.cuda.Event() for _ in range(2)]
+            pending = None
         for it in range(n):
             if e2e:
                 if graphed is not None:
                     # every step: pinned host batch -> staging buffers (copy stream, prefetched during the previous
-                    # replay like a data loader would) -> the graph's static buffers -> replay -> loss read on the host
+                    # replay like a data loader would) -> the graph's static buffers -> replay -> the step's loss copied
+                    # to pinned host memory.  The host reads step k's loss after it has queued step k + 1 (one step of
+                    # logging delay): a sync before the next launch would leave the GPU idle for the launch latency of an
+                    # 8 000-node graph every step (measured: +4.4 ms / step on some boxes).
                     loss_t = graphed.run_staged()
+                    loss_host[it & 1].copy_(loss_t.detach().reshape(()), non_blocking=True)
+                    loss_evt[it & 1].record()
                     if it + 1 < n:
                         graphed.stage(host_batch)
-                    last = float(loss_t)
+                    if pending is not None:
+                        loss_evt[pending].synchronize()
+                        last = float(loss_host[pending])
+                    pending = it & 1
                 else:
                     last = step(to_dev(ib_h, dev), to_dev(rb_h, dev) if rb_h is not None else None, True)
             else:
                 last = step(ib_d, rb_d, False)
+        if e2e and graphed is not None and pending is not None:
+            loss_evt[pending].synchronize()
+            last = float(loss_host[pending])
         en.record()
         host_ms[0] = (time.perf_counter() - t_host) * 1e3 / n  # CPU time to enqueue a step (no sync inside unless e2e)
         torch.cuda.synchronize()

@@ -89,6 +89,27 @@ def giou_pairs(b1, b2):
     return inter / union - (area - union) / area
 
 
+class _GatherRowsFn(torch.autograd.Function):
+    """rows = x.view(-1, D)[idx]; backward = one zero fill + one index_add (idx may repeat: padded mask slots)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = x.shape
+        return x.reshape(-1, x.shape[-1]).index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        d = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        d.view(-1, ctx.shape[-1]).index_add_(0, idx, g)
+        return d, None
+
+
+def _gather_rows(x, idx):
+    return _GatherRowsFn.apply(x, idx)
+
+
 def _itm_labels(bs, device):
     """[1]*bs + [0]*2bs (models/xvlm.py:895-897), built on the device: a pageable host-to-device copy would be a
     hidden sync and is illegal inside CUDA-graph capture."""
@@ -382,22 +403,33 @@ class XVLM(nn.Module):
             enc += [emb_r, full[Bi:]]
         cross = self.get_cross_embeds(torch.cat(enc), torch.cat(iatt), text_embeds=torch.cat(txt), text_atts=torch.cat(tatt),
                                       encoder_kv_index=torch.cat(kv).to(torch.int32))
-        labels_i = _itm_labels(Bi, dev)
-        itm_logits_i = self.itm_head(cross[:3 * Bi, 0])
-        losses["image"]["loss_itm"] = F.cross_entropy(itm_logits_i, labels_i)
-        mlm_seq = [cross[3 * Bi:4 * Bi]]
+        # Every head reads a few rows of the [576, L, D] fusion output (cls tokens, masked positions).  Slicing it five
+        # times makes autograd build five full-size zero gradients and add them up (9 passes over 70 MB); ONE gather of
+        # all the rows the heads need has a backward of one fill + one index_add.
+        L = cross.shape[1]
+        o = 4 * Bi
         mpos, mids = [ib["masked_pos"]], [ib["masked_ids"]]
+        cls_seq = [torch.arange(0, 3 * Bi, device=dev)]
+        mlm_rows = [((3 * Bi + ar_i) * L).unsqueeze(1) + ib["masked_pos"]]
         if has_r:
-            o = 4 * Bi
-            labels_r = _itm_labels(Br, dev)
-            losses["region"]["loss_itm"] = F.cross_entropy(self.itm_head(cross[o:o + 3 * Br, 0]), labels_r)
-            mlm_seq.append(cross[o + 3 * Br:o + 4 * Br])
+            cls_seq += [torch.arange(o, o + 3 * Br, device=dev), torch.arange(o + 4 * Br, o + 5 * Br, device=dev)]
+            mlm_rows.append(((o + 3 * Br + ar_r) * L).unsqueeze(1) + rb["masked_pos"])
             mpos.append(rb["masked_pos"]); mids.append(rb["masked_ids"])
-            coord = self.bbox_head(cross[o + 4 * Br:o + 5 * Br, 0]).sigmoid()
+        n_cls = 3 * Bi + (4 * Br if has_r else 0)
+        rows = _gather_rows(cross, torch.cat([torch.cat(cls_seq) * L] + [m.reshape(-1) for m in mlm_rows]))
+        cls_rows = rows[:n_cls]
+        labels_i = _itm_labels(Bi, dev)
+        itm_logits_i = self.itm_head(cls_rows[:3 * Bi])
+        losses["image"]["loss_itm"] = F.cross_entropy(itm_logits_i, labels_i)
+        if has_r:
+            labels_r = _itm_labels(Br, dev)
+            losses["region"]["loss_itm"] = F.cross_entropy(self.itm_head(cls_rows[3 * Bi:3 * Bi + 3 * Br]), labels_r)
+            coord = self.bbox_head(cls_rows[3 * Bi + 3 * Br:]).sigmoid()
             losses["region"]["loss_bbox"], losses["region"]["loss_giou"] = self.get_bbox_loss(
                 coord, rb["target_bbox"], is_image=rb["is_image"])
         # ---- MLM head once over the masked positions of both sub-batches ----
-        seq = self.text_encoder.gather_seq_out_by_pos(torch.cat(mlm_seq), torch.cat(mpos))
+        n_pos = mpos[0].shape[1]
+        seq = rows[n_cls:].view(-1, n_pos, rows.shape[-1])
         # vocabulary GEMM fused with the cross entropy: per-position losses (0 where the target is -100) without the
         # [positions, 30522] logits; then the two means
         tgt = torch.cat(mids).reshape(-1)

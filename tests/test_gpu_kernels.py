@@ -177,6 +177,9 @@ def _heads(x, B, L, H):
 
 
 @pytest.mark.parametrize("case", ["beit", "text", "text3d", "cross_shared", "text_dropout", "n256",
+                                  # whole-range kernels (attn.cu) beyond the BEiT shape: one tile with key mask + dropout,
+                                  # 2 x 2 tiles with a per-query mask + dropout, two query tiles over one shared key block
+                                  "self100_dropout", "causal200_dropout", "q200_k72_shared",
                                   # key-blocked online-softmax kernels (attn_long.cu): 384 px / 768 px fine-tuning shapes
                                   "beit577", "beit2305", "cross577_shared_dropout", "causal300", "cross2305"])
 def test_attention_fwd_bwd(dev, case):
@@ -193,6 +196,15 @@ def test_attention_fwd_bwd(dev, case):
     elif case == "cross_shared":
         B, Lq, Lk, n_kv = 7, 40, 197, 3
         kv_index = torch.tensor([0, 2, 1, 1, 0, 2, 2], device=dev, dtype=torch.int32)
+    elif case == "self100_dropout":
+        B, Lq, Lk, n_kv, H = 3, 100, 100, 3, 4
+        p_drop = 0.1
+    elif case == "causal200_dropout":
+        B, Lq, Lk, n_kv, H = 2, 200, 200, 2, 4
+        p_drop = 0.1
+    elif case == "q200_k72_shared":
+        B, Lq, Lk, n_kv, H = 5, 200, 72, 2, 4
+        kv_index = torch.tensor([1, 0, 0, 1, 1], device=dev, dtype=torch.int32)
     elif case == "beit577":      # 384 px: 24 x 24 patches + cls, dense rel-pos bias streamed per key block
         B, Lq, Lk, n_kv, H = 2, 577, 577, 2, 2
     elif case == "beit2305":     # 768 px: 48 x 48 patches + cls (configs/finetune/vqa2_base.yaml)
@@ -223,10 +235,10 @@ def test_attention_fwd_bwd(dev, case):
     per_query = False
     if case in ("beit", "n256", "beit577", "beit2305"):
         bias = torch.zeros(H, Lq, ld, device=dev); bias[:, :, :Lk] = torch.randn(H, Lq, Lk, device=dev, generator=g)
-    if case in ("text", "text_dropout", "cross_shared", "cross577_shared_dropout", "cross2305"):
+    if case in ("text", "text_dropout", "cross_shared", "cross577_shared_dropout", "cross2305", "self100_dropout", "q200_k72_shared"):
         m01 = (torch.rand(B, Lk, device=dev, generator=g) > 0.3).float(); m01[:, 0] = 1
         mask = torch.zeros(B, ld, device=dev); mask[:, :Lk] = (1 - m01) * -10000.0
-    if case in ("text3d", "causal300"):
+    if case in ("text3d", "causal300", "causal200_dropout"):
         m01 = torch.tril(torch.ones(Lq, Lk, device=dev)).expand(B, -1, -1)
         mask = torch.zeros(B, Lq, ld, device=dev); mask[:, :, :Lk] = (1 - m01) * -10000.0
         per_query = True

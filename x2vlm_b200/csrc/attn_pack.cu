@@ -815,15 +815,18 @@ attn_group_build_kernel(const int32_t* __restrict__ kv_index, int B, int n_kv, i
 }
 
 // threads per CTA / 128 = how many warps share a TMEM lane quadrant (each takes a column part of the rows).
-// Measured on B200 (gpurun_out s3_attn_ab): 2 parts win for the 40-token self-attention shapes (53 vs 60 us fwd, 121 vs
-// 132 us bwd at B=256) and tie for cross-attention, so 2 is the default.
+// Measured on B200 (tools/profile_attn.py, round 2, after the drains became TMA stores): the FORWARD is faster with 2 parts
+// (57.9 / 90.5 / 171.5 us against 65.2 / 109.9 / 172.2 us with 4 for text B=256, fusion self B=576, grouped cross B=576: two
+// 256-thread CTAs share an SM), the BACKWARD with 4 (117.6 / 214.3 / 343.7 us against 126.0 / 228.5 / 395.3 us: one CTA per SM,
+// the softmax / dS passes are its longest phases and split four ways).
 // Tuning override: X2K_PACK_PARTS_FWD / X2K_PACK_PARTS_BWD = 2 | 4 (read once).
 int pack_parts(bool backward) {
   static int cached[2] = {0, 0};
   int& c = cached[backward ? 1 : 0];
   if (c == 0) {
     const char* e = getenv(backward ? "X2K_PACK_PARTS_BWD" : "X2K_PACK_PARTS_FWD");
-    c = (e && atoi(e) == 4) ? 4 : 2;
+    const int dflt = backward ? 4 : 2;
+    c = (e && (atoi(e) == 2 || atoi(e) == 4)) ? atoi(e) : dflt;
   }
   return c;
 }

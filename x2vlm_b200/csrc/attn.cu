@@ -379,7 +379,10 @@ __device__ __forceinline__ float row_delta(const AttnParams& p, int b, int q, in
 //     written by TMA stores whose 3-D maps clip the rows past the sequence.  Its elected lane joins bar_pd once the
 //     dS store has read the tile, so nobody overwrites it early.
 constexpr int BWD_THREADS = 384;
-constexpr int NB_CONSUMED = 1, NB_STORED = 2, NB_FINAL = 3;  // named barriers (0 = __syncthreads)
+// named barriers (0 = __syncthreads): every one has a single arriving site (compute warps, bar.arrive) and a single waiting
+// site (one issue warp, bar.sync), 256 + 32 threads — the MMA warp and the store warp wait on separate barriers
+constexpr int NB_CONSUMED = 1, NB_STORED_MMA = 2, NB_FINAL_MMA = 3, NB_STORED_ST = 4, NB_FINAL_ST = 5;
+constexpr int NB_COUNT = 256 + 32;
 
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -466,6 +469,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int k = 0; k < 4; ++k)
           if (elect_one()) umma_bf16(tmem + TM_DP, ddo + 2 * k, dv_ + 2 * k, idesc, k != 0);
         if (elect_one()) umma_commit(bar_s);
+        __syncwarp();  // the named barriers below are warp-aligned instructions: reconverge after the elected lane's work
       };
       mbar_wait(bar_ld, 0);
       tc_fence_after();
@@ -473,7 +477,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int t = 0; t < ntile; ++t) {
         const int kb = nqb == 2 ? (t >> 1) : t, qb = nqb == 2 ? (t & 1) : 0;
         const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
-        named_sync(NB_CONSUMED, 256 + 32);  // every compute thread has read S / dP of tile t out of TMEM
+        named_sync(NB_CONSUMED, NB_COUNT);  // every compute thread has read S / dP of tile t out of TMEM
         tc_fence_after();
         if (t + 1 < ntile) {
           const int kbn = nqb == 2 ? ((t + 1) >> 1) : t + 1, qbn = nqb == 2 ? ((t + 1) & 1) : 0;
@@ -482,7 +486,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           issue_scores(kbn, qbn);
         }
         AT_TRACE(46 + (t & 1) * 4);
-        named_sync(NB_STORED, 256 + 64);  // P / dS of tile t are in shared memory (fenced for the async proxy)
+        named_sync(NB_STORED_MMA, NB_COUNT);  // P / dS of tile t are in shared memory (fenced for the async proxy)
         tc_fence_after();
         AT_TRACE(47 + (t & 1) * 4);
         const uint32_t ads = sbase + BWD_SDS, ap = sbase + BWD_SP;
@@ -510,7 +514,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         AT_TRACE(48 + (t & 1) * 4);
       }
-      named_sync(NB_FINAL, 256 + 64);  // every accumulator has been read out of TMEM
+      named_sync(NB_FINAL_MMA, NB_COUNT);  // every accumulator has been read out of TMEM
       tc_fence_after();
       tmem_dealloc(tmem, 512);
     } else if (warp_u == 9) {
@@ -519,7 +523,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int t = 0; t < ntile; ++t) {
         const int kb = nqb == 2 ? (t >> 1) : t, qb = nqb == 2 ? (t & 1) : 0;
         const int nkc = (min(p.Lk - kb * 128, 128) + 15) >> 4;
-        named_sync(NB_STORED, 256 + 64);  // dS of tile t (and the key block staged during its pass) are in shared memory
+        named_sync(NB_STORED_ST, NB_COUNT);  // dS of tile t (and the key block staged during its pass) are in shared memory
         if (lead) {
           if (drain_kb >= 0) {
             tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
@@ -538,7 +542,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         drain_kb = (qb == nqb - 1) ? kb : -1;
       }
-      named_sync(NB_FINAL, 256 + 64);  // last key block's dK / dV and dQ are staged in the K / V / Q tiles
+      named_sync(NB_FINAL_ST, NB_COUNT);  // last key block's dK / dV and dQ are staged in the K / V / Q tiles
       if (lead) {
         tma_store_3d(&tmap_dk, sbase + BWD_SK + drain_kb * 16384, h * 64, drain_kb * 128, b);
         tma_store_3d(&tmap_dv, sbase + BWD_SV + drain_kb * 16384, h * 64, drain_kb * 128, b);
@@ -672,7 +676,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     tc_fence_before();
-    named_arrive(NB_CONSUMED, 256 + 32);  // S / dP may be overwritten by the next tile's
+    named_arrive(NB_CONSUMED, NB_COUNT);  // S / dP may be overwritten by the next tile's
     AT_TRACE(5 + t * 6);
 
     // the next tile's first bias block: requested now, consumed after the wait for its S / dP
@@ -715,7 +719,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    named_arrive(NB_STORED, 256 + 64);
+    named_arrive(NB_STORED_MMA, NB_COUNT);
+    named_arrive(NB_STORED_ST, NB_COUNT);
     AT_TRACE(6 + t * 6);
     drain_kb = (qb == nqb - 1) ? kb : -1;
     g = gn;
@@ -732,7 +737,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   AT_TRACE(41);
   fence_proxy_async_smem();
   tc_fence_before();
-  named_arrive(NB_FINAL, 256 + 64);
+  named_arrive(NB_FINAL_MMA, NB_COUNT);
+  named_arrive(NB_FINAL_ST, NB_COUNT);
   AT_TRACE(60);
 }
 

@@ -1,3 +1,4 @@
+"""Pinned host<->device copy bandwidth and host fp32->bf16 conversion time at the step's batch size (developer tool)."""
 import torch, time
 dev = torch.device("cuda:0")
 for mb in (8, 54, 256):

@@ -402,9 +402,18 @@ def test_relpos_gather_scatter(dev):
     ops.relpos_bias_gather(table, index, N, H, out)
     ref = table[index.view(-1)].view(N, N, H).permute(2, 0, 1)
     assert torch.equal(out[:, :, :N], ref) and out[:, :, N:].abs().max() == 0
-    ds = _bf(torch.randn(4, H, N, 224, device=dev, generator=g))
+    for nb in (4, 5):  # the vectorised kernel walks the batch four at a time + a tail
+        ds = _bf(torch.randn(nb, H, N, 224, device=dev, generator=g))
+        ds[..., 208:] = float("nan")  # columns past pad16(N) are never written by the attention kernel, never read here
+        dt = torch.zeros(R, H, device=dev)
+        ops.relpos_bias_scatter(ds, nb, H, N, index, dt)
+        want = torch.zeros(R, H, device=dev).index_add_(0, index.view(-1),
+                                                        ds.float().sum(0)[:, :, :N].permute(1, 2, 0).reshape(N * N, H))
+        assert (dt - want).abs().max() < 1e-3 * want.abs().max()
+    # unaligned view (row stride not a multiple of 8): scalar fallback
+    ds = _bf(torch.randn(3, H, N, 203, device=dev, generator=g))
     dt = torch.zeros(R, H, device=dev)
-    ops.relpos_bias_scatter(ds, 4, H, N, index, dt)
+    ops.relpos_bias_scatter(ds, 3, H, N, index, dt)
     want = torch.zeros(R, H, device=dev).index_add_(0, index.view(-1), ds.float().sum(0)[:, :, :N].permute(1, 2, 0).reshape(N * N, H))
     assert (dt - want).abs().max() < 1e-3 * want.abs().max()
 

@@ -2,6 +2,8 @@
 
 The reference ships no tests/golden vectors, so its own execution is the pin.
 These tests only run where /root/reference exists (build container)."""
+import os
+
 import pytest
 import torch
 
@@ -262,3 +264,49 @@ def test_beit_drop_path_two_independent_draws(ref):
     with torch.no_grad():
         y, _ = restate.beit_block(x, sd, "vision_encoder.blocks.7.", 12, dp1, dp2)
     assert torch.allclose(y, y_ref, atol=1e-5, rtol=1e-5)
+
+
+def _itc_worker(rank, world, port, q):
+    """One rank of the ITC loss under data parallelism: ONE packed all-gather (pretrain.allgather_packed, what the mixed
+    step does) against the reference's own XVLMBase.get_contrastive_loss with its two all-gathers per loss."""
+    import types
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ref_shim.install()
+        import models.xvlm as ref_xvlm
+        from x2vlm_b200 import pretrain
+        g = torch.Generator().manual_seed(50 + rank)
+        D = 8
+        feats = [torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=-1).requires_grad_(True) for n in (4, 4, 3, 3)]
+        stub = types.SimpleNamespace(temp=torch.tensor(0.07), embed_dim=D)
+        # ours: one collective for the four matrices, then the two losses
+        gathered = pretrain.allgather_packed(feats)
+        ours = (pretrain.XVLM.get_contrastive_loss(stub, feats[0], feats[1], gathered=(gathered[0], gathered[1]))
+                + pretrain.XVLM.get_contrastive_loss(stub, feats[2], feats[3], gathered=(gathered[2], gathered[3])))
+        g_ours = torch.autograd.grad(ours, feats)
+        # the reference's method (models/xvlm.py:794-826), unmodified, on the same per-rank features
+        ref = (ref_xvlm.XVLMBase.get_contrastive_loss(stub, feats[0], feats[1])
+               + ref_xvlm.XVLMBase.get_contrastive_loss(stub, feats[2], feats[3]))
+        g_ref = torch.autograd.grad(ref, feats)
+        ok = torch.allclose(ours, ref, atol=1e-6) and all(torch.allclose(a, b, atol=1e-6) for a, b in zip(g_ours, g_ref))
+        # rank-major layout of the gathered matrices: rows [r * B, (r + 1) * B) hold rank r's features
+        mine = gathered[2][rank * 3:(rank + 1) * 3]
+        ok = ok and torch.equal(mine, feats[2].detach())
+        q.put((rank, bool(ok), float(ours), float(ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_itc_packed_allgather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_itc_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in procs]
+    [p.join(30) for p in procs]
+    assert all(ok for _, ok, _, _ in res), res
+    assert abs(res[0][2] - res[1][2]) < 1e-6  # the loss is a function of the gathered batch: identical on both ranks

@@ -67,6 +67,21 @@ def allgather(t):
     return t
 
 
+def allgather_packed(feats):
+    """ONE all-gather for several [B_k, D] feature matrices of a step (the ITC features of the image and the region
+    sub-batch): returns the gathered [W * B_k, D] matrices, rank-major exactly as one `allgather` per matrix gives them
+    (models/xvlm.py:804-805); the backward keeps the local slices (`AllGather`)."""
+    W = dist.get_world_size()
+    packed = torch.cat(feats, dim=0)
+    allp = allgather(packed).view(W, packed.shape[0], -1)
+    out, o = [], 0
+    for f in feats:
+        n = f.shape[0]
+        out.append(allp[:, o:o + n].reshape(W * n, -1))
+        o += n
+    return out
+
+
 def build_mlp(input_dim, output_dim):
     return nn.Sequential(nn.Linear(input_dim, input_dim * 2), nn.LayerNorm(input_dim * 2), nn.GELU(),
                          nn.Linear(input_dim * 2, output_dim))
@@ -376,12 +391,10 @@ class XVLM(nn.Module):
         # ONE all-gather for the (up to) four ITC feature matrices of the step instead of one per matrix
         g_i = g_r = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            W = dist.get_world_size()
-            packed = torch.cat([fi_i, ft_i] + ([fi_r, ft_r] if has_r else []), dim=0)
-            allp = allgather(packed).view(W, packed.shape[0], -1)
-            g_i = (allp[:, :Bi].reshape(W * Bi, -1), allp[:, Bi:2 * Bi].reshape(W * Bi, -1))
+            g = allgather_packed([fi_i, ft_i] + ([fi_r, ft_r] if has_r else []))
+            g_i = (g[0], g[1])
             if has_r:
-                g_r = (allp[:, 2 * Bi:2 * Bi + Br].reshape(W * Br, -1), allp[:, 2 * Bi + Br:].reshape(W * Br, -1))
+                g_r = (g[2], g[3])
         losses["image"]["loss_itc"] = self.get_contrastive_loss(fi_i, ft_i, gathered=g_i)
         ineg_i, tneg_i = neg_idx_i if neg_idx_i is not None else self.get_hard_negatives(fi_i, ft_i)
         if has_r:

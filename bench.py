@@ -25,9 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic FLOPs (fwd+bwd, 2 FLOP / MAC) of the reference algorithm, SURVEY.md §8d
-# average DRAM bytes per GEMM launch of the step (dram__bytes_read.sum + dram__bytes_write.sum over the 422 tcgen05 GEMM
-# launches of profiles/r01_launches_step.md), from the committed ncu capture — not re-measured at bench time
-ROOFLINE_TRAFFIC = 124.37e6
+# average DRAM bytes per GEMM launch of the step (dram__bytes_read.sum + dram__bytes_write.sum over the 423 tcgen05 GEMM
+# launches of profiles/r02_final_launches_step.md; round 1: 124.37 MB over 422), from the committed ncu capture — not
+# re-measured at bench time
+ROOFLINE_TRAFFIC = 121.32e6
 FLOP_IMAGE_PAIR = 231.4e9            # image iteration, per pair
 FLOP_REGION_SAMPLE = 3 * 48.92e9     # region iteration, per region-text sample (text x2, fusion x5, head)
 FLOP_VISION_IMAGE = 3 * 35.13e9      # + vision once per unique region image

@@ -416,3 +416,24 @@ def test_arena_gapped_beit_bias(xvlm):
     sq, eq = arena.span(blk.attn.q_bias)
     sv, ev = arena.span(blk.attn.v_bias)
     assert sv == eq + 768 and sq % 8 == 0
+
+
+def test_gather_rows_backward_matches_slicing():
+    """pretrain._gather_rows (one gather of every row the loss heads read from the fusion output): same values and the
+    same input gradient as the slices / torch.gather it replaced, including repeated rows (padded masked positions)."""
+    from x2vlm_b200 import pretrain
+    torch.manual_seed(0)
+    S, L, D = 6, 5, 4
+    x = torch.randn(S, L, D, requires_grad=True)
+    pos = torch.tensor([[1, 3, 0], [2, 2, 4]])              # masked positions of sequences 4 and 5 (a repeat on purpose)
+    cls_seq = torch.tensor([0, 1, 2, 3])
+    idx = torch.cat([cls_seq * L, ((4 + torch.arange(2)) * L).unsqueeze(1).add(pos).reshape(-1)])
+    rows = pretrain._gather_rows(x, idx)
+    w = torch.randn_like(rows)
+    (rows * w).sum().backward()
+    got = x.grad.clone()
+    x.grad = None
+    ref_rows = torch.cat([x[:4, 0], torch.gather(x[4:], 1, pos.unsqueeze(2).expand(-1, -1, D)).reshape(-1, D)])
+    assert torch.equal(rows, ref_rows)
+    (ref_rows * w).sum().backward()
+    assert torch.allclose(got, x.grad, atol=1e-6)
